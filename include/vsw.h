@@ -1,0 +1,218 @@
+/* vsw.h -- C ABI of libvsw_b200.so: hand-written sm_100a kernels for the Video-Swin 3D hot path
+ * of tsujuifu/pytorch_empirical-mvm (reference: visbackbone/video_swin.py; citations below are
+ * file:line relative to the reference tree).
+ *
+ * The reference has no FFI layer: its "operator interface" for this path is the set of torch ops
+ * inside visbackbone/video_swin.py.  Every entry point below replaces one group of those ops and is
+ * what a binding for this path has to bind (INTEGRATION.md shows the ctypes stub).
+ *
+ * Conventions (SURVEY.md section 8b "Lower"):
+ *   - plain C symbols, raw device pointers + sizes, no torch types;
+ *   - return 0 (VSW_OK) or a negative vsw_status; never throws, never aborts; the message of the
+ *     last failure on the calling thread is available through vsw_last_error();
+ *   - the CALLER owns every buffer (including workspaces), the library never allocates device
+ *     memory, never synchronises and never changes the current device;
+ *   - every launch goes to the caller's stream (a cudaStream_t passed as void*);
+ *   - re-entrant, callable from any host thread (autograd engine thread included);
+ *   - deterministic: no floating-point atomics, fixed reduction orders.
+ *   - "dtype" is the storage type of activations/weights (vsw_dtype); arithmetic is always fp32
+ *     (or bf16 x bf16 -> fp32 on the tensor cores for VSW_BF16 GEMM/attention tiles);
+ *     statistics (mean/rstd/lse) and index maps are fp32 / int32 / uint8 regardless of dtype.
+ *
+ * Token layout: channels-last.  An activation is (B, T, C) with T = D*H*W tokens in row-major
+ * (d,h,w) order; a windowed activation is (B, nW*N, C) with windows row-major over
+ * (Dp/wd, Hp/wh, Wp/ww) and slots row-major over (wd, wh, ww)  [video_swin.py:84-88].
+ */
+#ifndef VSW_H_
+#define VSW_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#if defined(__GNUC__)
+#pragma GCC visibility push(default)
+#endif
+
+typedef enum { VSW_F32 = 0, VSW_BF16 = 1, VSW_F16 = 2 } vsw_dtype;
+
+typedef enum {
+    VSW_OK = 0,
+    VSW_ERR_ARG = -1,      /* bad shape / null pointer / misaligned pointer */
+    VSW_ERR_DTYPE = -2,    /* dtype not supported by this entry point */
+    VSW_ERR_UNSUPPORTED = -3, /* geometry not supported by this kernel (caller must not fall back silently) */
+    VSW_ERR_CUDA = -4,     /* a CUDA runtime/driver call failed */
+    VSW_ERR_WORKSPACE = -5 /* workspace too small */
+} vsw_status;
+
+/* epilogues of vsw_linear_fwd */
+typedef enum {
+    VSW_EPI_BIAS = 0,       /* y = acc + bias                                        (qkv, fc-like)          */
+    VSW_EPI_GELU = 1,       /* y = gelu_erf(acc + bias); optional pre-activation out  [video_swin.py:76-77]   */
+    VSW_EPI_RESIDUAL = 2    /* y[dst] = res[dst] + rowscale[b] * (acc + bias), dst via optional row map
+                               [proj + window_reverse + roll back + residual, video_swin.py:170,233-241,256;
+                                fc2 + residual, video_swin.py:261]                                            */
+} vsw_epilogue;
+
+/* GEMM back ends (vsw_set_gemm_backend): the CUDA-core fp32 kernel is the only one for VSW_F32. */
+typedef enum { VSW_GEMM_AUTO = 0, VSW_GEMM_SIMT = 1, VSW_GEMM_TCGEN05 = 2 } vsw_gemm_backend;
+
+int vsw_version(void);
+/* copies the calling thread's last error message (NUL-terminated) into buf; returns its length */
+int vsw_last_error(char* buf, size_t n);
+/* selects the kernel family for VSW_BF16 GEMMs/attention; returns the previous value */
+int vsw_set_gemm_backend(int backend);
+int vsw_get_gemm_backend(void);
+/* number of kernel launches issued by this library since process start (bench.py's gpu_launches) */
+long long vsw_launch_count(void);
+
+/* ------------------------------------------------------------------------------------------------
+ * Index maps -- integer domain, bit-exact with the reference.
+ * ---------------------------------------------------------------------------------------------- */
+
+/* Shift + window-partition gather map and shift-mask region ids.
+ * Replaces torch.roll + window_partition (video_swin.py:84-88, 220-229) and the region counter of
+ * compute_mask (video_swin.py:294-302).
+ *   grid (D,H,W): unpadded token grid; (wd,wh,ww)/(sd,sh,sw): EFFECTIVE window/shift (after
+ *   get_window_size, video_swin.py:95-108).  Padded grid = ceil to window multiples.
+ *   gather [nW*N] int32: flat (d*H+h)*W+w index into the UNPADDED grid of the token read by window
+ *                        slot (w,n), or -1 where the slot lies in the post-norm zero padding.
+ *   region [nW*N] uint8: cnt = 9*rd + 3*rh + rw of the slot in the shifted frame.
+ * Either output pointer may be NULL. */
+int vsw_window_maps(int D, int H, int W, int wd, int wh, int ww, int sd, int sh, int sw,
+                    int32_t* gather, uint8_t* region, void* stream);
+
+/* relative_position_index buffer (N x N int64), video_swin.py:123-137 */
+int vsw_rel_pos_index(int wd, int wh, int ww, int64_t* out, void* stream);
+
+/* dense additive mask (nW,N,N) of {0,-100} from region ids, video_swin.py:303-307 */
+int vsw_shift_mask(const uint8_t* region, int nW, int N, void* out, int dtype, void* stream);
+
+/* PatchMerging gather map (video_swin.py:276-284): out [D*ceil(H/2)*ceil(W/2)*4] int32, flat token
+ * index in the (D,H,W) grid of channel group g in order (dh,dw)=(0,0),(1,0),(0,1),(1,1); -1 = pad */
+int vsw_merge_map(int D, int H, int W, int32_t* out, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * LayerNorm family (HBM-bound, vectorised, warp-shuffle).  eps = 1e-5 in the reference.
+ * ---------------------------------------------------------------------------------------------- */
+
+/* y[b,r,:] = LN(x[b, map[r], :]) * gamma + beta  for r < Tout;  map == NULL -> identity (Tout==Tin);
+ * map[r] < 0 -> y row = 0 (zero padding AFTER the norm, video_swin.py:211-217).
+ * mean/rstd [B*Tout] fp32 are written when non-NULL (needed by the backward).
+ * norm1 + pad + roll + window_partition: video_swin.py:211-229; norm2: :248; final norm: :479;
+ * patch_embed.norm: :401-405.  out_dtype may differ from dtype (final norm under autocast). */
+int vsw_ln_fwd(const void* x, const void* gamma, const void* beta, const int32_t* map,
+               void* y, float* mean, float* rstd,
+               int B, int Tin, int Tout, int C, float eps, int dtype, int out_dtype, void* stream);
+
+/* Backward of vsw_ln_fwd for the rows r < Tout:
+ *   dx[b, map[r], :] = (dres ? dres[b, map[r], :] : 0) + LN'(dy[b,r,:]) ;   rows with map[r] < 0 skipped.
+ * dy_dtype is the storage type of dy (fp32 for the final norm under autocast).
+ * dgamma/dbeta (fp32 [C]) get the column reductions sum_r dy*xhat / sum_r dy, computed through the
+ * fp32 workspace `ws` of at least vsw_ln_bwd_workspace(C) bytes (two-pass, fixed order). */
+size_t vsw_ln_bwd_workspace(int C);
+int vsw_ln_bwd(const void* dy, const void* x, const void* gamma, const float* mean, const float* rstd,
+               const int32_t* map, const void* dres, void* dx, float* dgamma, float* dbeta,
+               int B, int Tin, int Tout, int C, int dtype, int dy_dtype, void* ws, size_t ws_bytes,
+               void* stream);
+
+/* PatchMerging front half (video_swin.py:276-286): y[b,r,:] = LN_{4C}(concat_g x[b, map4[r,g], :]),
+ * map4 < 0 -> zero input (padding BEFORE the norm).  y is (B, Tout, 4C). */
+int vsw_merge_ln_fwd(const void* x, const void* gamma, const void* beta, const int32_t* map4,
+                     void* y, float* mean, float* rstd,
+                     int B, int Tin, int Tout, int C, float eps, int dtype, void* stream);
+int vsw_merge_ln_bwd(const void* dy, const void* x, const void* gamma, const float* mean, const float* rstd,
+                     const int32_t* map4, void* dx, float* dgamma, float* dbeta,
+                     int B, int Tin, int Tout, int C, int dtype, void* ws, size_t ws_bytes, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Linear layers  (nn.Linear convention: w is (N, K) row-major, y = x w^T + bias).
+ * ---------------------------------------------------------------------------------------------- */
+
+/* y = epilogue(x[M,K] w[N,K]^T + bias[N]).
+ *   VSW_EPI_GELU:     aux_out (M,N) receives the pre-activation when non-NULL.
+ *   VSW_EPI_RESIDUAL: rows are grouped in batches of rows_per_batch; source row m = b*rows_per_batch + r
+ *                     is written to destination row b*dst_rows_per_batch + (rowmap ? rowmap[r] : r),
+ *                     skipped when rowmap[r] < 0;  y[dst] = res[dst] + (rowscale ? rowscale[b] : 1) * (acc+bias).
+ *                     rowscale[b] is the drop-path factor floor(keep+U)/keep (video_swin.py:46-54). */
+int vsw_linear_fwd(const void* x, const void* w, const void* bias, void* y,
+                   int M, int N, int K, int epilogue,
+                   void* aux_out, const void* res, const int32_t* rowmap, const float* rowscale,
+                   int rows_per_batch, int dst_rows_per_batch,
+                   int dtype, void* stream);
+
+/* dx[M,K] = A w[N,K]   where A[m,:] = a_scale * dy[src(m), :] (*) gelu'(pre[m,:]) :
+ *   a_rowmap (optional): A row m = b*rows_per_batch + r reads dy row b*src_rows_per_batch + a_rowmap[r]
+ *                        (zero row if < 0)  -- the transpose of the RESIDUAL scatter epilogue;
+ *   a_rowscale (optional): per-batch factor (drop-path);
+ * gelu_pre (optional, (M,K)): dx = (dy w) (*) gelu'(gelu_pre)   -- fc2 backward fused with the GELU backward.
+ * When a_rowmap/a_rowscale are given and a_out != NULL the gathered+scaled A is also written to a_out (M,N)
+ * so that the weight-gradient GEMM can consume it. */
+int vsw_linear_dgrad(const void* dy, const void* w, void* dx,
+                     int M, int N, int K,
+                     const int32_t* a_rowmap, const float* a_rowscale, int rows_per_batch, int src_rows_per_batch,
+                     void* a_out, const void* gelu_pre,
+                     int dtype, void* stream);
+
+/* dw[N,K] = dy[M,N]^T x[M,K]; db[N] = sum_m dy[m,:] (db may be NULL).  Split over M with an fp32
+ * workspace (vsw_linear_wgrad_workspace bytes) and a fixed-order second pass.  dw/db are written in
+ * grad_dtype (VSW_F32 for fp32 master parameters under autocast). */
+size_t vsw_linear_wgrad_workspace(int M, int N, int K);
+int vsw_linear_wgrad(const void* dy, const void* x, void* dw, void* db,
+                     int M, int N, int K, int dtype, int grad_dtype,
+                     void* ws, size_t ws_bytes, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Fused window attention (video_swin.py:149-169): softmax(q*scale k^T + bias + mask) v, per
+ * (window, head); scores never touch HBM.
+ *   qkv  (B_, N, 3, nH, hd)   B_ = B*nW, windows of one clip contiguous, batch slowest
+ *   out  (B_, N, nH*hd)
+ *   lse  (B_, nH, N) fp32 log-sum-exp of the biased+masked scores (saved for the backward)
+ *   bias_table (L, nH) in dtype; bias[h,i,j] = bias_table[rowcode[i] + colcode[j], h] where
+ *       rowcode[i] = index[i,0], colcode[j] = index[0,j] - index[0,0] (exact because
+ *       relative_position_index is translation invariant; includes the [:N,:N] slice quirk, :155)
+ *   region (nW, N) uint8 or NULL: additive mask -100 where region[w,i] != region[w,j] (video_swin.py:303-307)
+ *   dense_mask (nW,N,N) in dtype or NULL: arbitrary additive mask (used instead of region when given)
+ * ---------------------------------------------------------------------------------------------- */
+int vsw_window_attn_fwd(const void* qkv, const void* bias_table, const int32_t* rowcode, const int32_t* colcode,
+                        const uint8_t* region, const void* dense_mask,
+                        void* out, float* lse,
+                        int B_, int nW, int N, int nH, int hd, int L, float scale,
+                        int dtype, void* stream);
+
+/* Recompute-based backward.  dqkv (B_,N,3,nH,hd); dbias_table (L,nH) fp32, OVERWRITTEN
+ * with the reduction over batch and windows, via workspace partials (fixed order). */
+size_t vsw_window_attn_bwd_workspace(int B_, int N, int nH, int hd, int L);
+int vsw_window_attn_bwd(const void* qkv, const void* out, const void* dout, const float* lse,
+                        const void* bias_table, const int32_t* rowcode, const int32_t* colcode,
+                        const uint8_t* region, const void* dense_mask,
+                        void* dqkv, float* dbias_table,
+                        int B_, int nW, int N, int nH, int hd, int L, float scale,
+                        int dtype, void* ws, size_t ws_bytes, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * PatchEmbed3D (video_swin.py:390-400): zero-pad H,W up to patch multiples, append one zero frame,
+ * Conv3d(k=(pd,ph,pw), stride=(1,ph,pw)).  The convolution is run as  im2col -> vsw_linear_fwd
+ * (K = Cin*pd*ph*pw = 96), so forward, weight gradient and input gradient all go through the GEMM
+ * family above; the patch_norm LayerNorm is a vsw_ln_fwd on the result.
+ *   x   (B,Cin,D,H,W) in x_dtype (fp32 clips are converted on load)
+ *   col (B*Dout*Hp*Wp, Cin*pd*ph*pw) in dtype, column order (c,dt,dy,dx) = Conv3d weight order,
+ *       Dout = D + 2 - pd, Hp = ceil(H/ph), Wp = ceil(W/pw); rows are tokens in (b,d,h',w') order.
+ * ---------------------------------------------------------------------------------------------- */
+int vsw_patch_im2col(const void* x, void* col, int B, int Cin, int D, int H, int W, int pd, int ph, int pw,
+                     int x_dtype, int dtype, void* stream);
+/* transpose of vsw_patch_im2col: dx (B,Cin,D,H,W) in x_dtype = sum of the <= pd column entries per element */
+int vsw_patch_col2im(const void* dcol, void* dx, int B, int Cin, int D, int H, int W, int pd, int ph, int pw,
+                     int x_dtype, int dtype, void* stream);
+
+#if defined(__GNUC__)
+#pragma GCC visibility pop
+#endif
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* VSW_H_ */

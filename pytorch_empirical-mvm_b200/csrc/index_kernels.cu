@@ -1,0 +1,94 @@
+// Integer index maps of the shifted-window machinery.  Bit-exact with the reference
+// (visbackbone/video_swin.py:84-93 window_partition/reverse, :220-241 roll, :292-307 compute_mask,
+//  :123-137 relative_position_index, :276-284 PatchMerging slicing).  Closed forms: SURVEY Appendix A.
+#include "common.cuh"
+#include "geometry.cuh"
+
+namespace vsw {
+
+__global__ void window_maps_kernel(WinGeom g, int32_t* __restrict__ gather, uint8_t* __restrict__ region) {
+    const int total = g.nW * g.N;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+        const int w = i / g.N, n = i - w * g.N;
+        if (gather) gather[i] = g.source_token(w, n);
+        if (region) region[i] = (uint8_t)g.region_id(w, n);
+    }
+}
+
+__global__ void rel_pos_index_kernel(int wd, int wh, int ww, int64_t* __restrict__ out) {
+    const int N = wd * wh * ww;
+    const long long total = (long long)N * N;
+    for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < total;
+         t += (long long)gridDim.x * blockDim.x) {
+        const int i = (int)(t / N), j = (int)(t - (long long)i * N);
+        const int di = i / (wh * ww), hi = (i / ww) % wh, wi = i % ww;
+        const int dj = j / (wh * ww), hj = (j / ww) % wh, wj = j % ww;
+        out[t] = (long long)(di - dj + wd - 1) * (2 * wh - 1) * (2 * ww - 1) +
+                 (long long)(hi - hj + wh - 1) * (2 * ww - 1) + (wi - wj + ww - 1);
+    }
+}
+
+template <typename T>
+__global__ void shift_mask_kernel(const uint8_t* __restrict__ region, int nW, int N, T* __restrict__ out) {
+    const long long total = (long long)nW * N * N;
+    for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < total;
+         t += (long long)gridDim.x * blockDim.x) {
+        const int j = (int)(t % N);
+        const long long wi = t / N;           // w*N + i
+        const int w = (int)(wi / N);
+        const uint8_t ri = region[wi], rj = region[(long long)w * N + j];
+        out[t] = from_f<T>(ri != rj ? -100.0f : 0.0f);
+    }
+}
+
+__global__ void merge_map_kernel(int D, int H, int W, int32_t* __restrict__ out) {
+    const int H2 = (H + 1) / 2, W2 = (W + 1) / 2;
+    const int total = D * H2 * W2 * 4;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+        const int g = i & 3, r = i >> 2;
+        const int w2 = r % W2, h2 = (r / W2) % H2, d = r / (W2 * H2);
+        const int h = 2 * h2 + (g & 1), w = 2 * w2 + (g >> 1);  // g: (dh,dw) = (0,0),(1,0),(0,1),(1,1)
+        out[i] = (h < H && w < W) ? (d * H + h) * W + w : -1;
+    }
+}
+
+}  // namespace vsw
+
+using namespace vsw;
+
+extern "C" int vsw_window_maps(int D, int H, int W, int wd, int wh, int ww, int sd, int sh, int sw,
+                               int32_t* gather, uint8_t* region, void* stream) {
+    WinGeom g;
+    VSW_REQUIRE(make_win_geom(D, H, W, wd, wh, ww, sd, sh, sw, &g), VSW_ERR_ARG,
+                "vsw_window_maps: bad geometry grid(%d,%d,%d) window(%d,%d,%d) shift(%d,%d,%d)", D, H, W, wd, wh, ww,
+                sd, sh, sw);
+    const int total = g.nW * g.N;
+    window_maps_kernel<<<ceil_div(total, 256), 256, 0, (cudaStream_t)stream>>>(g, gather, region);
+    return check_launch("vsw_window_maps");
+}
+
+extern "C" int vsw_rel_pos_index(int wd, int wh, int ww, int64_t* out, void* stream) {
+    VSW_REQUIRE(wd > 0 && wh > 0 && ww > 0 && out, VSW_ERR_ARG, "vsw_rel_pos_index: bad args");
+    const long long total = (long long)wd * wh * ww * wd * wh * ww;
+    int blocks = (int)((total + 255) / 256);
+    if (blocks > kNumSMs * 16) blocks = kNumSMs * 16;
+    rel_pos_index_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(wd, wh, ww, out);
+    return check_launch("vsw_rel_pos_index");
+}
+
+extern "C" int vsw_shift_mask(const uint8_t* region, int nW, int N, void* out, int dtype, void* stream) {
+    VSW_REQUIRE(region && out && nW > 0 && N > 0, VSW_ERR_ARG, "vsw_shift_mask: bad args");
+    const long long total = (long long)nW * N * N;
+    int blocks = (int)((total + 255) / 256);
+    if (blocks > kNumSMs * 16) blocks = kNumSMs * 16;
+    VSW_DISPATCH_DTYPE(dtype, T,
+                       (shift_mask_kernel<T><<<blocks, 256, 0, (cudaStream_t)stream>>>(region, nW, N, (T*)out)));
+    return check_launch("vsw_shift_mask");
+}
+
+extern "C" int vsw_merge_map(int D, int H, int W, int32_t* out, void* stream) {
+    VSW_REQUIRE(D > 0 && H > 0 && W > 0 && out, VSW_ERR_ARG, "vsw_merge_map: bad args");
+    const int total = D * ((H + 1) / 2) * ((W + 1) / 2) * 4;
+    merge_map_kernel<<<ceil_div(total, 256), 256, 0, (cudaStream_t)stream>>>(D, H, W, out);
+    return check_launch("vsw_merge_map");
+}

@@ -1,0 +1,456 @@
+// LayerNorm family: HBM-bound kernels, 16-byte vector loads, sub-warp shuffle reductions.
+//   vsw_ln_fwd / vsw_ln_bwd          norm1 (+pad+roll+window_partition gather), norm2, final norm, patch norm
+//   vsw_merge_ln_fwd / _bwd          PatchMerging 2x2 gather + LN(4C)
+// Reference: visbackbone/video_swin.py:211-229, 248, 273-286, 401-405, 479.
+// One row is owned by a group of LANES (<=32) lanes; each lane keeps VPL 16-byte vectors of the row
+// in registers, so x is read exactly once.  Column reductions (dgamma/dbeta) run as a separate
+// fixed-order two-pass column kernel (deterministic, no atomics).
+#include "common.cuh"
+
+namespace vsw {
+
+template <int LANES>
+__device__ __forceinline__ float group_sum(float v) {
+#pragma unroll
+    for (int o = LANES / 2; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+// ------------------------------------------------------------------------------------------
+// forward.  GROUPS = number of concatenated source rows per output row (1 = plain/gather LN,
+// 4 = PatchMerging).  For GROUPS==1 a negative map entry zeroes the OUTPUT row (post-norm pad);
+// for GROUPS==4 it zeroes that INPUT group (pre-norm pad).
+// ------------------------------------------------------------------------------------------
+template <typename T, typename TO, int LANES, int VPL, int GROUPS>
+__global__ void __launch_bounds__(256) ln_fwd_kernel(const T* __restrict__ x, const T* __restrict__ gamma,
+                                                     const T* __restrict__ beta, const int32_t* __restrict__ map,
+                                                     TO* __restrict__ y, float* __restrict__ mean_out,
+                                                     float* __restrict__ rstd_out, int B, int Tin, int Tout, int C,
+                                                     float eps) {
+    constexpr int VN = Vec16<T>::N;
+    constexpr int RPW = 32 / LANES;  // rows per warp
+    const int Cw = C * GROUPS;       // normalised width
+    const int nvec = Cw / VN;
+    const int vec_per_group = C / VN;
+    const int lane = threadIdx.x & 31, sub = lane / LANES, l = lane % LANES;
+    const long long nrows = (long long)B * Tout;
+    const long long warp_global = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const long long warp_stride = (long long)gridDim.x * (blockDim.x >> 5);
+    const float inv_c = 1.0f / (float)Cw;
+
+    for (long long row0 = warp_global * RPW; row0 < nrows; row0 += warp_stride * RPW) {
+        const long long row = row0 + sub;
+        const bool row_ok = row < nrows;
+        const int b = row_ok ? (int)(row / Tout) : 0;
+        const int r = row_ok ? (int)(row - (long long)b * Tout) : 0;
+        int src1 = r;
+        if (GROUPS == 1 && map) src1 = map[r];
+        float v[VPL][VN];
+        float s = 0.f;
+#pragma unroll
+        for (int k = 0; k < VPL; ++k) {
+            const int vi = l + k * LANES;
+#pragma unroll
+            for (int e = 0; e < VN; ++e) v[k][e] = 0.f;
+            if (row_ok && vi < nvec) {
+                int src = src1, col = vi * VN;
+                if (GROUPS > 1) {
+                    const int g = vi / vec_per_group;
+                    src = map[(long long)r * GROUPS + g];
+                    col = (vi - g * vec_per_group) * VN;
+                }
+                if (src >= 0) load_vec<T>(x + ((long long)b * Tin + src) * C + col, v[k]);
+            }
+#pragma unroll
+            for (int e = 0; e < VN; ++e) s += v[k][e];
+        }
+        const float mu = group_sum<LANES>(s) * inv_c;
+        float q = 0.f;
+#pragma unroll
+        for (int k = 0; k < VPL; ++k) {
+            const int vi = l + k * LANES;
+            if (vi < nvec) {
+#pragma unroll
+                for (int e = 0; e < VN; ++e) { const float d = v[k][e] - mu; q += d * d; }
+            }
+        }
+        const float rs = rsqrtf(group_sum<LANES>(q) * inv_c + eps);
+        const bool zero_row = (GROUPS == 1) && (src1 < 0);
+        if (row_ok) {
+#pragma unroll
+            for (int k = 0; k < VPL; ++k) {
+                const int vi = l + k * LANES;
+                if (vi < nvec) {
+                    float gmm[VN], bt[VN], o[VN];
+                    load_vec<T>(gamma + vi * VN, gmm);
+                    load_vec<T>(beta + vi * VN, bt);
+#pragma unroll
+                    for (int e = 0; e < VN; ++e) o[e] = zero_row ? 0.f : (v[k][e] - mu) * rs * gmm[e] + bt[e];
+                    // TO may be wider than T (fp32 output of a bf16 row): store element groups of TO's vector width
+                    constexpr int VO = Vec16<TO>::N;
+                    if constexpr (VO == VN) {
+                        store_vec<TO>(y + row * Cw + vi * VN, o);
+                    } else {
+#pragma unroll
+                        for (int h = 0; h < VN / VO; ++h) {
+                            float oo[VO];
+#pragma unroll
+                            for (int e = 0; e < VO; ++e) oo[e] = o[h * VO + e];
+                            store_vec<TO>(y + row * Cw + vi * VN + h * VO, oo);
+                        }
+                    }
+                }
+            }
+            if (l == 0 && mean_out) {
+                mean_out[row] = zero_row ? 0.f : mu;
+                rstd_out[row] = zero_row ? 0.f : rs;
+            }
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// backward (row part): dx = dres + rstd * (g - mean(g) - xhat * mean(g*xhat)),  g = dy*gamma
+// ------------------------------------------------------------------------------------------
+template <typename T, typename TDY, int LANES, int VPL, int GROUPS>
+__global__ void __launch_bounds__(256) ln_bwd_kernel(const TDY* __restrict__ dy, const T* __restrict__ x,
+                                                     const T* __restrict__ gamma, const float* __restrict__ mean,
+                                                     const float* __restrict__ rstd, const int32_t* __restrict__ map,
+                                                     const T* __restrict__ dres, T* __restrict__ dx, int B, int Tin,
+                                                     int Tout, int C) {
+    constexpr int VN = Vec16<T>::N;
+    constexpr int RPW = 32 / LANES;
+    const int Cw = C * GROUPS;
+    const int nvec = Cw / VN;
+    const int vec_per_group = C / VN;
+    const int lane = threadIdx.x & 31, sub = lane / LANES, l = lane % LANES;
+    const long long nrows = (long long)B * Tout;
+    const long long warp_global = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const long long warp_stride = (long long)gridDim.x * (blockDim.x >> 5);
+    const float inv_c = 1.0f / (float)Cw;
+
+    for (long long row0 = warp_global * RPW; row0 < nrows; row0 += warp_stride * RPW) {
+        const long long row = row0 + sub;
+        const bool row_ok = row < nrows;
+        const int b = row_ok ? (int)(row / Tout) : 0;
+        const int r = row_ok ? (int)(row - (long long)b * Tout) : 0;
+        int src1 = r;
+        if (GROUPS == 1 && map) src1 = map[r];
+        const float mu = row_ok ? mean[row] : 0.f, rs = row_ok ? rstd[row] : 0.f;
+        float xh[VPL][VN], g[VPL][VN];
+        long long off[VPL];
+        float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+        for (int k = 0; k < VPL; ++k) {
+            const int vi = l + k * LANES;
+            off[k] = -1;
+#pragma unroll
+            for (int e = 0; e < VN; ++e) { xh[k][e] = 0.f; g[k][e] = 0.f; }
+            if (row_ok && vi < nvec) {
+                int src = src1, col = vi * VN;
+                if (GROUPS > 1) {
+                    const int gi = vi / vec_per_group;
+                    src = map[(long long)r * GROUPS + gi];
+                    col = (vi - gi * vec_per_group) * VN;
+                }
+                float gm[VN], d[VN];
+                load_vec<T>(gamma + vi * VN, gm);
+                // dy row (width Cw) in TDY
+                {
+                    constexpr int VD = Vec16<TDY>::N;
+                    if constexpr (VD == VN) {
+                        load_vec<TDY>(dy + row * Cw + vi * VN, d);
+                    } else {
+#pragma unroll
+                        for (int h = 0; h < VN / VD; ++h) {
+                            float dd[VD];
+                            load_vec<TDY>(dy + row * Cw + vi * VN + h * VD, dd);
+#pragma unroll
+                            for (int e = 0; e < VD; ++e) d[h * VD + e] = dd[e];
+                        }
+                    }
+                }
+                if (src >= 0) {
+                    off[k] = ((long long)b * Tin + src) * C + col;
+                    float xv[VN];
+                    load_vec<T>(x + off[k], xv);
+#pragma unroll
+                    for (int e = 0; e < VN; ++e) xh[k][e] = (xv[e] - mu) * rs;
+                } else if (GROUPS > 1) {
+                    // padded INPUT group: x = 0 took part in the statistics
+#pragma unroll
+                    for (int e = 0; e < VN; ++e) xh[k][e] = (0.f - mu) * rs;
+                }
+#pragma unroll
+                for (int e = 0; e < VN; ++e) {
+                    g[k][e] = d[e] * gm[e];
+                    s1 += g[k][e];
+                    s2 += g[k][e] * xh[k][e];
+                }
+            }
+        }
+        const float c1 = group_sum<LANES>(s1) * inv_c;
+        const float c2 = group_sum<LANES>(s2) * inv_c;
+#pragma unroll
+        for (int k = 0; k < VPL; ++k) {
+            if (off[k] >= 0) {
+                float o[VN];
+#pragma unroll
+                for (int e = 0; e < VN; ++e) o[e] = rs * (g[k][e] - c1 - xh[k][e] * c2);
+                if (dres) {
+                    float rr[VN];
+                    load_vec<T>(dres + off[k], rr);
+#pragma unroll
+                    for (int e = 0; e < VN; ++e) o[e] += rr[e];
+                }
+                store_vec<T>(dx + off[k], o);
+            }
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// column reductions: part[split][0][c] = sum_rows dy*xhat, part[split][1][c] = sum_rows dy
+// thread = one 16B column vector; blockDim = (TX, TY); rows strided by TY*gridDim.y
+// ------------------------------------------------------------------------------------------
+template <typename T, typename TDY, int GROUPS>
+__global__ void __launch_bounds__(256) ln_colsum_kernel(const TDY* __restrict__ dy, const T* __restrict__ x,
+                                                        const float* __restrict__ mean, const float* __restrict__ rstd,
+                                                        const int32_t* __restrict__ map, float* __restrict__ part,
+                                                        int B, int Tin, int Tout, int C) {
+    constexpr int VN = Vec16<T>::N;
+    const int Cw = C * GROUPS;
+    const int nvec = Cw / VN;
+    const int vec_per_group = C / VN;
+    const int vi = blockIdx.x * blockDim.x + threadIdx.x;
+    const long long nrows = (long long)B * Tout;
+    float a1[VN], a2[VN];
+#pragma unroll
+    for (int e = 0; e < VN; ++e) { a1[e] = 0.f; a2[e] = 0.f; }
+    if (vi < nvec) {
+        const int gi = GROUPS > 1 ? vi / vec_per_group : 0;
+        const int col = GROUPS > 1 ? (vi - gi * vec_per_group) * VN : vi * VN;
+        for (long long row = (long long)blockIdx.y * blockDim.y + threadIdx.y; row < nrows;
+             row += (long long)gridDim.y * blockDim.y) {
+            const int b = (int)(row / Tout);
+            const int r = (int)(row - (long long)b * Tout);
+            int src = r;
+            if (GROUPS > 1) src = map[(long long)r * GROUPS + gi];
+            else if (map) src = map[r];
+            if (GROUPS == 1 && src < 0) continue;  // zeroed output row: no gradient
+            float d[VN];
+            constexpr int VD = Vec16<TDY>::N;
+            if constexpr (VD == VN) {
+                load_vec<TDY>(dy + row * Cw + vi * VN, d);
+            } else {
+#pragma unroll
+                for (int h = 0; h < VN / VD; ++h) {
+                    float dd[VD];
+                    load_vec<TDY>(dy + row * Cw + vi * VN + h * VD, dd);
+#pragma unroll
+                    for (int e = 0; e < VD; ++e) d[h * VD + e] = dd[e];
+                }
+            }
+            float xv[VN];
+#pragma unroll
+            for (int e = 0; e < VN; ++e) xv[e] = 0.f;
+            if (src >= 0) load_vec<T>(x + ((long long)b * Tin + src) * C + col, xv);
+            const float mu = mean[row], rs = rstd[row];
+#pragma unroll
+            for (int e = 0; e < VN; ++e) {
+                a1[e] += d[e] * (xv[e] - mu) * rs;
+                a2[e] += d[e];
+            }
+        }
+    }
+    // fixed-order reduction over threadIdx.y through shared memory
+    extern __shared__ float sm[];  // [TY][TX][2*VN]
+    float* mine = sm + ((size_t)threadIdx.y * blockDim.x + threadIdx.x) * 2 * VN;
+#pragma unroll
+    for (int e = 0; e < VN; ++e) { mine[e] = a1[e]; mine[VN + e] = a2[e]; }
+    __syncthreads();
+    if (threadIdx.y == 0 && vi < nvec) {
+        for (int ty = 1; ty < blockDim.y; ++ty) {
+            const float* o = sm + ((size_t)ty * blockDim.x + threadIdx.x) * 2 * VN;
+#pragma unroll
+            for (int e = 0; e < VN; ++e) { a1[e] += o[e]; a2[e] += o[VN + e]; }
+        }
+        float* p = part + (size_t)blockIdx.y * 2 * Cw;
+#pragma unroll
+        for (int e = 0; e < VN; ++e) { p[vi * VN + e] = a1[e]; p[Cw + vi * VN + e] = a2[e]; }
+    }
+}
+
+__global__ void colsum_finish_kernel(const float* __restrict__ part, int splits, int Cw, float* __restrict__ dgamma,
+                                     float* __restrict__ dbeta) {
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= Cw) return;
+    float s1 = 0.f, s2 = 0.f;
+    for (int s = 0; s < splits; ++s) {
+        s1 += part[(size_t)s * 2 * Cw + c];
+        s2 += part[(size_t)s * 2 * Cw + Cw + c];
+    }
+    if (dgamma) dgamma[c] = s1;
+    if (dbeta) dbeta[c] = s2;
+}
+
+constexpr int kColSplits = 256;
+
+// ------------------------------------------------------------------------------------------
+// host-side dispatch
+// ------------------------------------------------------------------------------------------
+struct RowCfg { int lanes, vpl; };
+static bool pick_row_cfg(int nvec, RowCfg* c) {
+    if (nvec <= 0) return false;
+    int lanes = 1;
+    while (lanes < 32 && lanes < nvec) lanes <<= 1;
+    int vpl = (nvec + lanes - 1) / lanes;
+    static const int allowed[] = {1, 2, 4, 8, 16, 32};
+    for (int a : allowed)
+        if (vpl <= a) { c->lanes = lanes; c->vpl = a; return true; }
+    return false;
+}
+
+#define VSW_ROW_DISPATCH(cfg, ...)                                                                         \
+    do {                                                                                                   \
+        if (cfg.lanes == 32) {                                                                             \
+            switch (cfg.vpl) {                                                                             \
+                case 1: { constexpr int LANES = 32, VPL = 1; __VA_ARGS__; } break;                         \
+                case 2: { constexpr int LANES = 32, VPL = 2; __VA_ARGS__; } break;                         \
+                case 4: { constexpr int LANES = 32, VPL = 4; __VA_ARGS__; } break;                         \
+                case 8: { constexpr int LANES = 32, VPL = 8; __VA_ARGS__; } break;                         \
+                case 16: { constexpr int LANES = 32, VPL = 16; __VA_ARGS__; } break;                       \
+                default: { constexpr int LANES = 32, VPL = 32; __VA_ARGS__; } break;                       \
+            }                                                                                              \
+        } else if (cfg.lanes == 16) { constexpr int LANES = 16, VPL = 1; __VA_ARGS__; }                    \
+        else if (cfg.lanes == 8) { constexpr int LANES = 8, VPL = 1; __VA_ARGS__; }                        \
+        else if (cfg.lanes == 4) { constexpr int LANES = 4, VPL = 1; __VA_ARGS__; }                        \
+        else if (cfg.lanes == 2) { constexpr int LANES = 2, VPL = 1; __VA_ARGS__; }                        \
+        else { constexpr int LANES = 1, VPL = 1; __VA_ARGS__; }                                            \
+    } while (0)
+
+static int row_grid(long long nrows, int lanes) {
+    const long long rows_per_block = 8LL * (32 / lanes);
+    long long blocks = (nrows + rows_per_block - 1) / rows_per_block;
+    const long long cap = (long long)kNumSMs * 16;
+    return (int)(blocks < cap ? (blocks > 0 ? blocks : 1) : cap);
+}
+
+template <typename T, typename TO, int GROUPS>
+static int launch_ln_fwd(const void* x, const void* gamma, const void* beta, const int32_t* map, void* y, float* mean,
+                         float* rstd, int B, int Tin, int Tout, int C, float eps, cudaStream_t st) {
+    constexpr int VN = Vec16<T>::N;
+    RowCfg cfg;
+    VSW_REQUIRE((C % VN) == 0 && pick_row_cfg(C * GROUPS / VN, &cfg), VSW_ERR_UNSUPPORTED,
+                "layernorm: C=%d must be a multiple of %d and <= %d", C, VN, 32 * 32 * VN / GROUPS);
+    const int grid = row_grid((long long)B * Tout, cfg.lanes);
+    VSW_ROW_DISPATCH(cfg, (ln_fwd_kernel<T, TO, LANES, VPL, GROUPS><<<grid, 256, 0, st>>>(
+                              (const T*)x, (const T*)gamma, (const T*)beta, map, (TO*)y, mean, rstd, B, Tin, Tout, C,
+                              eps)));
+    return check_launch("ln_fwd");
+}
+
+template <typename T, typename TDY, int GROUPS>
+static int launch_ln_bwd(const void* dy, const void* x, const void* gamma, const float* mean, const float* rstd,
+                         const int32_t* map, const void* dres, void* dx, float* dgamma, float* dbeta, int B, int Tin,
+                         int Tout, int C, void* ws, size_t ws_bytes, cudaStream_t st) {
+    constexpr int VN = Vec16<T>::N;
+    RowCfg cfg;
+    const int Cw = C * GROUPS;
+    VSW_REQUIRE((C % VN) == 0 && pick_row_cfg(Cw / VN, &cfg), VSW_ERR_UNSUPPORTED,
+                "layernorm bwd: C=%d must be a multiple of %d", C, VN);
+    if (dx) {
+        const int grid = row_grid((long long)B * Tout, cfg.lanes);
+        VSW_ROW_DISPATCH(cfg, (ln_bwd_kernel<T, TDY, LANES, VPL, GROUPS><<<grid, 256, 0, st>>>(
+                                  (const TDY*)dy, (const T*)x, (const T*)gamma, mean, rstd, map, (const T*)dres, (T*)dx,
+                                  B, Tin, Tout, C)));
+        int rc = check_launch("ln_bwd");
+        if (rc) return rc;
+    }
+    if (dgamma || dbeta) {
+        VSW_REQUIRE(ws && ws_bytes >= (size_t)kColSplits * 2 * Cw * sizeof(float), VSW_ERR_WORKSPACE,
+                    "layernorm bwd: workspace %zu < %zu", ws_bytes, (size_t)kColSplits * 2 * Cw * sizeof(float));
+        const int nvec = Cw / VN;
+        const int TX = nvec >= 32 ? 32 : 16, TY = 256 / TX;
+        long long nrows = (long long)B * Tout;
+        int splits = (int)((nrows + TY - 1) / TY);
+        if (splits > kColSplits) splits = kColSplits;
+        if (splits < 1) splits = 1;
+        dim3 grid(ceil_div(nvec, TX), splits), block(TX, TY);
+        const size_t smem = (size_t)256 * 2 * VN * sizeof(float);
+        ln_colsum_kernel<T, TDY, GROUPS><<<grid, block, smem, st>>>((const TDY*)dy, (const T*)x, mean, rstd, map,
+                                                                     (float*)ws, B, Tin, Tout, C);
+        int rc = check_launch("ln_colsum");
+        if (rc) return rc;
+        colsum_finish_kernel<<<ceil_div(Cw, 256), 256, 0, st>>>((const float*)ws, splits, Cw, dgamma, dbeta);
+        rc = check_launch("ln_colsum_finish");
+        if (rc) return rc;
+    }
+    return VSW_OK;
+}
+
+}  // namespace vsw
+
+using namespace vsw;
+
+extern "C" size_t vsw_ln_bwd_workspace(int C) { return (size_t)kColSplits * 2 * (size_t)C * sizeof(float); }
+
+extern "C" int vsw_ln_fwd(const void* x, const void* gamma, const void* beta, const int32_t* map, void* y, float* mean,
+                          float* rstd, int B, int Tin, int Tout, int C, float eps, int dtype, int out_dtype,
+                          void* stream) {
+    VSW_REQUIRE(x && gamma && beta && y && B > 0 && Tin > 0 && Tout > 0 && C > 0, VSW_ERR_ARG, "vsw_ln_fwd: bad args");
+    VSW_REQUIRE(map || Tin == Tout, VSW_ERR_ARG, "vsw_ln_fwd: identity map needs Tin == Tout");
+    VSW_REQUIRE((mean == nullptr) == (rstd == nullptr), VSW_ERR_ARG, "vsw_ln_fwd: mean/rstd must both be given or NULL");
+    cudaStream_t st = (cudaStream_t)stream;
+    if (out_dtype == dtype) {
+        VSW_DISPATCH_DTYPE(dtype, T,
+                           return (launch_ln_fwd<T, T, 1>(x, gamma, beta, map, y, mean, rstd, B, Tin, Tout, C, eps, st)));
+    }
+    VSW_REQUIRE(out_dtype == VSW_F32, VSW_ERR_DTYPE, "vsw_ln_fwd: out_dtype must equal dtype or be fp32");
+    VSW_DISPATCH_DTYPE(dtype, T,
+                       return (launch_ln_fwd<T, float, 1>(x, gamma, beta, map, y, mean, rstd, B, Tin, Tout, C, eps, st)));
+    return VSW_OK;
+}
+
+extern "C" int vsw_ln_bwd(const void* dy, const void* x, const void* gamma, const float* mean, const float* rstd,
+                          const int32_t* map, const void* dres, void* dx, float* dgamma, float* dbeta, int B, int Tin,
+                          int Tout, int C, int dtype, int dy_dtype, void* ws, size_t ws_bytes, void* stream) {
+    VSW_REQUIRE(dy && x && gamma && mean && rstd && B > 0 && Tin > 0 && Tout > 0 && C > 0, VSW_ERR_ARG,
+                "vsw_ln_bwd: bad args");
+    VSW_REQUIRE(map || Tin == Tout, VSW_ERR_ARG, "vsw_ln_bwd: identity map needs Tin == Tout");
+    cudaStream_t st = (cudaStream_t)stream;
+    if (dy_dtype == dtype) {
+        VSW_DISPATCH_DTYPE(dtype, T,
+                           return (launch_ln_bwd<T, T, 1>(dy, x, gamma, mean, rstd, map, dres, dx, dgamma, dbeta, B, Tin,
+                                                          Tout, C, ws, ws_bytes, st)));
+    }
+    VSW_REQUIRE(dy_dtype == VSW_F32, VSW_ERR_DTYPE, "vsw_ln_bwd: dy_dtype must equal dtype or be fp32");
+    VSW_DISPATCH_DTYPE(dtype, T,
+                       return (launch_ln_bwd<T, float, 1>(dy, x, gamma, mean, rstd, map, dres, dx, dgamma, dbeta, B, Tin,
+                                                          Tout, C, ws, ws_bytes, st)));
+    return VSW_OK;
+}
+
+extern "C" int vsw_merge_ln_fwd(const void* x, const void* gamma, const void* beta, const int32_t* map4, void* y,
+                                float* mean, float* rstd, int B, int Tin, int Tout, int C, float eps, int dtype,
+                                void* stream) {
+    VSW_REQUIRE(x && gamma && beta && map4 && y && B > 0 && Tin > 0 && Tout > 0 && C > 0, VSW_ERR_ARG,
+                "vsw_merge_ln_fwd: bad args");
+    VSW_REQUIRE((mean == nullptr) == (rstd == nullptr), VSW_ERR_ARG, "vsw_merge_ln_fwd: mean/rstd both or none");
+    cudaStream_t st = (cudaStream_t)stream;
+    VSW_DISPATCH_DTYPE(dtype, T,
+                       return (launch_ln_fwd<T, T, 4>(x, gamma, beta, map4, y, mean, rstd, B, Tin, Tout, C, eps, st)));
+    return VSW_OK;
+}
+
+extern "C" int vsw_merge_ln_bwd(const void* dy, const void* x, const void* gamma, const float* mean, const float* rstd,
+                                const int32_t* map4, void* dx, float* dgamma, float* dbeta, int B, int Tin, int Tout,
+                                int C, int dtype, void* ws, size_t ws_bytes, void* stream) {
+    VSW_REQUIRE(dy && x && gamma && mean && rstd && map4 && B > 0 && Tin > 0 && Tout > 0 && C > 0, VSW_ERR_ARG,
+                "vsw_merge_ln_bwd: bad args");
+    cudaStream_t st = (cudaStream_t)stream;
+    VSW_DISPATCH_DTYPE(dtype, T,
+                       return (launch_ln_bwd<T, T, 4>(dy, x, gamma, mean, rstd, map4, nullptr, dx, dgamma, dbeta, B, Tin,
+                                                      Tout, C, ws, ws_bytes, st)));
+    return VSW_OK;
+}

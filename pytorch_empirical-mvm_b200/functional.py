@@ -1,0 +1,524 @@
+"""Autograd functions over the vsw C ABI -- the host side of the Video-Swin 3D hot path.
+
+Every tensor op on the path is a hand-written CUDA kernel reached through ``_lib`` (ctypes);
+PyTorch only owns memory, streams and the autograd graph.  Tensors are channels-last tokens
+``(B, T, C)``; windowed tensors are ``(B*nW*N, C)``.
+"""
+from __future__ import annotations
+
+import functools
+from dataclasses import dataclass
+from typing import Optional, Tuple
+
+import torch
+
+from . import _lib as L
+
+Triple = Tuple[int, int, int]
+LN_EPS = 1e-5
+
+
+# ----------------------------------------------------------------------------------------------
+# geometry (host ints) + cached device index maps
+# ----------------------------------------------------------------------------------------------
+def get_window_size(x_size, window_size, shift_size=None):
+    """Clamp the window to the grid and zero the shift on clamped axes (video_swin.py:95-108)."""
+    ws = tuple(int(x_size[i]) if x_size[i] <= window_size[i] else int(window_size[i]) for i in range(len(x_size)))
+    if shift_size is None:
+        return ws
+    ss = tuple(0 if x_size[i] <= window_size[i] else int(shift_size[i]) for i in range(len(x_size)))
+    return ws, ss
+
+
+@dataclass(frozen=True)
+class WindowPlan:
+    grid: Triple          # (D,H,W) unpadded
+    pgrid: Triple         # padded to window multiples
+    ws: Triple            # effective window
+    ss: Triple            # effective shift
+    nW: int
+    N: int
+    gather: torch.Tensor  # (nW*N,) int32, token index or -1
+    region: Optional[torch.Tensor]  # (nW*N,) uint8 region ids; None when the block is unshifted
+
+    @property
+    def shifted(self) -> bool:
+        return any(s > 0 for s in self.ss)
+
+
+@functools.lru_cache(maxsize=256)
+def _window_plan(grid: Triple, window: Triple, shift: Triple, device_index: int) -> WindowPlan:
+    ws, ss = get_window_size(grid, window, shift)
+    pg = tuple(-(-grid[a] // ws[a]) * ws[a] for a in range(3))
+    nW = (pg[0] // ws[0]) * (pg[1] // ws[1]) * (pg[2] // ws[2])
+    N = ws[0] * ws[1] * ws[2]
+    dev = torch.device("cuda", device_index)
+    with torch.cuda.device(dev):
+        gather = torch.empty(nW * N, dtype=torch.int32, device=dev)
+        region = torch.empty(nW * N, dtype=torch.uint8, device=dev) if any(ss) else None
+        L.check(L.lib().vsw_window_maps(*grid, *ws, *ss, L.ptr(gather), L.ptr(region), L.stream()), "vsw_window_maps")
+    return WindowPlan(grid, pg, ws, ss, nW, N, gather, region)
+
+
+def window_plan(grid, window, shift, device) -> WindowPlan:
+    device = torch.device(device)
+    if device.type != "cuda":
+        raise L.VswError("vsw kernels are CUDA-only (no CPU fallback)")
+    idx = device.index if device.index is not None else torch.cuda.current_device()
+    return _window_plan(tuple(int(g) for g in grid), tuple(int(w) for w in window), tuple(int(s) for s in shift), idx)
+
+
+@functools.lru_cache(maxsize=64)
+def _merge_map(grid: Triple, device_index: int) -> torch.Tensor:
+    D, H, W = grid
+    dev = torch.device("cuda", device_index)
+    with torch.cuda.device(dev):
+        out = torch.empty(D * ((H + 1) // 2) * ((W + 1) // 2) * 4, dtype=torch.int32, device=dev)
+        L.check(L.lib().vsw_merge_map(D, H, W, L.ptr(out), L.stream()), "vsw_merge_map")
+    return out
+
+
+def merge_map(grid, device) -> torch.Tensor:
+    device = torch.device(device)
+    idx = device.index if device.index is not None else torch.cuda.current_device()
+    return _merge_map(tuple(int(g) for g in grid), idx)
+
+
+def rel_pos_index(window: Triple, device) -> torch.Tensor:
+    """relative_position_index buffer (N,N) int64 (video_swin.py:123-137), built on the device."""
+    N = window[0] * window[1] * window[2]
+    out = torch.empty(N, N, dtype=torch.int64, device=device)
+    with torch.cuda.device(out.device):
+        L.check(L.lib().vsw_rel_pos_index(*window, L.ptr(out), L.stream()), "vsw_rel_pos_index")
+    return out
+
+
+def shift_mask_from_region(region: torch.Tensor, nW: int, N: int, dtype=torch.float32) -> torch.Tensor:
+    out = torch.empty(nW, N, N, dtype=dtype, device=region.device)
+    with torch.cuda.device(out.device):
+        L.check(L.lib().vsw_shift_mask(L.ptr(region), nW, N, L.ptr(out), L.dt(dtype), L.stream()), "vsw_shift_mask")
+    return out
+
+
+def bias_codes(rel_index: torch.Tensor, N: int):
+    """rowcode[i] = index[i,0], colcode[j] = index[0,j] - index[0,0] over the [:N,:N] slice
+    (video_swin.py:155); index[i,j] == rowcode[i] + colcode[j] because the index is a function of
+    coordinate differences only."""
+    idx = rel_index[:N, :N]
+    rowcode = idx[:, 0].to(torch.int32).contiguous()
+    colcode = (idx[0, :] - idx[0, 0]).to(torch.int32).contiguous()
+    return rowcode, colcode
+
+
+# ----------------------------------------------------------------------------------------------
+# thin kernel wrappers (no autograd)
+# ----------------------------------------------------------------------------------------------
+def _empty(shape, dtype, device):
+    return torch.empty(shape, dtype=dtype, device=device)
+
+
+def ln_fwd(x, gamma, beta, gmap, B, Tin, Tout, C, out_dtype=None, want_stats=True):
+    out_dtype = out_dtype or x.dtype
+    y = _empty((B, Tout, C), out_dtype, x.device)
+    mean = _empty((B * Tout,), torch.float32, x.device) if want_stats else None
+    rstd = _empty((B * Tout,), torch.float32, x.device) if want_stats else None
+    L.check(L.lib().vsw_ln_fwd(L.ptr(x), L.ptr(gamma), L.ptr(beta), L.ptr(gmap), L.ptr(y), L.ptr(mean), L.ptr(rstd),
+                               B, Tin, Tout, C, LN_EPS, L.dt(x), L.dt(out_dtype), L.stream()), "vsw_ln_fwd")
+    return y, mean, rstd
+
+
+def ln_bwd(dy, x, gamma, mean, rstd, gmap, dres, B, Tin, Tout, C, need_dx=True, need_dparams=True):
+    dx = _empty((B, Tin, C), x.dtype, x.device) if need_dx else None
+    dg = _empty((C,), torch.float32, x.device) if need_dparams else None
+    db = _empty((C,), torch.float32, x.device) if need_dparams else None
+    wsb = int(L.lib().vsw_ln_bwd_workspace(C)) if need_dparams else 0
+    ws = _empty((max(wsb, 4),), torch.uint8, x.device) if need_dparams else None
+    L.check(L.lib().vsw_ln_bwd(L.ptr(dy), L.ptr(x), L.ptr(gamma), L.ptr(mean), L.ptr(rstd), L.ptr(gmap), L.ptr(dres),
+                               L.ptr(dx), L.ptr(dg), L.ptr(db), B, Tin, Tout, C, L.dt(x), L.dt(dy), L.ptr(ws), wsb,
+                               L.stream()), "vsw_ln_bwd")
+    return dx, dg, db
+
+
+def linear_fwd(x2d, w, bias, M, N, K, epi=L.EPI_BIAS, out=None, aux_out=None, res=None, rowmap=None, rowscale=None,
+               rows_per_batch=0, dst_rows_per_batch=0, out_rows=None):
+    y = out if out is not None else _empty((out_rows if out_rows is not None else M, N), x2d.dtype, x2d.device)
+    L.check(L.lib().vsw_linear_fwd(L.ptr(x2d), L.ptr(w), L.ptr(bias), L.ptr(y), M, N, K, epi, L.ptr(aux_out), L.ptr(res),
+                                   L.ptr(rowmap), L.ptr(rowscale), rows_per_batch, dst_rows_per_batch, L.dt(x2d),
+                                   L.stream()), "vsw_linear_fwd")
+    return y
+
+
+def linear_dgrad(dy, w, M, N, K, a_rowmap=None, a_rowscale=None, rows_per_batch=0, src_rows_per_batch=0, a_out=None,
+                 gelu_pre=None):
+    dx = _empty((M, K), dy.dtype, dy.device)
+    L.check(L.lib().vsw_linear_dgrad(L.ptr(dy), L.ptr(w), L.ptr(dx), M, N, K, L.ptr(a_rowmap), L.ptr(a_rowscale),
+                                     rows_per_batch, src_rows_per_batch, L.ptr(a_out), L.ptr(gelu_pre), L.dt(dy),
+                                     L.stream()), "vsw_linear_dgrad")
+    return dx
+
+
+def linear_wgrad(dy, x2d, M, N, K, need_bias=True, grad_dtype=None):
+    grad_dtype = grad_dtype or dy.dtype
+    dw = _empty((N, K), grad_dtype, dy.device)
+    db = _empty((N,), grad_dtype, dy.device) if need_bias else None
+    wsb = int(L.lib().vsw_linear_wgrad_workspace(M, N, K))
+    ws = _empty((max(wsb, 4),), torch.uint8, dy.device)
+    L.check(L.lib().vsw_linear_wgrad(L.ptr(dy), L.ptr(x2d), L.ptr(dw), L.ptr(db), M, N, K, L.dt(dy), L.dt(grad_dtype),
+                                     L.ptr(ws), wsb, L.stream()), "vsw_linear_wgrad")
+    return dw, db
+
+
+def attn_fwd(qkv, table, rowcode, colcode, region, dense_mask, B_, nW, N, nH, hd, scale):
+    C = nH * hd
+    out = _empty((B_ * N, C), qkv.dtype, qkv.device)
+    lse = _empty((B_, nH, N), torch.float32, qkv.device)
+    L.check(L.lib().vsw_window_attn_fwd(L.ptr(qkv), L.ptr(table), L.ptr(rowcode), L.ptr(colcode), L.ptr(region),
+                                        L.ptr(dense_mask), L.ptr(out), L.ptr(lse), B_, nW, N, nH, hd, table.shape[0],
+                                        float(scale), L.dt(qkv), L.stream()), "vsw_window_attn_fwd")
+    return out, lse
+
+
+def attn_bwd(qkv, out, dout, lse, table, rowcode, colcode, region, dense_mask, B_, nW, N, nH, hd, scale):
+    dqkv = torch.empty_like(qkv)
+    Lt = table.shape[0]
+    dtable = _empty((Lt, nH), torch.float32, qkv.device)
+    wsb = int(L.lib().vsw_window_attn_bwd_workspace(B_, N, nH, hd, Lt))
+    ws = _empty((max(wsb, 4),), torch.uint8, qkv.device)
+    L.check(L.lib().vsw_window_attn_bwd(L.ptr(qkv), L.ptr(out), L.ptr(dout), L.ptr(lse), L.ptr(table), L.ptr(rowcode),
+                                        L.ptr(colcode), L.ptr(region), L.ptr(dense_mask), L.ptr(dqkv), L.ptr(dtable),
+                                        B_, nW, N, nH, hd, Lt, float(scale), L.dt(qkv), L.ptr(ws), wsb, L.stream()),
+            "vsw_window_attn_bwd")
+    return dqkv, dtable
+
+
+def _c(t):
+    return t if t is None or t.is_contiguous() else t.contiguous()
+
+
+def _grad_to(g, like):
+    return None if g is None else g.to(like.dtype)
+
+
+# ----------------------------------------------------------------------------------------------
+# autograd: attention half of a block   x1 = x + dp * proj(attn(qkv(LN1(x) windows)))
+# (video_swin.py:206-245, 256)
+# ----------------------------------------------------------------------------------------------
+class _AttnBranch(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, g1, b1, wqkv, bqkv, table, wproj, bproj, rowscale, plan: WindowPlan, rowcode, colcode,
+                dense_mask, nH, scale):
+        B, T, C = x.shape
+        nW, N = plan.nW, plan.N
+        hd = C // nH
+        R = nW * N
+        x = _c(x)
+        xw, mean, rstd = ln_fwd(x, g1, b1, plan.gather, B, T, R, C)
+        qkv = linear_fwd(xw.view(B * R, C), wqkv, bqkv, B * R, 3 * C, C)
+        region = plan.region if (plan.shifted and dense_mask is None) else None
+        o, lse = attn_fwd(qkv, table, rowcode, colcode, region, dense_mask, B * nW, nW, N, nH, hd, scale)
+        x1 = linear_fwd(o, wproj, bproj, B * R, C, C, epi=L.EPI_RESIDUAL, res=x, rowmap=plan.gather,
+                        rowscale=rowscale, rows_per_batch=R, dst_rows_per_batch=T, out_rows=B * T).view(B, T, C)
+        ctx.save_for_backward(x, g1, wqkv, table, wproj, rowscale, xw, mean, rstd, qkv, o, lse, rowcode, colcode,
+                              dense_mask)
+        ctx.plan, ctx.nH, ctx.scale = plan, nH, scale
+        ctx.has_qkv_bias = bqkv is not None
+        return x1
+
+    @staticmethod
+    def backward(ctx, dx1):
+        (x, g1, wqkv, table, wproj, rowscale, xw, mean, rstd, qkv, o, lse, rowcode, colcode, dense_mask) = ctx.saved_tensors
+        plan, nH, scale = ctx.plan, ctx.nH, ctx.scale
+        B, T, C = x.shape
+        nW, N = plan.nW, plan.N
+        hd = C // nH
+        R = nW * N
+        M = B * R
+        dx1 = _c(dx1)
+        # proj: A = gather(dx1) * rowscale ; dO = A Wp ; dWp = A^T O ; dbp = sum A
+        a_buf = _empty((M, C), x.dtype, x.device)
+        dO = linear_dgrad(dx1, wproj, M, C, C, a_rowmap=plan.gather, a_rowscale=rowscale, rows_per_batch=R,
+                          src_rows_per_batch=T, a_out=a_buf)
+        dwp, dbp = linear_wgrad(a_buf, o, M, C, C)
+        del a_buf
+        region = plan.region if (plan.shifted and dense_mask is None) else None
+        dqkv, dtable = attn_bwd(qkv, o, dO, lse, table, rowcode, colcode, region, dense_mask, B * nW, nW, N, nH, hd, scale)
+        del dO
+        dxw = linear_dgrad(dqkv, wqkv, M, 3 * C, C)
+        dwq, dbq = linear_wgrad(dqkv, xw.view(M, C), M, 3 * C, C, need_bias=ctx.has_qkv_bias)
+        del dqkv
+        dx, dg1, db1 = ln_bwd(dxw, x, g1, mean, rstd, plan.gather, dx1, B, T, R, C)
+        return (dx, _grad_to(dg1, g1), _grad_to(db1, g1), dwq, dbq, _grad_to(dtable, table), dwp, dbp,
+                None, None, None, None, None, None, None)
+
+
+# ----------------------------------------------------------------------------------------------
+# autograd: MLP half of a block   out = x + dp * fc2(gelu(fc1(LN2(x))))   (video_swin.py:247-248, 261)
+# ----------------------------------------------------------------------------------------------
+class _MlpBranch(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, g2, b2, w1, bb1, w2, bb2, rowscale):
+        B, T, C = x.shape
+        Hd = w1.shape[0]
+        M = B * T
+        x = _c(x)
+        n2, mean, rstd = ln_fwd(x, g2, b2, None, B, T, T, C)
+        need_grad = any(ctx.needs_input_grad)
+        u = _empty((M, Hd), x.dtype, x.device) if need_grad else None
+        g = linear_fwd(n2.view(M, C), w1, bb1, M, Hd, C, epi=L.EPI_GELU, aux_out=u)
+        out = linear_fwd(g, w2, bb2, M, C, Hd, epi=L.EPI_RESIDUAL, res=x, rowscale=rowscale, rows_per_batch=T,
+                         dst_rows_per_batch=T).view(B, T, C)
+        if need_grad:
+            ctx.save_for_backward(x, g2, w1, w2, rowscale, n2, mean, rstd, u, g)
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        x, g2, w1, w2, rowscale, n2, mean, rstd, u, g = ctx.saved_tensors
+        B, T, C = x.shape
+        Hd = w1.shape[0]
+        M = B * T
+        dout = _c(dout)
+        a_buf = _empty((M, C), x.dtype, x.device) if rowscale is not None else None
+        du = linear_dgrad(dout.view(M, C), w2, M, C, Hd, a_rowscale=rowscale, rows_per_batch=T, src_rows_per_batch=T,
+                          a_out=a_buf, gelu_pre=u)
+        dw2, db2 = linear_wgrad(a_buf if a_buf is not None else dout.view(M, C), g, M, C, Hd)
+        del a_buf
+        dn2 = linear_dgrad(du, w1, M, Hd, C)
+        dw1, db1 = linear_wgrad(du, n2.view(M, C), M, Hd, C)
+        del du
+        dx, dg2, dbeta2 = ln_bwd(dn2, x, g2, mean, rstd, None, dout, B, T, T, C)
+        return dx, _grad_to(dg2, g2), _grad_to(dbeta2, g2), dw1, db1, dw2, db2, None
+
+
+# ----------------------------------------------------------------------------------------------
+# autograd: standalone WindowAttention3D.forward on pre-partitioned windows (video_swin.py:147-172)
+# ----------------------------------------------------------------------------------------------
+class _WindowAttention(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, xw, wqkv, bqkv, table, wproj, bproj, rowcode, colcode, dense_mask, nW, nH, scale):
+        B_, N, C = xw.shape
+        hd = C // nH
+        M = B_ * N
+        xw = _c(xw)
+        qkv = linear_fwd(xw.view(M, C), wqkv, bqkv, M, 3 * C, C)
+        o, lse = attn_fwd(qkv, table, rowcode, colcode, None, dense_mask, B_, nW, N, nH, hd, scale)
+        y = linear_fwd(o, wproj, bproj, M, C, C).view(B_, N, C)
+        ctx.save_for_backward(xw, wqkv, table, wproj, qkv, o, lse, rowcode, colcode, dense_mask)
+        ctx.nW, ctx.nH, ctx.scale, ctx.has_qkv_bias = nW, nH, scale, bqkv is not None
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        xw, wqkv, table, wproj, qkv, o, lse, rowcode, colcode, dense_mask = ctx.saved_tensors
+        B_, N, C = xw.shape
+        nH = ctx.nH
+        hd = C // nH
+        M = B_ * N
+        dy = _c(dy).view(M, C)
+        dO = linear_dgrad(dy, wproj, M, C, C)
+        dwp, dbp = linear_wgrad(dy, o, M, C, C)
+        dqkv, dtable = attn_bwd(qkv, o, dO, lse, table, rowcode, colcode, None, dense_mask, B_, ctx.nW, N, nH, hd, ctx.scale)
+        dxw = linear_dgrad(dqkv, wqkv, M, 3 * C, C).view(B_, N, C)
+        dwq, dbq = linear_wgrad(dqkv, xw.view(M, C), M, 3 * C, C, need_bias=ctx.has_qkv_bias)
+        return dxw, dwq, dbq, _grad_to(dtable, table), dwp, dbp, None, None, None, None, None, None
+
+
+# ----------------------------------------------------------------------------------------------
+# autograd: Mlp on arbitrary (..., C) input, LayerNorm, Linear  (stand-alone module use)
+# ----------------------------------------------------------------------------------------------
+class _Mlp(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x2d, w1, b1, w2, b2):
+        M, C = x2d.shape
+        Hd, Co = w1.shape[0], w2.shape[0]
+        x2d = _c(x2d)
+        u = _empty((M, Hd), x2d.dtype, x2d.device)
+        g = linear_fwd(x2d, w1, b1, M, Hd, C, epi=L.EPI_GELU, aux_out=u)
+        y = linear_fwd(g, w2, b2, M, Co, Hd)
+        ctx.save_for_backward(x2d, w1, w2, u, g)
+        ctx.has_bias = (b1 is not None, b2 is not None)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        x2d, w1, w2, u, g = ctx.saved_tensors
+        M, C = x2d.shape
+        Hd, Co = w1.shape[0], w2.shape[0]
+        dy = _c(dy)
+        du = linear_dgrad(dy, w2, M, Co, Hd, gelu_pre=u)
+        dw2, db2 = linear_wgrad(dy, g, M, Co, Hd, need_bias=ctx.has_bias[1])
+        dx = linear_dgrad(du, w1, M, Hd, C)
+        dw1, db1 = linear_wgrad(du, x2d, M, Hd, C, need_bias=ctx.has_bias[0])
+        return dx, dw1, db1, dw2, db2
+
+
+class _LayerNorm(torch.autograd.Function):
+    """LayerNorm over the last dim of (B,T,C); ``out_dtype`` lets the final norm return fp32 under autocast."""
+
+    @staticmethod
+    def forward(ctx, x, gamma, beta, out_dtype):
+        B, T, C = x.shape
+        x = _c(x)
+        y, mean, rstd = ln_fwd(x, gamma, beta, None, B, T, T, C, out_dtype=out_dtype)
+        ctx.save_for_backward(x, gamma, mean, rstd)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, gamma, mean, rstd = ctx.saved_tensors
+        B, T, C = x.shape
+        dy = _c(dy)
+        if dy.dtype not in (x.dtype, torch.float32):
+            dy = dy.to(x.dtype)
+        dx, dg, db = ln_bwd(dy, x, gamma, mean, rstd, None, None, B, T, T, C, need_dx=ctx.needs_input_grad[0])
+        return dx, _grad_to(dg, gamma), _grad_to(db, gamma), None
+
+
+class _Linear(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x2d, w, b):
+        M, K = x2d.shape
+        x2d = _c(x2d)
+        y = linear_fwd(x2d, w, b, M, w.shape[0], K)
+        ctx.save_for_backward(x2d, w)
+        ctx.has_bias = b is not None
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        x2d, w = ctx.saved_tensors
+        M, K = x2d.shape
+        N = w.shape[0]
+        dy = _c(dy)
+        dx = linear_dgrad(dy, w, M, N, K) if ctx.needs_input_grad[0] else None
+        dw, db = linear_wgrad(dy, x2d, M, N, K, need_bias=ctx.has_bias)
+        return dx, dw, db
+
+
+# ----------------------------------------------------------------------------------------------
+# autograd: PatchMerging (video_swin.py:273-289) and PatchEmbed3D (video_swin.py:390-407)
+# ----------------------------------------------------------------------------------------------
+class _PatchMerge(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, gamma, beta, wred, grid: Triple):
+        B, T, C = x.shape
+        D, H, W = grid
+        T2 = D * ((H + 1) // 2) * ((W + 1) // 2)
+        x = _c(x)
+        m4 = merge_map(grid, x.device)
+        y4 = _empty((B, T2, 4 * C), x.dtype, x.device)
+        mean = _empty((B * T2,), torch.float32, x.device)
+        rstd = _empty((B * T2,), torch.float32, x.device)
+        L.check(L.lib().vsw_merge_ln_fwd(L.ptr(x), L.ptr(gamma), L.ptr(beta), L.ptr(m4), L.ptr(y4), L.ptr(mean),
+                                         L.ptr(rstd), B, T, T2, C, LN_EPS, L.dt(x), L.stream()), "vsw_merge_ln_fwd")
+        y = linear_fwd(y4.view(B * T2, 4 * C), wred, None, B * T2, 2 * C, 4 * C).view(B, T2, 2 * C)
+        ctx.save_for_backward(x, gamma, wred, y4, mean, rstd, m4)
+        ctx.grid = grid
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, gamma, wred, y4, mean, rstd, m4 = ctx.saved_tensors
+        B, T, C = x.shape
+        T2 = y4.shape[1]
+        M = B * T2
+        dy = _c(dy).view(M, 2 * C)
+        dy4 = linear_dgrad(dy, wred, M, 2 * C, 4 * C)
+        dw, _ = linear_wgrad(dy, y4.view(M, 4 * C), M, 2 * C, 4 * C, need_bias=False)
+        # odd H/W: padded input tokens do not exist, every real token is written exactly once
+        dx = _empty((B, T, C), x.dtype, x.device)
+        dg = _empty((4 * C,), torch.float32, x.device)
+        db = _empty((4 * C,), torch.float32, x.device)
+        wsb = int(L.lib().vsw_ln_bwd_workspace(4 * C))
+        ws = _empty((wsb,), torch.uint8, x.device)
+        L.check(L.lib().vsw_merge_ln_bwd(L.ptr(dy4), L.ptr(x), L.ptr(gamma), L.ptr(mean), L.ptr(rstd), L.ptr(m4),
+                                         L.ptr(dx), L.ptr(dg), L.ptr(db), B, T, T2, C, L.dt(x), L.ptr(ws), wsb,
+                                         L.stream()), "vsw_merge_ln_bwd")
+        return dx, _grad_to(dg, gamma), _grad_to(db, gamma), dw, None
+
+
+class _PatchEmbed(torch.autograd.Function):
+    """x (B,Cin,D,H,W) any float dtype -> tokens (B, Dout*Hp*Wp, E) in the compute dtype of ``w``."""
+
+    @staticmethod
+    def forward(ctx, x, w, b, gamma, beta, patch: Triple):
+        B, Cin, D, H, W = x.shape
+        pd, ph, pw = patch
+        E = w.shape[0]
+        Dout, Hp, Wp = D + 2 - pd, -(-H // ph), -(-W // pw)
+        T = Dout * Hp * Wp
+        Kv = Cin * pd * ph * pw
+        x = _c(x)
+        cdt = w.dtype
+        col = _empty((B * T, Kv), cdt, x.device)
+        L.check(L.lib().vsw_patch_im2col(L.ptr(x), L.ptr(col), B, Cin, D, H, W, pd, ph, pw, L.dt(x), L.dt(cdt),
+                                         L.stream()), "vsw_patch_im2col")
+        w2d = w.reshape(E, Kv)
+        y = linear_fwd(col, w2d, b, B * T, E, Kv).view(B, T, E)
+        if gamma is not None:
+            yn, mean, rstd = ln_fwd(y, gamma, beta, None, B, T, T, E)
+        else:
+            yn, mean, rstd = y, None, None
+        ctx.save_for_backward(col, w2d, y if gamma is not None else None, gamma, mean, rstd)
+        ctx.meta = (x.shape, x.dtype, patch, w.shape)
+        return yn
+
+    @staticmethod
+    def backward(ctx, dyn):
+        col, w2d, y, gamma, mean, rstd = ctx.saved_tensors
+        xshape, xdtype, patch, wshape = ctx.meta
+        B, Cin, D, H, W = xshape
+        pd, ph, pw = patch
+        E, Kv = w2d.shape
+        M = col.shape[0]
+        T = M // B
+        dyn = _c(dyn)
+        dg = dbeta = None
+        if gamma is not None:
+            dy, dg, dbeta = ln_bwd(dyn, y, gamma, mean, rstd, None, None, B, T, T, E)
+        else:
+            dy = dyn
+        dy2 = dy.view(M, E)
+        dw, db = linear_wgrad(dy2, col, M, E, Kv)
+        dx = None
+        if ctx.needs_input_grad[0]:
+            dcol = linear_dgrad(dy2, w2d, M, E, Kv)
+            dx = _empty(xshape, xdtype, col.device)
+            L.check(L.lib().vsw_patch_col2im(L.ptr(dcol), L.ptr(dx), B, Cin, D, H, W, pd, ph, pw, L.dt(xdtype),
+                                             L.dt(col), L.stream()), "vsw_patch_col2im")
+        return (dx, dw.view(wshape), db, _grad_to(dg, gamma) if gamma is not None else None,
+                _grad_to(dbeta, gamma) if gamma is not None else None, None)
+
+
+# public functional entry points --------------------------------------------------------------
+def attn_branch(x, g1, b1, wqkv, bqkv, table, wproj, bproj, rowscale, plan, rowcode, colcode, dense_mask, nH, scale):
+    return _AttnBranch.apply(x, g1, b1, wqkv, bqkv, table, wproj, bproj, rowscale, plan, rowcode, colcode, dense_mask,
+                             nH, scale)
+
+
+def mlp_branch(x, g2, b2, w1, bb1, w2, bb2, rowscale):
+    return _MlpBranch.apply(x, g2, b2, w1, bb1, w2, bb2, rowscale)
+
+
+def window_attention(xw, wqkv, bqkv, table, wproj, bproj, rowcode, colcode, dense_mask, nW, nH, scale):
+    return _WindowAttention.apply(xw, wqkv, bqkv, table, wproj, bproj, rowcode, colcode, dense_mask, nW, nH, scale)
+
+
+def mlp(x2d, w1, b1, w2, b2):
+    return _Mlp.apply(x2d, w1, b1, w2, b2)
+
+
+def layer_norm(x3d, gamma, beta, out_dtype=None):
+    return _LayerNorm.apply(x3d, gamma, beta, out_dtype)
+
+
+def linear(x2d, w, b):
+    return _Linear.apply(x2d, w, b)
+
+
+def patch_merge(x, gamma, beta, wred, grid):
+    return _PatchMerge.apply(x, gamma, beta, wred, grid)
+
+
+def patch_embed(x, w, b, gamma, beta, patch):
+    return _PatchEmbed.apply(x, w, b, gamma, beta, patch)
