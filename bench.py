@@ -1,0 +1,303 @@
+#!/usr/bin/env python
+"""bench.py -- Video-Swin-B fwd+bwd clips/sec on N B200s (BASELINE.json metric), one JSON line.
+
+    python bench.py --gpus 1 --steps 10 --warmup 3
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port P \
+        bench.py --gpus N --steps K --warmup W
+    python bench.py --impl reference ...     # the reference algorithm on the host CPU (oracle port)
+
+A step = forward + backward (all 327 parameter gradients) of SwinTransformer3D (Swin-B widths,
+embed_dim 128, heads 4/8/16/32, depths 2/2/18/2, drop_path_rate 0.2, train mode) over one batch of
+synthetic 8x224^2 clips; bf16 parameters and activations, fp32 softmax/LN statistics.  Data parallel:
+every rank owns `--batch` clips (weak scaling); gradients are all-reduced by DDP/NCCL inside backward.
+
+  value : clips/s with the clips already resident in HBM.
+  e2e   : same step called through the public module API with fp32 clips in PINNED HOST memory:
+          H2D copy of the batch + D2H read of the scalar loss inside the timed region.
+  roofline : the kernel family with the largest share of the timed step, timed live with CUDA events.
+  cpu_baseline : the oracle port of the reference on the host cores, bounded sample.
+"""
+import argparse
+import importlib
+import json
+import os
+import sys
+import threading
+import time
+
+import torch
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+PKG = "pytorch_empirical-mvm_b200"
+
+MODELS = {
+    "swin_b": dict(embed_dim=128, depths=[2, 2, 18, 2], num_heads=[4, 8, 16, 32], window_size=(8, 7, 7)),
+    "violet": dict(embed_dim=96, depths=[2, 2, 18, 2], num_heads=[3, 6, 12, 24], window_size=(8, 7, 7)),
+    "swin_l_384": dict(embed_dim=192, depths=[2, 2, 18, 2], num_heads=[6, 12, 24, 48], window_size=(8, 12, 12)),
+}
+FWD_BWD_GFLOP_PER_CLIP = {"swin_b": 844.0, "violet": 497.0, "swin_l_384": 6319.1}  # SURVEY 8d (3 x fwd)
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        with open(p) as f:
+            d = json.load(f)
+        return dict(hbm=d["hbm_gbs"], tf_burst=d["bf16_tflops"], tf_sustained=d["bf16_tflops_sustained"],
+                    source="MEASURED_PEAKS.json")
+    return dict(hbm=6650.0, tf_burst=1590.0, tf_sustained=1400.0, source="fallback (B200_PROFILING.md)")
+
+
+class ClockSampler(threading.Thread):
+    """samples SM clock + throttle reasons through NVML while the timed region runs"""
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index, self.stop_flag, self.samples, self.reasons, self.max_mhz = index, False, [], set(), None
+
+    def run(self):
+        try:
+            import pynvml as nv
+            nv.nvmlInit()
+            h = nv.nvmlDeviceGetHandleByIndex(self.index)
+            self.max_mhz = nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM)
+            names = {nv.nvmlClocksThrottleReasonHwSlowdown: "hw_slowdown",
+                     nv.nvmlClocksThrottleReasonHwThermalSlowdown: "hw_thermal_slowdown",
+                     nv.nvmlClocksThrottleReasonSwThermalSlowdown: "sw_thermal_slowdown",
+                     nv.nvmlClocksThrottleReasonSwPowerCap: "sw_power_cap",
+                     nv.nvmlClocksThrottleReasonHwPowerBrakeSlowdown: "hw_power_brake"}
+            while not self.stop_flag:
+                self.samples.append(nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM))
+                r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(h)
+                for bit, nm in names.items():
+                    if r & bit:
+                        self.reasons.add(nm)
+                time.sleep(0.1)
+        except Exception as e:  # NVML missing: report that instead of inventing clocks
+            self.reasons.add(f"nvml_unavailable:{type(e).__name__}")
+
+    def result(self):
+        s = sorted(self.samples)
+        return dict(sm_mhz=(s[len(s) // 2] if s else None), sm_max_mhz=self.max_mhz, reasons=sorted(self.reasons))
+
+
+def cpu_reference_run(model_name, batch, steps, warmup, threads):
+    """the reference algorithm (oracle port, fp32) forward+backward on the host cores -> clips/s"""
+    from oracle import swin3d_oracle as O
+    torch.set_num_threads(threads)
+    kw = MODELS[model_name]
+    cfg = O.SwinCfg(embed_dim=kw["embed_dim"], depths=tuple(kw["depths"]), num_heads=tuple(kw["num_heads"]),
+                    window_size=tuple(kw["window_size"]))
+    sd = O.make_state_dict(cfg, seed=0)
+    side = 384 if model_name == "swin_l_384" else 224
+    torch.manual_seed(0)
+    x = torch.randn(batch, 3, 8, side, side)
+    y0 = O.swin_forward(sd, x[:1], cfg)
+    R = torch.randn(batch, *y0.shape[1:]) / 1024
+    times = []
+    for i in range(warmup + steps):
+        t0 = time.perf_counter()
+        O.forward_backward(sd, x, cfg, R)
+        dt = time.perf_counter() - t0
+        if i >= warmup:
+            times.append(dt)
+    return batch * len(times) / sum(times), sum(times) / len(times)
+
+
+def cpu_model_name():
+    try:
+        with open("/proc/cpuinfo") as f:
+            for line in f:
+                if line.startswith("model name"):
+                    return line.split(":", 1)[1].strip()
+    except OSError:
+        pass
+    return "unknown"
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--model", default="swin_b", choices=list(MODELS))
+    ap.add_argument("--batch", type=int, default=32, help="clips per GPU (BASELINE config 2: 32)")
+    ap.add_argument("--cpu-batch", type=int, default=2, help="clips per CPU-baseline step (BASELINE config 1: 2)")
+    ap.add_argument("--backend", default="auto", choices=["auto", "simt", "tcgen05"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    args = ap.parse_args()
+    assert args.warmup >= 3 or args.impl == "reference", "timing rules: at least 3 warm-up steps"
+
+    rank = int(os.environ.get("RANK", 0))
+    world = int(os.environ.get("WORLD_SIZE", 1))
+    local_rank = int(os.environ.get("LOCAL_RANK", 0))
+    side = 384 if args.model == "swin_l_384" else 224
+    workload = f"Video-{args.model} fwd+bwd, {args.batch} clips/GPU x 8x{side}^2, bf16, drop_path 0.2 train mode"
+
+    # ------------------------------------------------------------------ reference arm (host CPU)
+    if args.impl == "reference":
+        if rank != 0:
+            return
+        threads = os.cpu_count() or 1
+        steps = max(1, min(args.steps, 3))
+        cps, sec = cpu_reference_run(args.model, args.cpu_batch, steps, 1, threads)
+        sample = (f"{steps} timed steps (1 warm-up) of fwd+bwd over {args.cpu_batch} clips of 8x{side}^2, fp32, "
+                  f"oracle port of visbackbone/video_swin.py, torch {torch.__version__} CPU, {threads} threads, {cpu_model_name()}")
+        print(json.dumps({
+            "impl": "reference", "metric": "Video-Swin-B fwd+bwd clips/sec", "value": cps, "unit": "clips/s",
+            "n_gpus": args.gpus, "steps": steps, "warmup": 1, "ms_per_step": sec * 1e3, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": workload, "cpu_sample_clips_per_step": args.cpu_batch},
+            "cpu_baseline": {"value": cps, "unit": "clips/s", "cores": threads, "kind": "port", "sample": sample},
+            "e2e": {"value": cps, "unit": "clips/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        }))
+        return
+
+    # ------------------------------------------------------------------ our arm (B200)
+    vsw = importlib.import_module(PKG)
+    VF, L = vsw.functional, vsw._lib
+    assert torch.cuda.is_available(), "bench.py needs a GPU (there is no CPU fallback)"
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=dev)
+    L.set_gemm_backend({"auto": L.GEMM_AUTO, "simt": L.GEMM_SIMT, "tcgen05": L.GEMM_TCGEN05}[args.backend])
+
+    torch.manual_seed(0)  # identical weights on every rank
+    model = vsw.SwinTransformer3D(pretrained=None, drop_path_rate=0.2, **MODELS[args.model])
+    model.init_weights()
+    model = model.to(dev).bfloat16().train()
+    net = model
+    if world > 1:
+        from torch.nn.parallel import DistributedDataParallel as DDP
+        net = DDP(model, device_ids=[local_rank], gradient_as_bucket_view=True, bucket_cap_mb=50)
+    B = args.batch
+    torch.manual_seed(1 + rank)  # per-rank clips
+    x_host = torch.randn(B, 3, 8, side, side).pin_memory()  # fp32 frames as the data loader yields them
+    x_dev = x_host.to(dev, non_blocking=True)
+    with torch.no_grad():
+        y0 = model(x_dev[:1])
+    Rm = (torch.randn(B, *y0.shape[1:], device=dev) / 1024).to(torch.bfloat16)
+    # inputs (154 MB fp32) + saved activations (GBs) exceed the 126 MB L2 every step: no explicit flush needed
+    l2_note = "inputs+activations per step >> 126 MB L2 (no explicit flush)"
+
+    def step(x):
+        for p in model.parameters():
+            p.grad = None
+        y = net(x)
+        loss = (y * Rm).sum(dtype=torch.float32)
+        loss.backward()
+        return loss
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, steps):
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            fn()
+        e1.record()
+        barrier()
+        ms = e0.elapsed_time(e1)
+        if dist is not None:
+            t = torch.tensor([ms], device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t.item())
+        return ms
+
+    for _ in range(args.warmup):
+        step(x_dev)
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    n0 = L.launch_count()
+    ms_total = timed(lambda: step(x_dev), args.steps)
+    launches = L.launch_count() - n0
+    sampler.stop_flag = True
+    sampler.join(timeout=2)
+    ms_step = ms_total / args.steps
+    value = world * B / (ms_step / 1e3)
+
+    # ---- e2e: pinned host clips -> H2D -> module API -> D2H loss
+    e2e = None
+    if not args.no_e2e:
+        def e2e_step():
+            xd = x_host.to(dev, non_blocking=True)
+            loss = step(xd)
+            return float(loss.item())  # D2H read of the result
+        e2e_step()
+        ms_e2e = timed(e2e_step, args.steps) / args.steps
+        e2e = {"value": world * B / (ms_e2e / 1e3), "unit": "clips/s", "ms_per_step": ms_e2e,
+               "h2d_bytes_per_step": x_host.numel() * x_host.element_size(), "d2h_bytes_per_step": 4}
+
+    # ---- roofline of the dominant kernel family: per-launch CUDA events on the launching stream
+    roofline, families = None, None
+    if rank == 0:
+        VF.PROFILER = VF.KernelTimer()
+        torch.cuda.synchronize()
+        psteps = 2
+        pe0, pe1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        pe0.record()
+        for _ in range(psteps):
+            step(x_dev)
+        pe1.record()
+        torch.cuda.synchronize()
+        summ = VF.PROFILER.summary()
+        VF.PROFILER = None
+        pk = peaks()
+        step_ms = pe0.elapsed_time(pe1)
+        families = {k: dict(launches=v["launches"] // psteps, ms_per_step=v["ms"] / psteps,
+                            share_of_step=v["ms"] / step_ms,
+                            tflops=(v["flops"] / (v["ms"] * 1e-3) / 1e12 if v["ms"] > 0 else 0.0),
+                            gbs=(v["bytes"] / (v["ms"] * 1e-3) / 1e9 if v["ms"] > 0 else 0.0))
+                    for k, v in summ.items()}
+        top = max(summ, key=lambda k: summ[k]["ms"])
+        v = summ[top]
+        tensor_bound = v["flops"] > 0
+        ach = (v["flops"] / (v["ms"] * 1e-3) / 1e12) if tensor_bound else (v["bytes"] / (v["ms"] * 1e-3) / 1e9)
+        peak = pk["tf_sustained"] if tensor_bound else pk["hbm"]
+        roofline = {"kernel": top, "bound": "tensor" if tensor_bound else "hbm", "achieved": ach, "peak": peak,
+                    "unit": "TFLOP/s" if tensor_bound else "GB/s", "frac": ach / peak, "traffic": None,
+                    "peak_source": pk["source"] + (" (sustained bf16)" if tensor_bound else ""),
+                    "launches_per_step": v["launches"] // psteps,
+                    "avg_launch_ms": v["ms"] / max(1, v["launches"])}
+    # ---- CPU baseline (rank 0, N=1 only): oracle port on the host cores, bounded sample
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        threads = os.cpu_count() or 1
+        cps, sec = cpu_reference_run(args.model, args.cpu_batch, 2, 1, threads)
+        cpu = {"value": cps, "unit": "clips/s", "cores": threads, "kind": "port",
+               "sample": f"2 timed steps (1 warm-up) of fwd+bwd over {args.cpu_batch} clips of 8x{side}^2, fp32, "
+                         f"{sec:.2f} s/step, {cpu_model_name()}"}
+
+    if rank == 0:
+        pk = peaks()
+        step_tflops = world * B * FWD_BWD_GFLOP_PER_CLIP[args.model] / ms_step  # GF/ms == TF/s
+        out = {
+            "metric": "Video-Swin-B fwd+bwd clips/sec", "value": value, "unit": "clips/s", "n_gpus": world,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+            "config": {"workload": workload, "model": args.model, "clips_per_gpu": B, "global_batch": world * B,
+                       "parallelism": f"dp{world}", "gemm_backend": args.backend, "l2": l2_note,
+                       "optimizer": "excluded (metric is encoder fwd+bwd, SURVEY 8d)"},
+            "clocks": sampler.result(), "e2e": e2e, "gpu_launches": int(launches),
+            "step_tflops_per_gpu": step_tflops / world,
+            "step_frac_of_bf16_sustained": step_tflops / world / pk["tf_sustained"],
+            "roofline": roofline, "kernel_families": families, "cpu_baseline": cpu,
+        }
+        print(json.dumps(out))
+    if dist is not None:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

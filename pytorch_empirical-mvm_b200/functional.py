@@ -111,6 +111,41 @@ def bias_codes(rel_index: torch.Tensor, N: int):
 
 
 # ----------------------------------------------------------------------------------------------
+# optional per-kernel CUDA-event timing (bench.py's roofline leg); off by default
+# ----------------------------------------------------------------------------------------------
+class KernelTimer:
+    """Records a CUDA-event pair on the launching stream around every call of the wrapped kernel
+    families, with the ALGORITHMIC flops / bytes of that call."""
+
+    def __init__(self):
+        self.records = {}  # name -> [(start, end, flops, bytes)]
+
+    def begin(self):
+        ev = torch.cuda.Event(enable_timing=True)
+        ev.record(torch.cuda.current_stream())
+        return ev
+
+    def end(self, name, start, flops, nbytes):
+        ev = torch.cuda.Event(enable_timing=True)
+        ev.record(torch.cuda.current_stream())
+        self.records.setdefault(name, []).append((start, ev, flops, nbytes))
+
+    def summary(self):
+        out = {}
+        for name, recs in self.records.items():
+            ms = sum(a.elapsed_time(b) for a, b, _, _ in recs)
+            out[name] = dict(launches=len(recs), ms=ms, flops=sum(r[2] for r in recs), bytes=sum(r[3] for r in recs))
+        return out
+
+
+PROFILER: Optional[KernelTimer] = None
+
+
+def _esz(t):
+    return t.element_size()
+
+
+# ----------------------------------------------------------------------------------------------
 # thin kernel wrappers (no autograd)
 # ----------------------------------------------------------------------------------------------
 def _empty(shape, dtype, device):
@@ -122,8 +157,11 @@ def ln_fwd(x, gamma, beta, gmap, B, Tin, Tout, C, out_dtype=None, want_stats=Tru
     y = _empty((B, Tout, C), out_dtype, x.device)
     mean = _empty((B * Tout,), torch.float32, x.device) if want_stats else None
     rstd = _empty((B * Tout,), torch.float32, x.device) if want_stats else None
+    t0 = PROFILER.begin() if PROFILER is not None else None
     L.check(L.lib().vsw_ln_fwd(L.ptr(x), L.ptr(gamma), L.ptr(beta), L.ptr(gmap), L.ptr(y), L.ptr(mean), L.ptr(rstd),
                                B, Tin, Tout, C, LN_EPS, L.dt(x), L.dt(out_dtype), L.stream()), "vsw_ln_fwd")
+    if t0 is not None:
+        PROFILER.end("ln_fwd", t0, 0.0, B * C * (Tin * _esz(x) + Tout * y.element_size()))
     return y, mean, rstd
 
 
@@ -133,27 +171,40 @@ def ln_bwd(dy, x, gamma, mean, rstd, gmap, dres, B, Tin, Tout, C, need_dx=True, 
     db = _empty((C,), torch.float32, x.device) if need_dparams else None
     wsb = int(L.lib().vsw_ln_bwd_workspace(C)) if need_dparams else 0
     ws = _empty((max(wsb, 4),), torch.uint8, x.device) if need_dparams else None
+    t0 = PROFILER.begin() if PROFILER is not None else None
     L.check(L.lib().vsw_ln_bwd(L.ptr(dy), L.ptr(x), L.ptr(gamma), L.ptr(mean), L.ptr(rstd), L.ptr(gmap), L.ptr(dres),
                                L.ptr(dx), L.ptr(dg), L.ptr(db), B, Tin, Tout, C, L.dt(x), L.dt(dy), L.ptr(ws), wsb,
                                L.stream()), "vsw_ln_bwd")
+    if t0 is not None:
+        PROFILER.end("ln_bwd", t0, 0.0, B * C * (Tout * dy.element_size() + Tin * _esz(x) * (2 + (dres is not None))))
     return dx, dg, db
 
 
 def linear_fwd(x2d, w, bias, M, N, K, epi=L.EPI_BIAS, out=None, aux_out=None, res=None, rowmap=None, rowscale=None,
                rows_per_batch=0, dst_rows_per_batch=0, out_rows=None):
     y = out if out is not None else _empty((out_rows if out_rows is not None else M, N), x2d.dtype, x2d.device)
+    t0 = PROFILER.begin() if PROFILER is not None else None
     L.check(L.lib().vsw_linear_fwd(L.ptr(x2d), L.ptr(w), L.ptr(bias), L.ptr(y), M, N, K, epi, L.ptr(aux_out), L.ptr(res),
                                    L.ptr(rowmap), L.ptr(rowscale), rows_per_batch, dst_rows_per_batch, L.dt(x2d),
                                    L.stream()), "vsw_linear_fwd")
+    if t0 is not None:
+        e = _esz(x2d)
+        nb = (M * K + N * K + M * N * (1 + (aux_out is not None) + (res is not None))) * e
+        PROFILER.end("linear_fwd", t0, 2.0 * M * N * K, nb)
     return y
 
 
 def linear_dgrad(dy, w, M, N, K, a_rowmap=None, a_rowscale=None, rows_per_batch=0, src_rows_per_batch=0, a_out=None,
                  gelu_pre=None):
     dx = _empty((M, K), dy.dtype, dy.device)
+    t0 = PROFILER.begin() if PROFILER is not None else None
     L.check(L.lib().vsw_linear_dgrad(L.ptr(dy), L.ptr(w), L.ptr(dx), M, N, K, L.ptr(a_rowmap), L.ptr(a_rowscale),
                                      rows_per_batch, src_rows_per_batch, L.ptr(a_out), L.ptr(gelu_pre), L.dt(dy),
                                      L.stream()), "vsw_linear_dgrad")
+    if t0 is not None:
+        e = _esz(dy)
+        nb = (M * N * (1 + (a_out is not None)) + N * K + M * K * (1 + (gelu_pre is not None))) * e
+        PROFILER.end("linear_dgrad", t0, 2.0 * M * N * K, nb)
     return dx
 
 
@@ -163,8 +214,11 @@ def linear_wgrad(dy, x2d, M, N, K, need_bias=True, grad_dtype=None):
     db = _empty((N,), grad_dtype, dy.device) if need_bias else None
     wsb = int(L.lib().vsw_linear_wgrad_workspace(M, N, K))
     ws = _empty((max(wsb, 4),), torch.uint8, dy.device)
+    t0 = PROFILER.begin() if PROFILER is not None else None
     L.check(L.lib().vsw_linear_wgrad(L.ptr(dy), L.ptr(x2d), L.ptr(dw), L.ptr(db), M, N, K, L.dt(dy), L.dt(grad_dtype),
                                      L.ptr(ws), wsb, L.stream()), "vsw_linear_wgrad")
+    if t0 is not None:
+        PROFILER.end("linear_wgrad", t0, 2.0 * M * N * K, (M * N + M * K + N * K) * _esz(dy))
     return dw, db
 
 
@@ -172,9 +226,12 @@ def attn_fwd(qkv, table, rowcode, colcode, region, dense_mask, B_, nW, N, nH, hd
     C = nH * hd
     out = _empty((B_ * N, C), qkv.dtype, qkv.device)
     lse = _empty((B_, nH, N), torch.float32, qkv.device)
+    t0 = PROFILER.begin() if PROFILER is not None else None
     L.check(L.lib().vsw_window_attn_fwd(L.ptr(qkv), L.ptr(table), L.ptr(rowcode), L.ptr(colcode), L.ptr(region),
                                         L.ptr(dense_mask), L.ptr(out), L.ptr(lse), B_, nW, N, nH, hd, table.shape[0],
                                         float(scale), L.dt(qkv), L.stream()), "vsw_window_attn_fwd")
+    if t0 is not None:  # QK^T + PV = 4*N*N*hd flops per (window, head); q,k,v read + o written once
+        PROFILER.end("window_attn_fwd", t0, 4.0 * B_ * nH * N * N * hd, 4 * B_ * N * C * _esz(qkv))
     return out, lse
 
 
@@ -184,10 +241,13 @@ def attn_bwd(qkv, out, dout, lse, table, rowcode, colcode, region, dense_mask, B
     dtable = _empty((Lt, nH), torch.float32, qkv.device)
     wsb = int(L.lib().vsw_window_attn_bwd_workspace(B_, N, nH, hd, Lt))
     ws = _empty((max(wsb, 4),), torch.uint8, qkv.device)
+    t0 = PROFILER.begin() if PROFILER is not None else None
     L.check(L.lib().vsw_window_attn_bwd(L.ptr(qkv), L.ptr(out), L.ptr(dout), L.ptr(lse), L.ptr(table), L.ptr(rowcode),
                                         L.ptr(colcode), L.ptr(region), L.ptr(dense_mask), L.ptr(dqkv), L.ptr(dtable),
                                         B_, nW, N, nH, hd, Lt, float(scale), L.dt(qkv), L.ptr(ws), wsb, L.stream()),
             "vsw_window_attn_bwd")
+    if t0 is not None:  # dV, dP, dQ, dK = 8*N*N*hd useful flops (the S/P recompute is not counted)
+        PROFILER.end("window_attn_bwd", t0, 8.0 * B_ * nH * N * N * hd, 8 * B_ * N * nH * hd * _esz(qkv))
     return dqkv, dtable
 
 

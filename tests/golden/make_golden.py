@@ -137,7 +137,7 @@ def model_golden(vs, name):
     ref.eval()
     y = ref(x)
     torch.manual_seed(11)
-    R = torch.randn_like(y) / 64.0
+    R = torch.randn(*y.shape) / 64.0  # explicit recipe: contiguous (B,C,D,H,W) order
     (y * R).sum().backward()
     grads = {k: p.grad.detach().clone() for k, p in ref.named_parameters()}
     # oracle vs reference, checked at generation time as well

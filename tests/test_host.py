@@ -1,0 +1,110 @@
+"""CPU: host-side logic of the drop-in modules (no kernels run)."""
+import json
+import os
+
+import pytest
+import torch
+
+GOLD = os.path.join(os.path.dirname(__file__), "golden")
+
+
+@pytest.fixture(scope="module")
+def keys_gold():
+    with open(os.path.join(GOLD, "state_keys.json")) as f:
+        return json.load(f)
+
+
+@pytest.mark.parametrize("name,kw", [
+    ("swin_b", dict(embed_dim=128, num_heads=[4, 8, 16, 32])),
+    ("violet", dict(embed_dim=96, num_heads=[3, 6, 12, 24])),
+    ("swin_l_384", dict(embed_dim=192, num_heads=[6, 12, 24, 48], window_size=(8, 12, 12))),
+])
+def test_state_dict_surface_matches_reference(vsw, keys_gold, name, kw):
+    """351 entries, same key order, shapes and dtypes as the reference module."""
+    m = vsw.SwinTransformer3D(pretrained=None, depths=[2, 2, 18, 2], **kw)
+    sd = m.state_dict()
+    g = keys_gold[name]
+    assert len(sd) == g["n_entries"] == 351
+    assert sum(p.numel() for p in m.parameters()) == g["n_params"]
+    assert len(list(m.parameters())) == g["n_param_tensors"] == 327
+    assert [[k, list(v.shape), str(v.dtype)] for k, v in sd.items()] == g["entries"]
+    dp = [(b.drop_path.drop_prob if hasattr(b.drop_path, "drop_prob") else 0.0) for l in m.layers for b in l.blocks]
+    assert dp == pytest.approx(g["drop_path"])
+    assert m.norm.normalized_shape[0] == m.num_features  # model.py:13 reads this
+
+
+def test_relative_position_index_closed_form(vsw, oracle):
+    import numpy as np
+    for w in [(8, 7, 7), (8, 12, 12), (2, 3, 3), (16, 7, 7)]:
+        a = vsw.WindowAttention3D(32, w, 1).relative_position_index
+        assert a.dtype == torch.int64
+        assert np.array_equal(a.numpy(), oracle.relative_position_index(w))
+
+
+def test_get_window_size(vsw):
+    with open(os.path.join(GOLD, "index.json")) as f:
+        cases = json.load(f)["get_window_size"]
+    for c in cases:
+        ws, ss = vsw.get_window_size(tuple(c["grid"]), tuple(c["window"]), tuple(c["shift"]))
+        assert list(ws) == c["ws"] and list(ss) == c["ss"]
+    assert vsw.get_window_size((8, 4, 4), (8, 7, 7)) == (8, 4, 4)
+
+
+def test_load_state_dict_roundtrip_with_oracle_layout(vsw, oracle):
+    cfg = oracle.SwinCfg(embed_dim=32, depths=(2, 2), num_heads=(1, 2))
+    sd = oracle.make_state_dict(cfg, seed=3)
+    m = vsw.SwinTransformer3D(embed_dim=32, depths=[2, 2], num_heads=[1, 2])
+    res = m.load_state_dict(sd, strict=True)
+    assert not res.missing_keys and not res.unexpected_keys
+    for k, v in m.state_dict().items():
+        assert torch.equal(v, sd[k]), k
+
+
+def test_config_loader_presets_and_inheritance(vsw, tmp_path):
+    from importlib import import_module
+    cl = import_module("pytorch_empirical-mvm_b200.config_loader")
+    bb = cl.load_backbone_cfg("videoswin/swin_violet_patch244_window877.py")  # reference's broken path
+    assert bb["embed_dim"] == 96 and bb["num_heads"] == [3, 6, 12, 24] and tuple(bb["patch_size"]) == (2, 4, 4)
+    base = tmp_path / "base.py"
+    base.write_text("model = dict(backbone=dict(embed_dim=96, depths=[2,2,6,2], num_heads=[3,6,12,24], "
+                    "patch_size=(4,4,4), window_size=(8,7,7), patch_norm=True))\n")
+    child = tmp_path / "child.py"
+    child.write_text("_base_ = ['./base.py']\nmodel = dict(backbone=dict(patch_size=(2,4,4), embed_dim=128))\n")
+    bb = cl.load_backbone_cfg(str(child))
+    assert bb["embed_dim"] == 128 and tuple(bb["patch_size"]) == (2, 4, 4) and bb["depths"] == [2, 2, 6, 2]
+    with pytest.raises(FileNotFoundError):
+        cl.load_backbone_cfg("nope/does_not_exist.py")
+
+
+def test_factory_side_effects(vsw):
+    from types import SimpleNamespace as NS
+    a = NS(size_img=224, vis_backbone_size="violet", vis_backbone_init="2d", kinetics=400)
+    m = vsw.get_vidswin_model(a)
+    assert a.vis_backbone_init == "random" and a.vis_backbone_pretrained_weight is None  # video_swin.py:603,615
+    assert m.embed_dim == 96 and len(m.state_dict()) == 351
+
+
+def test_cpu_input_fails_loudly(vsw):
+    m = vsw.SwinTransformer3D(embed_dim=32, depths=[2], num_heads=[1])
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        m(torch.zeros(1, 3, 2, 8, 8))
+
+
+def test_unsupported_options_fail_loudly(vsw):
+    with pytest.raises(NotImplementedError):
+        vsw.SwinTransformer3D(embed_dim=32, depths=[2], num_heads=[1], drop_rate=0.1)
+    with pytest.raises(NotImplementedError):
+        vsw.SwinTransformer3D(embed_dim=32, depths=[2], num_heads=[1], attn_drop_rate=0.1)
+
+
+def test_init_weights_statistics(vsw):
+    torch.manual_seed(0)
+    m = vsw.SwinTransformer3D(embed_dim=32, depths=[2, 2], num_heads=[1, 2])
+    m.init_weights()
+    w = m.layers[1].blocks[0].mlp.fc1.weight
+    assert float(w.abs().max()) <= 2.0 and 0.015 < float(w.std()) < 0.025
+    assert float(m.layers[0].blocks[0].attn.qkv.bias.abs().max()) == 0.0
+    assert torch.all(m.norm.weight == 1) and torch.all(m.norm.bias == 0)
+    with pytest.raises(TypeError):
+        m.pretrained = 3
+        m.init_weights()

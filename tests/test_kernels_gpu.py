@@ -1,0 +1,260 @@
+"""GPU: every C-ABI kernel against a plain torch fp64/fp32 restatement of the same op on the same
+seeded inputs.  Tolerances (relative L2): fp32 1e-4 (north_star), bf16 2e-2."""
+import pytest
+import torch
+import torch.nn.functional as F
+
+from conftest import rel_l2
+
+pytestmark = pytest.mark.gpu
+TOL = {torch.float32: 1e-4, torch.bfloat16: 2e-2, torch.float16: 5e-3}
+DTYPES = [torch.float32, torch.bfloat16]
+
+
+def backends(vsw):
+    return [vsw._lib.GEMM_SIMT, vsw._lib.GEMM_AUTO]
+
+
+@pytest.fixture(autouse=True)
+def _reset_backend(vsw):
+    yield
+    vsw._lib.set_gemm_backend(vsw._lib.GEMM_AUTO)
+
+
+def rnd(*shape, dtype=torch.float32, scale=1.0, seed=None):
+    if seed is not None:
+        torch.manual_seed(seed)
+    return (torch.randn(*shape, device="cuda") * scale).to(dtype)
+
+
+# ---------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("dtype", DTYPES + [torch.float16])
+@pytest.mark.parametrize("C", [32, 96, 128, 1024, 3072])
+def test_layernorm_fwd_bwd(vsw, dtype, C):
+    VF = vsw.functional
+    torch.manual_seed(C)
+    B, T = 3, 37
+    x = rnd(B, T, C, dtype=dtype, scale=2.0) + 0.5
+    g = rnd(C, dtype=dtype) * 0.2 + 1
+    b = rnd(C, dtype=dtype) * 0.1
+    dy = rnd(B, T, C, dtype=dtype)
+    dres = rnd(B, T, C, dtype=dtype)
+    y, mean, rstd = VF.ln_fwd(x, g, b, None, B, T, T, C)
+    xr = x.double().requires_grad_(True)
+    gr, br = g.double().requires_grad_(True), b.double().requires_grad_(True)
+    yr = F.layer_norm(xr, (C,), gr, br, 1e-5)
+    assert rel_l2(y, yr) < TOL[dtype]
+    assert rel_l2(mean, x.double().mean(-1).reshape(-1)) < 1e-5
+    yr.backward(dy.double())
+    dx, dg, db = VF.ln_bwd(dy, x, g, mean, rstd, None, dres, B, T, T, C)
+    assert rel_l2(dx, xr.grad + dres.double()) < TOL[dtype]
+    assert rel_l2(dg, gr.grad) < 1e-4 and rel_l2(db, br.grad) < 1e-4
+
+
+@pytest.mark.parametrize("dtype", DTYPES)
+def test_layernorm_gather_with_padding(vsw, oracle, dtype):
+    """norm1 + zero-pad-after-norm + roll + window_partition as ONE gather-LN kernel, and its transpose"""
+    VF = vsw.functional
+    grid, window, shift = (4, 11, 13), (8, 7, 7), (4, 3, 3)
+    B, C = 2, 64
+    T = grid[0] * grid[1] * grid[2]
+    plan = VF.window_plan(grid, window, shift, "cuda")
+    R = plan.nW * plan.N
+    x = rnd(B, T, C, dtype=dtype, seed=1)
+    g, b = rnd(C, dtype=dtype) * 0.2 + 1, rnd(C, dtype=dtype) * 0.1
+    y, mean, rstd = VF.ln_fwd(x, g, b, plan.gather, B, T, R, C)
+    n = F.layer_norm(x.double(), (C,), g.double(), b.double(), 1e-5)
+    n = torch.cat([n, n.new_zeros(B, 1, C)], 1)
+    ref = n[:, plan.gather.long()]  # -1 -> the appended zero row
+    assert rel_l2(y, ref) < TOL[dtype]
+    assert float(y[:, plan.gather < 0].abs().max()) == 0.0
+    dy = rnd(B, R, C, dtype=dtype)
+    dres = rnd(B, T, C, dtype=dtype)
+    xr = x.double().requires_grad_(True)
+    gr, br = g.double().requires_grad_(True), b.double().requires_grad_(True)
+    n = F.layer_norm(xr, (C,), gr, br, 1e-5)
+    n = torch.cat([n, n.new_zeros(B, 1, C)], 1)[:, plan.gather.long()]
+    n.backward(dy.double())
+    dx, dg, db = VF.ln_bwd(dy, x, g, mean, rstd, plan.gather, dres, B, T, R, C)
+    assert rel_l2(dx, xr.grad + dres.double()) < TOL[dtype]
+    assert rel_l2(dg, gr.grad) < 1e-4 and rel_l2(db, br.grad) < 1e-4
+
+
+# ---------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("dtype", DTYPES)
+@pytest.mark.parametrize("M,N,K", [(392, 96, 32), (1000, 384, 128), (777, 128, 512), (300, 2048, 512), (64, 24, 96)])
+@pytest.mark.parametrize("backend", [1, 0])
+def test_linear_fwd_epilogues(vsw, dtype, M, N, K, backend):
+    VF, L = vsw.functional, vsw._lib
+    L.set_gemm_backend(backend)
+    x, w, b = rnd(M, K, dtype=dtype, seed=M + N), rnd(N, K, dtype=dtype, scale=0.05), rnd(N, dtype=dtype, scale=0.1)
+    ref = x.double() @ w.double().t() + b.double()
+    y = VF.linear_fwd(x, w, b, M, N, K)
+    assert rel_l2(y, ref) < TOL[dtype]
+    y = VF.linear_fwd(x, w, None, M, N, K)
+    assert rel_l2(y, x.double() @ w.double().t()) < TOL[dtype]
+    u = torch.empty(M, N, dtype=dtype, device="cuda")
+    y = VF.linear_fwd(x, w, b, M, N, K, epi=L.EPI_GELU, aux_out=u)
+    assert rel_l2(u, ref) < TOL[dtype] and rel_l2(y, F.gelu(ref)) < TOL[dtype]
+    res = rnd(M, N, dtype=dtype)
+    y = VF.linear_fwd(x, w, b, M, N, K, epi=L.EPI_RESIDUAL, res=res, rows_per_batch=M, dst_rows_per_batch=M)
+    assert rel_l2(y, res.double() + ref) < TOL[dtype]
+
+
+@pytest.mark.parametrize("dtype", DTYPES)
+@pytest.mark.parametrize("backend", [1, 0])
+def test_linear_scatter_residual_epilogue_and_its_transpose(vsw, dtype, backend):
+    """proj + window_reverse + roll-back + crop + drop-path + residual in one epilogue; the dgrad
+    gathers the same rows"""
+    VF, L = vsw.functional, vsw._lib
+    L.set_gemm_backend(backend)
+    grid, window, shift = (4, 11, 13), (8, 7, 7), (4, 3, 3)
+    plan = VF.window_plan(grid, window, shift, "cuda")
+    B, C, T, R = 2, 64, 4 * 11 * 13, plan.nW * plan.N
+    o = rnd(B * R, C, dtype=dtype, seed=5)
+    w, b = rnd(C, C, dtype=dtype, scale=0.1), rnd(C, dtype=dtype, scale=0.1)
+    res = rnd(B, T, C, dtype=dtype)
+    scale = torch.tensor([0.0, 1.25], device="cuda")
+    y = VF.linear_fwd(o, w, b, B * R, C, C, epi=L.EPI_RESIDUAL, res=res, rowmap=plan.gather, rowscale=scale,
+                      rows_per_batch=R, dst_rows_per_batch=T, out_rows=B * T).view(B, T, C)
+    lin = (o.double() @ w.double().t() + b.double()).view(B, R, C)
+    ref = res.double().clone()
+    gm = plan.gather.long()
+    ok = gm >= 0
+    ref[:, gm[ok]] += lin[:, ok] * scale.double().view(B, 1, 1)
+    assert rel_l2(y, ref) < TOL[dtype]
+    dy = rnd(B, T, C, dtype=dtype)
+    a_out = torch.empty(B * R, C, dtype=dtype, device="cuda")
+    dx = VF.linear_dgrad(dy, w, B * R, C, C, a_rowmap=plan.gather, a_rowscale=scale, rows_per_batch=R,
+                         src_rows_per_batch=T, a_out=a_out)
+    a_ref = torch.zeros(B, R, C, dtype=torch.float64, device="cuda")
+    a_ref[:, ok] = dy.double()[:, gm[ok]] * scale.double().view(B, 1, 1)
+    assert rel_l2(a_out, a_ref.view(B * R, C)) < TOL[dtype]
+    assert rel_l2(dx, a_ref.view(B * R, C) @ w.double()) < TOL[dtype]
+
+
+@pytest.mark.parametrize("dtype", DTYPES)
+@pytest.mark.parametrize("M,N,K", [(392, 96, 32), (3000, 384, 128), (1111, 128, 512), (4096, 512, 2048), (50, 24, 96)])
+@pytest.mark.parametrize("backend", [1, 0])
+def test_linear_dgrad_wgrad(vsw, dtype, M, N, K, backend):
+    VF, L = vsw.functional, vsw._lib
+    L.set_gemm_backend(backend)
+    dy, w, x = rnd(M, N, dtype=dtype, seed=K), rnd(N, K, dtype=dtype, scale=0.05), rnd(M, K, dtype=dtype)
+    u = rnd(M, K, dtype=dtype)
+    dx = VF.linear_dgrad(dy, w, M, N, K)
+    assert rel_l2(dx, dy.double() @ w.double()) < TOL[dtype]
+    dxg = VF.linear_dgrad(dy, w, M, N, K, gelu_pre=u)
+    ud = u.double().requires_grad_(True)
+    F.gelu(ud).backward(dy.double() @ w.double())
+    assert rel_l2(dxg, ud.grad) < TOL[dtype]
+    dw, db = VF.linear_wgrad(dy, x, M, N, K)
+    assert rel_l2(dw, dy.double().t() @ x.double()) < TOL[dtype]
+    assert rel_l2(db, dy.double().sum(0)) < TOL[dtype]
+    dw32, _ = VF.linear_wgrad(dy, x, M, N, K, need_bias=False, grad_dtype=torch.float32)
+    assert dw32.dtype == torch.float32 and rel_l2(dw32, dy.double().t() @ x.double()) < 1e-4
+
+
+# ---------------------------------------------------------------------------------------------
+def attn_reference(qkv, table, rel_index, mask, nW, nH, scale):
+    """plain torch restatement of video_swin.py:149-169 in fp64"""
+    B_, N, _, _, hd = qkv.shape
+    q, k, v = [qkv[:, :, i].transpose(1, 2).double() for i in range(3)]
+    s = (q * scale) @ k.transpose(-1, -2)
+    bias = table.double()[rel_index[:N, :N].reshape(-1)].view(N, N, nH).permute(2, 0, 1)
+    s = s + bias[None]
+    if mask is not None:
+        s = (s.view(B_ // nW, nW, nH, N, N) + mask.double()[None, :, None]).view(B_, nH, N, N)
+    p = torch.softmax(s, -1)
+    return (p @ v).transpose(1, 2).reshape(B_, N, nH * hd), torch.logsumexp(s, -1)
+
+
+@pytest.mark.parametrize("dtype", DTYPES)
+@pytest.mark.parametrize("geom", [((8, 14, 14), (8, 7, 7), (0, 3, 3), 3), ((8, 7, 7), (8, 7, 7), (0, 0, 0), 2),
+                                  ((4, 12, 12), (4, 6, 6), (0, 3, 3), 4), ((16, 7, 7), (8, 7, 7), (4, 0, 0), 1),
+                                  ((8, 4, 4), (8, 7, 7), (4, 3, 3), 2)])
+@pytest.mark.parametrize("backend", [1, 0])
+def test_window_attention_fwd_bwd(vsw, oracle, dtype, geom, backend):
+    VF, L = vsw.functional, vsw._lib
+    L.set_gemm_backend(backend)
+    grid, window, shift, nH = geom
+    hd, B = 32, 2
+    plan = VF.window_plan(grid, window, shift, "cuda")
+    nW, N = plan.nW, plan.N
+    B_ = B * nW
+    torch.manual_seed(nH)
+    qkv = rnd(B_, N, 3, nH, hd, dtype=dtype)
+    Lt = (2 * window[0] - 1) * (2 * window[1] - 1) * (2 * window[2] - 1)
+    table = rnd(Lt, nH, dtype=dtype, scale=0.5)
+    rel_index = torch.from_numpy(oracle.relative_position_index(window)).cuda()
+    rowcode, colcode = VF.bias_codes(rel_index, N)
+    mask = vsw.compute_mask(*plan.pgrid, plan.ws, plan.ss, "cuda") if plan.shifted else None
+    qr = qkv.double().requires_grad_(True)
+    tr = table.double().requires_grad_(True)
+    oref, lref = attn_reference(qr, tr, rel_index, mask, nW, nH, hd ** -0.5)
+    out, lse = VF.attn_fwd(qkv.view(B_ * N, -1), table, rowcode, colcode, plan.region, None, B_, nW, N, nH, hd, hd ** -0.5)
+    assert rel_l2(out.view(B_, N, -1), oref) < TOL[dtype]
+    assert rel_l2(lse, lref) < (1e-5 if dtype == torch.float32 else 1e-2)
+    if plan.shifted:  # the dense-mask path must agree with the region-id path
+        L.set_gemm_backend(L.GEMM_SIMT)
+        out2, _ = VF.attn_fwd(qkv.view(B_ * N, -1), table, rowcode, colcode, None, mask.to(dtype), B_, nW, N, nH, hd, hd ** -0.5)
+        assert rel_l2(out2.view(B_, N, -1), oref) < TOL[dtype]
+        L.set_gemm_backend(backend)
+    dout = rnd(B_, N, nH * hd, dtype=dtype)
+    oref.backward(dout.double())
+    dqkv, dtab = VF.attn_bwd(qkv.view(B_ * N, -1), out, dout.view(B_ * N, -1), lse, table, rowcode, colcode, plan.region,
+                             None, B_, nW, N, nH, hd, hd ** -0.5)
+    dq = dqkv.view(B_, N, 3, nH, hd)
+    for i, nm in enumerate("qkv"):
+        assert rel_l2(dq[:, :, i], qr.grad[:, :, i]) < TOL[dtype] * (1 if dtype == torch.float32 else 1.5), nm
+    assert rel_l2(dtab, tr.grad) < TOL[dtype] * (1 if dtype == torch.float32 else 1.5)
+
+
+# ---------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("dtype", DTYPES)
+@pytest.mark.parametrize("shape", [(2, 3, 8, 32, 32), (1, 3, 4, 30, 27), (2, 3, 3, 8, 8)])
+def test_patch_embed(vsw, dtype, shape):
+    VF = vsw.functional
+    B, Cin, D, H, W = shape
+    E, patch = 64, (2, 4, 4)
+    x = rnd(*shape, seed=3)  # clips arrive in fp32
+    w, b = rnd(E, Cin, *patch, dtype=dtype, scale=0.1), rnd(E, dtype=dtype, scale=0.1)
+    g, be = rnd(E, dtype=dtype) * 0.2 + 1, rnd(E, dtype=dtype) * 0.1
+    xr = x.double().requires_grad_(True)
+    wr, br = w.double().requires_grad_(True), b.double().requires_grad_(True)
+    xp = F.pad(xr, (0, (-W) % 4, 0, (-H) % 4, 0, 1))
+    yr = F.conv3d(xp, wr, br, stride=(1, 4, 4)).permute(0, 2, 3, 4, 1)
+    yr = F.layer_norm(yr, (E,), g.double(), be.double(), 1e-5)
+    xg = x.clone().requires_grad_(True)
+    wg, bg = w.clone().requires_grad_(True), b.clone().requires_grad_(True)
+    y = VF.patch_embed(xg, wg, bg, g, be, patch)
+    assert rel_l2(y.view(yr.shape), yr) < TOL[dtype]
+    dy = rnd(*yr.shape, dtype=dtype)
+    yr.backward(dy.double())
+    y.backward(dy.view(y.shape))
+    assert rel_l2(wg.grad, wr.grad) < TOL[dtype]
+    assert rel_l2(bg.grad, br.grad) < TOL[dtype]
+    assert rel_l2(xg.grad, xr.grad) < TOL[dtype]
+
+
+@pytest.mark.parametrize("dtype", DTYPES)
+@pytest.mark.parametrize("grid", [(2, 8, 8), (3, 7, 9)])
+def test_patch_merge(vsw, dtype, grid):
+    VF = vsw.functional
+    D, H, W = grid
+    B, C = 2, 32
+    x = rnd(B, D, H, W, C, dtype=dtype, seed=9)
+    g, be = rnd(4 * C, dtype=dtype) * 0.2 + 1, rnd(4 * C, dtype=dtype) * 0.1
+    w = rnd(2 * C, 4 * C, dtype=dtype, scale=0.1)
+    xr = x.double().requires_grad_(True)
+    gr, ber, wr = [t.double().requires_grad_(True) for t in (g, be, w)]
+    xp = F.pad(xr, (0, 0, 0, W % 2, 0, H % 2))
+    cat = torch.cat([xp[:, :, 0::2, 0::2], xp[:, :, 1::2, 0::2], xp[:, :, 0::2, 1::2], xp[:, :, 1::2, 1::2]], -1)
+    yr = F.layer_norm(cat, (4 * C,), gr, ber, 1e-5) @ wr.t()
+    xs = [t.clone().requires_grad_(True) for t in (x, g, be, w)]
+    y = VF.patch_merge(xs[0].view(B, D * H * W, C), xs[1], xs[2], xs[3], grid)
+    assert rel_l2(y.view(yr.shape), yr) < TOL[dtype]
+    dy = rnd(*yr.shape, dtype=dtype)
+    yr.backward(dy.double())
+    y.backward(dy.view(y.shape))
+    for got, ref, nm in zip(xs, (xr, gr, ber, wr), ("x", "gamma", "beta", "w")):
+        assert rel_l2(got.grad, ref.grad) < TOL[dtype], nm

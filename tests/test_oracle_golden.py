@@ -1,0 +1,100 @@
+"""CPU: pin the oracle (oracle/swin3d_oracle.py) against the golden vectors that
+tests/golden/make_golden.py produced from the UNMODIFIED reference module."""
+import hashlib
+import json
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from conftest import rel_l2
+
+GOLD = os.path.join(os.path.dirname(__file__), "golden")
+
+
+def sha16(arr) -> str:
+    t = torch.as_tensor(arr).contiguous()
+    return hashlib.sha256(t.numpy().tobytes()).hexdigest()[:16]
+
+
+@pytest.fixture(scope="module")
+def index_gold():
+    with open(os.path.join(GOLD, "index.json")) as f:
+        return json.load(f)
+
+
+def test_survey_known_answers(index_gold):
+    """the SURVEY section 8c table, which was produced independently of make_golden.py"""
+    r = index_gold["relative_position_index"]["8x7x7"]
+    assert (r["sum"], r["max"], r["c00"], r["c01"], r["c0m1"], r["cm10"], r["sha"]) == \
+           (194692288, 2534, 1267, 1266, 0, 2534, "617532ad86365ae6")
+    assert index_gold["relative_position_index"]["8x12x12"]["sha"] == "779ff0bed9d27d0a"
+    assert index_gold["relative_position_index"]["16x7x7"]["sha"] == "8fcb73f0949d1851"
+    m = index_gold["compute_mask"]
+    assert m["g8x56x56_w8x7x7_s0x3x3"]["sha"] == "6dc7dfe987078f4b" and m["g8x56x56_w8x7x7_s0x3x3"]["nonzero"] == 1167360
+    assert m["g8x28x28_w8x7x7_s0x3x3"]["sha"] == "dd58cbc13cfee521"
+    assert m["g8x14x14_w8x7x7_s0x3x3"]["sha"] == "e8feda2b6042e292"
+    assert m["g8x7x7_w8x7x7_s0x0x0"]["sha"] == "21369b918a617d97"
+    assert m["g8x96x96_w8x12x12_s0x6x6"]["sha"] == "7a80a90c974ab8e8"
+    assert m["g16x56x56_w8x7x7_s4x3x3"]["sha"] == "d35f8c6cb1adbf69"
+    assert m["g4x56x56_w4x7x7_s0x3x3"]["sha"] == "27587be74dc59681"
+    assert index_gold["gather_map"]["g8x14x14_w8x7x7_s0x3x3"]["sha"] == "4b59eb8b47ac5cc2"
+
+
+def test_oracle_rel_pos_index(oracle, index_gold):
+    for key, g in index_gold["relative_position_index"].items():
+        w = tuple(int(v) for v in key.split("x"))
+        idx = oracle.relative_position_index(w)
+        assert list(idx.shape) == g["shape"]
+        assert int(idx.sum()) == g["sum"] and int(idx.max()) == g["max"] and int(idx.min()) == g["min"]
+        assert sha16(idx.astype(np.int64)) == g["sha"], key
+
+
+def test_oracle_mask_and_gather(oracle, index_gold):
+    for key, g in index_gold["compute_mask"].items():
+        pg, ws, ss = tuple(g["grid"]), tuple(g["window"]), tuple(g["shift"])
+        m = oracle.shift_mask(pg, ws, ss)
+        assert list(m.shape) == g["shape"]
+        assert int((m != 0).sum()) == g["nonzero"]
+        assert sha16(m.float()) == g["sha"], key
+        gm = oracle.window_gather_map(pg, ws, ss)
+        gg = index_gold["gather_map"][key]
+        assert gm[0, :5].tolist() == gg["first5"] and gm[-1, -3:].tolist() == gg["last3"]
+        assert sha16(gm.astype(np.int64)) == gg["sha"], key
+        # reverse o roll-back is the identity: the map is a permutation of the padded grid
+        assert sorted(gm.reshape(-1).tolist()) == list(range(pg[0] * pg[1] * pg[2]))
+
+
+def test_oracle_get_window_size(oracle, index_gold):
+    for c in index_gold["get_window_size"]:
+        ws, ss = oracle.effective_window(tuple(c["grid"]), tuple(c["window"]), tuple(c["shift"]))
+        assert list(ws) == c["ws"] and list(ss) == c["ss"]
+
+
+@pytest.mark.parametrize("name", ["tiny_a", "tiny_b", "tiny_c", "tiny_d"])
+def test_oracle_tiny_models(oracle, name):
+    """forward + every parameter gradient of small SwinTransformer3D configs vs the reference's own
+    outputs (fp32 round-off level: both sides are fp32 CPU)."""
+    fx = torch.load(os.path.join(GOLD, f"{name}.pt"), weights_only=False)
+    kw = fx["kwargs"]
+    cfg = oracle.SwinCfg(embed_dim=kw["embed_dim"], depths=tuple(kw["depths"]), num_heads=tuple(kw["num_heads"]),
+                         window_size=tuple(kw["window_size"]))
+    sd = oracle.make_state_dict(cfg, seed=fx["sd_seed"], ln_jitter=fx["ln_jitter"])
+    assert list(sd.keys()) == fx["state_keys"]
+    torch.manual_seed(fx["x_seed"])
+    x = torch.randn(*fx["x_shape"])
+    assert sha16(x) == fx["x_sha"], "torch CPU RNG changed: regenerate goldens"
+    y_ref = fx["y"]
+    torch.manual_seed(fx["R_seed"])
+    R = torch.randn(*y_ref.shape) * fx["R_scale"]
+    y, grads = oracle.forward_backward(sd, x, cfg, R)
+    assert rel_l2(y, y_ref) < 2e-6
+    g = torch.Generator().manual_seed(99)
+    for k, (s, n, p) in fx["grad_stats"].items():
+        r = torch.randn(grads[k].shape, generator=g, dtype=torch.float64)
+        v = grads[k].double()
+        assert abs(float(v.norm()) - n) <= 2e-5 * n + 1e-9, k
+        assert abs(float((v * r).sum()) - p) <= 5e-5 * n * float(r.norm()) / max(1.0, v.numel() ** 0.5) + 1e-7, k
+    for k, gref in fx["grad_full"].items():
+        assert rel_l2(grads[k], gref) < 2e-5, k
