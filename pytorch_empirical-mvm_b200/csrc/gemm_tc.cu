@@ -1,15 +1,439 @@
-// tcgen05 GEMM family -- placeholder until the TMA/TMEM kernels land (returns UNSUPPORTED so that
-// VSW_GEMM_AUTO uses the CUDA-core kernels and VSW_GEMM_TCGEN05 fails loudly).
+// tcgen05 / TMEM / TMA bf16 GEMM family for sm_100a.
+//
+// One persistent, warp-specialised kernel template covers the three GEMM forms of a Linear layer:
+//   forward  y  = x  w^T        A = x  (K-major),  B = w  (K-major)
+//   dgrad    dx = dy w          A = dy (K-major),  B = w  (MN-major: w is (N,K) row-major, reduced over N)
+//   wgrad    dw = dy^T x        A = dy (MN-major), B = x  (MN-major), reduced over the M rows, split across
+//                               CTAs into fp32 partials + fixed-order second pass (deterministic)
+// Roles (10 warps, 1 CTA/SM): warp 0 = TMA producer, warp 1 = MMA issuer (one elected lane) + TMEM owner,
+// warps 2..9 = epilogue (TMEM -> registers -> fused epilogue -> global).  The accumulator is double-buffered
+// in TMEM (2 x BN fp32 columns) so the epilogue of tile i overlaps the MMAs of tile i+1; operands flow
+// through a STAGES-deep TMA ring with 128-byte swizzle (no bank conflicts, no padding).
+// Fused epilogues: bias | bias+GELU(+pre-activation) | bias+drop-path scale+row scatter+residual |
+//                  dgrad (* GELU') | fp32 partial.
+#include <cudaTypedefs.h>
+#include <mutex>
+#include "gemm_simt.cuh"
 #include "gemm_tc.cuh"
+#include "tc_common.cuh"
 
 namespace vsw {
 
-int tc_linear(const TcLinearArgs&, cudaStream_t) { set_error("tcgen05 linear: not built"); return VSW_ERR_UNSUPPORTED; }
-int tc_dgrad(const TcDgradArgs&, cudaStream_t) { set_error("tcgen05 dgrad: not built"); return VSW_ERR_UNSUPPORTED; }
-size_t tc_wgrad_workspace(int, int, int) { return 0; }
-int tc_wgrad(const void*, const void*, void*, int, int, int, int, void*, size_t, cudaStream_t) {
-    set_error("tcgen05 wgrad: not built");
-    return VSW_ERR_UNSUPPORTED;
+// ---------------------------------------------------------------------------------------------
+// host: tensor map encoder
+// ---------------------------------------------------------------------------------------------
+static PFN_cuTensorMapEncodeTiled_v12000 get_encode_fn() {
+    static PFN_cuTensorMapEncodeTiled_v12000 fn = nullptr;
+    static std::once_flag once;
+    std::call_once(once, [] {
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+            q == cudaDriverEntryPointSuccess)
+            fn = (PFN_cuTensorMapEncodeTiled_v12000)p;
+    });
+    return fn;
+}
+
+bool make_tmap_2d_bf16(CUtensorMap* out, const void* base, uint64_t rows, uint64_t cols, uint64_t row_stride_elems,
+                       uint32_t box_rows, uint32_t box_cols) {
+    auto fn = get_encode_fn();
+    if (!fn) { set_error("cuTensorMapEncodeTiled entry point not available"); return false; }
+    cuuint64_t gdim[2] = {cols, rows};
+    cuuint64_t gstride[1] = {row_stride_elems * 2};
+    cuuint32_t box[2] = {box_cols, box_rows};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = fn(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), gdim, gstride, box, estr,
+                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+        set_error("cuTensorMapEncodeTiled failed (%d) rows=%llu cols=%llu stride=%llu box=%ux%u", (int)r,
+                  (unsigned long long)rows, (unsigned long long)cols, (unsigned long long)row_stride_elems, box_rows,
+                  box_cols);
+        return false;
+    }
+    return true;
+}
+
+// ---------------------------------------------------------------------------------------------
+// kernel
+// ---------------------------------------------------------------------------------------------
+namespace {
+
+constexpr int BM = 128, BK = 64;
+constexpr int A_BYTES = BM * BK * 2;  // 16 KB
+constexpr int NUM_EPI_WARPS = 8;
+constexpr int NUM_THREADS = 64 + NUM_EPI_WARPS * 32;
+
+enum TcEpi { TE_BIAS = 0, TE_GELU = 1, TE_RESIDUAL = 2, TE_DGRAD = 3, TE_PARTIAL = 4 };
+
+struct TcParams {
+    int M, N, K;                 // output M x N, reduction length K
+    int n_tiles_m, n_tiles_n, splits, k_per_split;
+    int epi;
+    const __nv_bfloat16* bias; __nv_bfloat16* out; __nv_bfloat16* aux_out; const __nv_bfloat16* res;
+    const int32_t* rowmap; const float* rowscale; int rows_per_batch, dst_rows_per_batch;
+    const __nv_bfloat16* gelu_pre; float* partial;
+    long long ldc;
+};
+
+// erf via Abramowitz-Stegun 7.1.26 (|err| <= 1.5e-7): 1 rcp + 1 ex2 + 6 fma instead of erff's branchy polynomial
+__device__ __forceinline__ void gelu_terms(float x, float& cdf, float& pdf) {
+    const float z = fabsf(x) * 0.70710678118654752f;
+    const float t = __fdividef(1.0f, fmaf(0.3275911f, z, 1.0f));
+    const float e = __expf(-z * z);  // = exp(-x^2/2)
+    float poly = fmaf(1.061405429f, t, -1.453152027f);
+    poly = fmaf(poly, t, 1.421413741f);
+    poly = fmaf(poly, t, -0.284496736f);
+    poly = fmaf(poly, t, 0.254829592f);
+    const float erfa = 1.0f - poly * t * e;              // erf(|x|/sqrt2)
+    cdf = 0.5f * (1.0f + copysignf(erfa, x));
+    pdf = 0.39894228040143268f * e;
+}
+__device__ __forceinline__ float gelu_fast(float x) { float c, p; gelu_terms(x, c, p); return x * c; }
+__device__ __forceinline__ float gelu_grad_fast(float x) { float c, p; gelu_terms(x, c, p); return fmaf(x, p, c); }
+
+__device__ __forceinline__ void ld8(const __nv_bfloat16* p, float (&o)[8]) {
+    const uint4 u = __ldg(reinterpret_cast<const uint4*>(p));
+    float2 a = tc::unpack_bf16(u.x), b = tc::unpack_bf16(u.y), c = tc::unpack_bf16(u.z), d = tc::unpack_bf16(u.w);
+    o[0] = a.x; o[1] = a.y; o[2] = b.x; o[3] = b.y; o[4] = c.x; o[5] = c.y; o[6] = d.x; o[7] = d.y;
+}
+__device__ __forceinline__ void st8(__nv_bfloat16* p, const float (&v)[8]) {
+    uint4 u;
+    u.x = tc::pack_bf16(v[0], v[1]); u.y = tc::pack_bf16(v[2], v[3]);
+    u.z = tc::pack_bf16(v[4], v[5]); u.w = tc::pack_bf16(v[6], v[7]);
+    *reinterpret_cast<uint4*>(p) = u;
+}
+
+template <int BN, bool A_MN, bool B_MN, int STAGES>
+__global__ void __launch_bounds__(NUM_THREADS, 1)
+tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const TcParams p) {
+    constexpr int B_BYTES = BN * BK * 2;
+    constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+    constexpr uint32_t TMEM_COLS = 2 * BN;  // power of two for BN in {64,128,256}
+    constexpr uint32_t IDESC = tc::idesc_bf16(BM, BN, A_MN ? 1 : 0, B_MN ? 1 : 0);
+
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    uint64_t* full = reinterpret_cast<uint64_t*>(smem + STAGES * STAGE_BYTES);
+    uint64_t* empty = full + STAGES;
+    uint64_t* tfull = empty + STAGES;
+    uint64_t* tempty = tfull + 2;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int tiles = p.n_tiles_m * p.n_tiles_n;
+    const int total = tiles * p.splits;
+
+    if (warp == 0 && lane == 0) {
+        tc::prefetch_tmap(&tmA);
+        tc::prefetch_tmap(&tmB);
+        for (int s = 0; s < STAGES; ++s) { tc::mbar_init(&full[s], 1); tc::mbar_init(&empty[s], 1); }
+        for (int a = 0; a < 2; ++a) { tc::mbar_init(&tfull[a], 1); tc::mbar_init(&tempty[a], NUM_EPI_WARPS); }
+        tc::fence_barrier_init();
+    }
+    if (warp == 1) tc::tmem_alloc(tmem_slot, TMEM_COLS);
+    tc::tc_fence_before();
+    __syncthreads();
+    tc::tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        // ================= TMA producer =================
+        if (lane == 0) {
+            int stage = 0; uint32_t phase = 0;
+            for (int w = blockIdx.x; w < total; w += gridDim.x) {
+                const int split = w / tiles, t = w - split * tiles;
+                const int m0 = (t / p.n_tiles_n) * BM, n0 = (t % p.n_tiles_n) * BN;
+                const int kbeg = split * p.k_per_split;
+                const int kend = min(p.K, kbeg + p.k_per_split);
+                for (int k0 = kbeg; k0 < kend; k0 += BK) {
+                    tc::mbar_wait(&empty[stage], phase ^ 1);
+                    tc::mbar_expect_tx(&full[stage], STAGE_BYTES);
+                    uint8_t* sA = smem + stage * STAGE_BYTES;
+                    uint8_t* sB = sA + A_BYTES;
+                    if (!A_MN) {
+                        tc::tma_load_2d(&tmA, &full[stage], sA, k0, m0);          // box 64(k) x 128(m)
+                    } else {
+#pragma unroll
+                        for (int j = 0; j < BM / 64; ++j)                          // box 64(m) x 64(k)
+                            tc::tma_load_2d(&tmA, &full[stage], sA + j * 8192, m0 + 64 * j, k0);
+                    }
+                    if (!B_MN) {
+                        tc::tma_load_2d(&tmB, &full[stage], sB, k0, n0);          // box 64(k) x BN(n)
+                    } else {
+#pragma unroll
+                        for (int j = 0; j < BN / 64; ++j)                          // box 64(n) x 64(k)
+                            tc::tma_load_2d(&tmB, &full[stage], sB + j * 8192, n0 + 64 * j, k0);
+                    }
+                    if (++stage == STAGES) { stage = 0; phase ^= 1; }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ================= MMA issuer =================
+        if (lane == 0) {
+            int stage = 0; uint32_t phase = 0;
+            int acc = 0; uint32_t acc_phase = 0;
+            for (int w = blockIdx.x; w < total; w += gridDim.x) {
+                const int split = w / tiles;
+                const int kbeg = split * p.k_per_split;
+                const int kend = min(p.K, kbeg + p.k_per_split);
+                tc::mbar_wait(&tempty[acc], acc_phase ^ 1);
+                tc::tc_fence_after();
+                const uint32_t d_tmem = tmem_base + acc * BN;
+                uint32_t accumulate = 0;
+                for (int k0 = kbeg; k0 < kend; k0 += BK) {
+                    tc::mbar_wait(&full[stage], phase);
+                    tc::tc_fence_after();
+                    const uint32_t aaddr = tc::smem_u32(smem + stage * STAGE_BYTES);
+                    const uint32_t baddr = aaddr + A_BYTES;
+#pragma unroll
+                    for (int k = 0; k < BK / 16; ++k) {
+                        const uint64_t ad = A_MN ? tc::smem_desc_sw128(aaddr + k * 2048, 8192, 1024)
+                                                 : tc::smem_desc_sw128(aaddr + k * 32, 0, 1024);
+                        const uint64_t bd = B_MN ? tc::smem_desc_sw128(baddr + k * 2048, 8192, 1024)
+                                                 : tc::smem_desc_sw128(baddr + k * 32, 0, 1024);
+                        tc::umma_bf16(d_tmem, ad, bd, IDESC, accumulate);
+                        accumulate = 1;
+                    }
+                    tc::umma_commit(&empty[stage]);  // smem slot reusable once these MMAs retire
+                    if (++stage == STAGES) { stage = 0; phase ^= 1; }
+                }
+                tc::umma_commit(&tfull[acc]);        // accumulator complete -> epilogue
+                if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+            }
+        }
+    } else {
+        // ================= epilogue warps =================
+        const int q = warp & 3;                 // TMEM lane quadrant this warp may access
+        const int half = (warp - 2) >> 2;       // which interleaved 32-column chunks it owns
+        int acc = 0; uint32_t acc_phase = 0;
+        for (int w = blockIdx.x; w < total; w += gridDim.x) {
+            const int split = w / tiles, t = w - split * tiles;
+            const int m0 = (t / p.n_tiles_n) * BM, n0 = (t % p.n_tiles_n) * BN;
+            tc::mbar_wait(&tfull[acc], acc_phase);
+            tc::tc_fence_after();
+            const int row = m0 + q * 32 + lane;
+            const bool row_in = row < p.M;
+            long long drow = row;
+            float rsc = 1.f;
+            bool row_ok = row_in;
+            if (p.epi == TE_RESIDUAL && row_in) {
+                const int b = row / p.rows_per_batch;
+                const int r = row - b * p.rows_per_batch;
+                int d = r;
+                if (p.rowmap) { d = __ldg(p.rowmap + r); row_ok = d >= 0; }
+                drow = (long long)b * p.dst_rows_per_batch + d;
+                if (p.rowscale) rsc = __ldg(p.rowscale + b);
+            }
+#pragma unroll 1
+            for (int c = half; c < BN / 32; c += 2) {
+                uint32_t r32[32];
+                __syncwarp();
+                tc::tmem_ld_32x32(tmem_base + acc * BN + c * 32 + ((uint32_t)(q * 32) << 16), r32);
+                tc::tmem_ld_wait();
+                const int col0 = n0 + c * 32;
+                if (row_ok) {
+#pragma unroll
+                    for (int g = 0; g < 4; ++g) {
+                        const int col = col0 + g * 8;
+                        if (col < p.N) {
+                            float v[8];
+#pragma unroll
+                            for (int e = 0; e < 8; ++e) v[e] = __uint_as_float(r32[g * 8 + e]);
+                            if (p.epi == TE_PARTIAL) {
+                                float* dst = p.partial + ((long long)split * p.M + row) * p.N + col;
+                                *reinterpret_cast<float4*>(dst) = make_float4(v[0], v[1], v[2], v[3]);
+                                *reinterpret_cast<float4*>(dst + 4) = make_float4(v[4], v[5], v[6], v[7]);
+                            } else {
+                                if (p.bias) {
+                                    float bb[8];
+                                    ld8(p.bias + col, bb);
+#pragma unroll
+                                    for (int e = 0; e < 8; ++e) v[e] += bb[e];
+                                }
+                                const long long o = drow * p.ldc + col;
+                                if (p.epi == TE_GELU) {
+                                    if (p.aux_out) st8(p.aux_out + o, v);
+#pragma unroll
+                                    for (int e = 0; e < 8; ++e) v[e] = gelu_fast(v[e]);
+                                } else if (p.epi == TE_RESIDUAL) {
+                                    float rr[8];
+                                    ld8(p.res + o, rr);
+#pragma unroll
+                                    for (int e = 0; e < 8; ++e) v[e] = fmaf(rsc, v[e], rr[e]);
+                                } else if (p.epi == TE_DGRAD) {
+                                    if (p.gelu_pre) {
+                                        float u[8];
+                                        ld8(p.gelu_pre + o, u);
+#pragma unroll
+                                        for (int e = 0; e < 8; ++e) v[e] *= gelu_grad_fast(u[e]);
+                                    }
+                                }
+                                st8(p.out + o, v);
+                            }
+                        }
+                    }
+                }
+            }
+            tc::tc_fence_before();
+            __syncwarp();
+            if (lane == 0) tc::mbar_arrive(&tempty[acc]);
+            if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+        }
+    }
+
+    tc::tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        tc::tc_fence_after();
+        tc::tmem_dealloc(tmem_base, TMEM_COLS);
+    }
+}
+
+// rows gather + per-batch scale:  out[m,:] = scale[b] * in[b*src_rows + map[r], :]  (zero row if map < 0)
+__global__ void __launch_bounds__(256) gather_rows_kernel(const __nv_bfloat16* __restrict__ in,
+                                                          __nv_bfloat16* __restrict__ out, const int32_t* __restrict__ map,
+                                                          const float* __restrict__ scale, int M, int C,
+                                                          int rows_per_batch, int src_rows_per_batch) {
+    const int vec_per_row = C / 8;
+    const long long total = (long long)M * vec_per_row;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+         i += (long long)gridDim.x * blockDim.x) {
+        const int m = (int)(i / vec_per_row), vcol = (int)(i - (long long)m * vec_per_row);
+        const int b = m / rows_per_batch, r = m - b * rows_per_batch;
+        const int s = map ? __ldg(map + r) : r;
+        float v[8];
+#pragma unroll
+        for (int e = 0; e < 8; ++e) v[e] = 0.f;
+        if (s >= 0) {
+            ld8(in + ((long long)b * src_rows_per_batch + s) * C + vcol * 8, v);
+            if (scale) {
+                const float sc = __ldg(scale + b);
+#pragma unroll
+                for (int e = 0; e < 8; ++e) v[e] *= sc;
+            }
+        }
+        st8(out + (long long)m * C + vcol * 8, v);
+    }
+}
+
+template <int BN, bool A_MN, bool B_MN>
+int launch_tc(const CUtensorMap& tmA, const CUtensorMap& tmB, const TcParams& p, cudaStream_t st) {
+    constexpr int STAGES = BN <= 128 ? 5 : 4;
+    constexpr size_t SMEM = (size_t)STAGES * (A_BYTES + BN * BK * 2) + 1024 + 256;
+    auto kern = tc_gemm_kernel<BN, A_MN, B_MN, STAGES>;
+    static bool configured = false;  // benign race: the attribute is idempotent
+    if (!configured) {
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM);
+        if (e != cudaSuccess) { set_error("tc gemm: cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return VSW_ERR_CUDA; }
+        configured = true;
+    }
+    const int total = p.n_tiles_m * p.n_tiles_n * p.splits;
+    const int grid = total < kNumSMs ? total : kNumSMs;
+    kern<<<grid, NUM_THREADS, SMEM, st>>>(tmA, tmB, p);
+    return check_launch("tc_gemm");
+}
+
+bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
+
+}  // namespace
+
+// ---------------------------------------------------------------------------------------------
+// forward
+// ---------------------------------------------------------------------------------------------
+int tc_linear(const TcLinearArgs& a, cudaStream_t st) {
+    if ((a.K % 8) || (a.N % 8) || !aligned16(a.x) || !aligned16(a.w) || !aligned16(a.y) ||
+        (a.bias && !aligned16(a.bias)) || (a.res && !aligned16(a.res)) || (a.aux_out && !aligned16(a.aux_out))) {
+        set_error("tcgen05 linear: needs K %% 8 == 0, N %% 8 == 0 and 16-byte aligned pointers (M=%d N=%d K=%d)", a.M,
+                  a.N, a.K);
+        return VSW_ERR_UNSUPPORTED;
+    }
+    CUtensorMap tmA, tmB;
+    const int BN = 128;
+    if (!make_tmap_2d_bf16(&tmA, a.x, a.M, a.K, a.K, BM, BK)) return VSW_ERR_CUDA;
+    if (!make_tmap_2d_bf16(&tmB, a.w, a.N, a.K, a.K, BN, BK)) return VSW_ERR_CUDA;
+    TcParams p{};
+    p.M = a.M; p.N = a.N; p.K = a.K;
+    p.n_tiles_m = ceil_div(a.M, BM); p.n_tiles_n = ceil_div(a.N, BN); p.splits = 1; p.k_per_split = ceil_div(a.K, BK) * BK;
+    p.epi = a.epi == VSW_EPI_BIAS ? TE_BIAS : (a.epi == VSW_EPI_GELU ? TE_GELU : TE_RESIDUAL);
+    p.bias = (const __nv_bfloat16*)a.bias; p.out = (__nv_bfloat16*)a.y; p.aux_out = (__nv_bfloat16*)a.aux_out;
+    p.res = (const __nv_bfloat16*)a.res; p.rowmap = a.rowmap; p.rowscale = a.rowscale;
+    p.rows_per_batch = a.rows_per_batch; p.dst_rows_per_batch = a.dst_rows_per_batch; p.ldc = a.N;
+    return launch_tc<128, false, false>(tmA, tmB, p, st);
+}
+
+// ---------------------------------------------------------------------------------------------
+// dgrad: dx (M x K) = A (M x N) w (N x K), A = optional gather/scale of dy
+// ---------------------------------------------------------------------------------------------
+int tc_dgrad(const TcDgradArgs& a, cudaStream_t st) {
+    if ((a.K % 8) || (a.N % 8) || !aligned16(a.dy) || !aligned16(a.w) || !aligned16(a.dx) ||
+        (a.gelu_pre && !aligned16(a.gelu_pre)) || (a.a_out && !aligned16(a.a_out))) {
+        set_error("tcgen05 dgrad: needs K %% 8 == 0, N %% 8 == 0 and 16-byte aligned pointers");
+        return VSW_ERR_UNSUPPORTED;
+    }
+    const void* A = a.dy;
+    if (a.a_rowmap || a.a_rowscale) {
+        if (!a.a_out) { set_error("tcgen05 dgrad: gathered A needs the a_out buffer"); return VSW_ERR_UNSUPPORTED; }
+        const long long total = (long long)a.M * (a.N / 8);
+        int blocks = (int)((total + 255) / 256 < (long long)kNumSMs * 16 ? (total + 255) / 256 : (long long)kNumSMs * 16);
+        gather_rows_kernel<<<blocks, 256, 0, st>>>((const __nv_bfloat16*)a.dy, (__nv_bfloat16*)a.a_out, a.a_rowmap,
+                                                   a.a_rowscale, a.M, a.N, a.rows_per_batch, a.src_rows_per_batch);
+        int rc = check_launch("gather_rows");
+        if (rc) return rc;
+        A = a.a_out;
+    }
+    CUtensorMap tmA, tmB;
+    if (!make_tmap_2d_bf16(&tmA, A, a.M, a.N, a.N, BM, BK)) return VSW_ERR_CUDA;       // K-major over N
+    if (!make_tmap_2d_bf16(&tmB, a.w, a.N, a.K, a.K, 64, 64)) return VSW_ERR_CUDA;     // MN-major: rows = reduction
+    TcParams p{};
+    p.M = a.M; p.N = a.K; p.K = a.N;
+    p.n_tiles_m = ceil_div(a.M, BM); p.n_tiles_n = ceil_div(a.K, 128); p.splits = 1; p.k_per_split = ceil_div(a.N, BK) * BK;
+    p.epi = TE_DGRAD; p.out = (__nv_bfloat16*)a.dx; p.gelu_pre = (const __nv_bfloat16*)a.gelu_pre; p.ldc = a.K;
+    return launch_tc<128, false, true>(tmA, tmB, p, st);
+}
+
+// ---------------------------------------------------------------------------------------------
+// wgrad: dw (N x K) = dy (M x N)^T x (M x K)
+// ---------------------------------------------------------------------------------------------
+static void tc_wgrad_split(int M, int N, int K, int* splits, int* m_per_split) {
+    const long long tiles = (long long)ceil_div(N, BM) * ceil_div(K, 128);
+    long long s = (2LL * kNumSMs + tiles - 1) / tiles;      // ~2 work items per SM
+    const long long smax = (M + 511) / 512;                 // each split reduces >= 512 rows
+    if (s > smax) s = smax;
+    if (s < 1) s = 1;
+    int mps = (int)((M + s - 1) / s);
+    mps = (mps + BK - 1) / BK * BK;
+    *m_per_split = mps;
+    *splits = (M + mps - 1) / mps;
+}
+
+size_t tc_wgrad_workspace(int M, int N, int K) {
+    int s, mps;
+    tc_wgrad_split(M, N, K, &s, &mps);
+    return (size_t)s * N * K * sizeof(float);
+}
+
+int tc_wgrad(const void* dy, const void* x, void* dw, int M, int N, int K, int grad_dtype, void* ws, size_t ws_bytes,
+             cudaStream_t st) {
+    if ((K % 8) || (N % 8) || !aligned16(dy) || !aligned16(x) || !aligned16(ws)) {
+        set_error("tcgen05 wgrad: needs K %% 8 == 0, N %% 8 == 0 and 16-byte aligned pointers");
+        return VSW_ERR_UNSUPPORTED;
+    }
+    int splits, mps;
+    tc_wgrad_split(M, N, K, &splits, &mps);
+    if (ws_bytes < (size_t)splits * N * K * sizeof(float)) { set_error("tcgen05 wgrad: workspace too small"); return VSW_ERR_WORKSPACE; }
+    CUtensorMap tmA, tmB;
+    if (!make_tmap_2d_bf16(&tmA, dy, M, N, N, 64, 64)) return VSW_ERR_CUDA;  // MN-major A: rows = reduction (m)
+    if (!make_tmap_2d_bf16(&tmB, x, M, K, K, 64, 64)) return VSW_ERR_CUDA;   // MN-major B
+    TcParams p{};
+    p.M = N; p.N = K; p.K = M;
+    p.n_tiles_m = ceil_div(N, BM); p.n_tiles_n = ceil_div(K, 128); p.splits = splits; p.k_per_split = mps;
+    p.epi = TE_PARTIAL; p.partial = (float*)ws; p.ldc = K;
+    int rc = launch_tc<128, true, true>(tmA, tmB, p, st);
+    if (rc) return rc;
+    return launch_partial_reduce((const float*)ws, splits, (long long)N * K, dw, grad_dtype, st);
 }
 
 }  // namespace vsw
