@@ -26,7 +26,7 @@ extern "C" int vsw_window_attn_fwd(const void* qkv, const void* bias_table, cons
     cudaStream_t st = (cudaStream_t)stream;
     if (attn_want_tc(dtype, hd, dense_mask)) {
         int rc = tc_attn_fwd(qkv, bias_table, rowcode, colcode, region, out, lse, B_, nW, N, nH, hd, L, scale, st);
-        if (rc != VSW_ERR_UNSUPPORTED) return rc;
+        if (rc != VSW_ERR_UNSUPPORTED || backend() == VSW_GEMM_TCGEN05) return rc;
     }
     return simt_attn_fwd(qkv, bias_table, rowcode, colcode, region, dense_mask, out, lse, B_, nW, N, nH, hd, L, scale,
                          dtype, st);
@@ -50,7 +50,7 @@ extern "C" int vsw_window_attn_bwd(const void* qkv, const void* out, const void*
     if (attn_want_tc(dtype, hd, dense_mask)) {
         int rc = tc_attn_bwd(qkv, out, dout, lse, bias_table, rowcode, colcode, region, dqkv, dbias_table, B_, nW, N,
                              nH, hd, L, scale, ws, ws_bytes, st);
-        if (rc != VSW_ERR_UNSUPPORTED) return rc;
+        if (rc != VSW_ERR_UNSUPPORTED || backend() == VSW_GEMM_TCGEN05) return rc;
     }
     return simt_attn_bwd(qkv, out, dout, lse, bias_table, rowcode, colcode, region, dense_mask, dqkv, dbias_table, B_,
                          nW, N, nH, hd, L, scale, dtype, ws, ws_bytes, st);

@@ -1,0 +1,444 @@
+// tcgen05 / TMEM recompute-based backward of fused window attention (included by attn_tc.cu).
+// Formulas: SURVEY A5.  Per (window, head) item and per (key block kb of 128, query tile t of 128):
+//   S  = Q_t K_kb^T,  dP = dO_t V_kb^T                 tcgen05.mma SS -> TMEM (128 x 128 fp32 each)
+//   P  = exp2(S*scale*log2e + bias*log2e [+mask] - lse*log2e),  dS = P (dP - delta)     8 softmax warps
+//        P, dS -> bf16 tiles in shared memory (manual 128B swizzle), d(bias table) into PRIVATE per-warp
+//        shared-memory histograms (lanes of a warp hit distinct entries -> plain read-modify-write, deterministic)
+//   dV_kb += P^T dO_t,  dK_kb += dS^T Q_t               A = P/dS (MN-major), B = dO_t/Q_t (MN-major)
+//   dQ_t  += dS K_kb                                    A = dS (K-major),    B = K_kb (MN-major)
+// dK/dV of the key block and dQ of all four query tiles stay in TMEM until complete (kb outer, t inner).
+// A CTA is pinned to ONE head so its bias-table column and histograms persist across all its windows; the
+// per-CTA histograms are summed by a fixed-order second pass.
+namespace vsw {
+namespace {
+
+constexpr int BW_KV_OFF = 0;                       // K_kb 8 KB, V_kb 8 KB
+constexpr int BW_QD_OFF = 16384;                   // 2 stages x (Q_t 8 KB + dO_t 8 KB)
+constexpr int BW_P_OFF = 49152;                    // P  tile: 2 chunks x (128 rows x 128 B)
+constexpr int BW_DS_OFF = 81920;                   // dS tile
+constexpr int BW_MISC_OFF = 114688;
+constexpr int BW_S = 0, BW_DP = 128, BW_DK = 256, BW_DV = 288, BW_DQ = 320;  // TMEM columns
+
+struct BwdParams {
+    const __nv_bfloat16* table; const int32_t* rowcode; const int32_t* colcode; const uint8_t* region;
+    const __nv_bfloat16* out; const __nv_bfloat16* dout; const float* lse;
+    __nv_bfloat16* dqkv; float* dbias_part;
+    int B_, nW, N, nH, L, Lpad, groups;
+    float scale, scale_log2;
+    int Npad, nq, nkb;
+};
+
+struct BwdSmem {
+    float* tab; float* hist;          // [Lpad], [8][Lpad]
+    float* delta; float* lse2;        // [2][512] each (one copy per column half)
+    int* rc; int* cc;                 // [512]
+    uint8_t* reg[2]; int* masked;     // region ids per item (double-buffered)
+    uint64_t *kv_full, *kv_empty, *qd_full, *qd_empty, *s_full, *pds_full, *dkv_full, *dq_full, *aux_full, *aux_empty;
+    uint32_t* tmem_slot;
+};
+__device__ __forceinline__ BwdSmem bwd_carve(uint8_t* base, int Lpad) {
+    BwdSmem s;
+    uint8_t* p = base + BW_MISC_OFF;
+    s.tab = (float*)p; p += (size_t)Lpad * 4;
+    s.hist = (float*)p; p += (size_t)8 * Lpad * 4;
+    s.delta = (float*)p; p += 2 * 512 * 4;
+    s.lse2 = (float*)p; p += 2 * 512 * 4;
+    s.rc = (int*)p; p += 512 * 4;
+    s.cc = (int*)p; p += 512 * 4;
+    s.kv_full = (uint64_t*)p; p += 8;
+    s.kv_empty = (uint64_t*)p; p += 8;
+    s.qd_full = (uint64_t*)p; p += 16;
+    s.qd_empty = (uint64_t*)p; p += 16;
+    s.s_full = (uint64_t*)p; p += 8;
+    s.pds_full = (uint64_t*)p; p += 8;
+    s.dkv_full = (uint64_t*)p; p += 8;
+    s.dq_full = (uint64_t*)p; p += 8;
+    s.aux_full = (uint64_t*)p; p += 16;
+    s.aux_empty = (uint64_t*)p; p += 16;
+    s.masked = (int*)p; p += 8;
+    s.tmem_slot = (uint32_t*)p; p += 8;
+    s.reg[0] = p; p += 512;
+    s.reg[1] = p; p += 512;
+    return s;
+}
+size_t bwd_smem_bytes(int Lpad) {
+    return 1024 + BW_MISC_OFF + (size_t)9 * Lpad * 4 + 4 * 512 * 4 + 2 * 512 * 4 + 15 * 8 + 16 + 1024 + 64;
+}
+
+// byte offset of the 16-byte unit holding keys [8u, 8u+8) of query row i inside a 128B-swizzled chunk
+__device__ __forceinline__ uint32_t sw128_off(int row, int unit) { return row * 128 + ((unit ^ (row & 7)) << 4); }
+
+__global__ void __launch_bounds__(NTHREADS, 1)
+attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant__ CUtensorMap tmDO,
+                   const BwdParams p) {
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* base = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    const BwdSmem s = bwd_carve(base, p.Lpad);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int C = p.nH * HD;
+    const int h = blockIdx.x / p.groups, gi = blockIdx.x % p.groups;   // CTA pinned to one head
+
+    if (warp == 0 && lane == 0) {
+        tc::prefetch_tmap(&tmQKV);
+        tc::prefetch_tmap(&tmDO);
+        tc::mbar_init(s.kv_full, 1); tc::mbar_init(s.kv_empty, 1);
+        for (int i = 0; i < 2; ++i) {
+            tc::mbar_init(&s.qd_full[i], 1); tc::mbar_init(&s.qd_empty[i], 1);
+            tc::mbar_init(&s.aux_full[i], 1); tc::mbar_init(&s.aux_empty[i], 8);
+        }
+        tc::mbar_init(s.s_full, 1); tc::mbar_init(s.pds_full, 8); tc::mbar_init(s.dkv_full, 1); tc::mbar_init(s.dq_full, 1);
+        tc::fence_barrier_init();
+    }
+    if (warp == 1) tc::tmem_alloc(s.tmem_slot, TMEM_COLS);
+    // one-time shared-memory state: codes, bias column (x log2e), zeroed histograms and P/dS tiles
+    for (int n = threadIdx.x; n < 512; n += NTHREADS) {
+        s.rc[n] = n < p.N ? p.rowcode[n] : 0;
+        s.cc[n] = n < p.N ? p.colcode[n] : 0;
+    }
+    for (int l = threadIdx.x; l < p.L; l += NTHREADS)
+        s.tab[l] = __bfloat162float(p.table[(long long)l * p.nH + h]) * LOG2E;
+    for (int l = threadIdx.x; l < 8 * p.Lpad; l += NTHREADS) s.hist[l] = 0.f;
+    for (int i = threadIdx.x; i < 65536 / 16; i += NTHREADS)
+        reinterpret_cast<uint4*>(base + BW_P_OFF)[i] = make_uint4(0, 0, 0, 0);
+    tc::fence_proxy_async();
+    tc::tc_fence_before();
+    __syncthreads();
+    tc::tc_fence_after();
+    const uint32_t tmem = *s.tmem_slot;
+
+    if (warp == 0) {
+        // ===================== TMA producer =====================
+        if (lane == 0) {
+            uint32_t kvn = 0, blk = 0;
+            for (int b_ = gi; b_ < p.B_; b_ += p.groups) {
+                for (int kb = 0; kb < p.nkb; ++kb, ++kvn) {
+                    tc::mbar_wait(s.kv_empty, (kvn & 1) ^ 1);
+                    tc::mbar_expect_tx(s.kv_full, 2 * BOX_BYTES);
+                    tc::tma_load_3d(&tmQKV, s.kv_full, base + BW_KV_OFF, C + h * HD, kb * QT, b_);
+                    tc::tma_load_3d(&tmQKV, s.kv_full, base + BW_KV_OFF + BOX_BYTES, 2 * C + h * HD, kb * QT, b_);
+                    for (int t = 0; t < p.nq; ++t, ++blk) {
+                        const int st = blk & 1; const uint32_t ph = (blk >> 1) & 1;
+                        tc::mbar_wait(&s.qd_empty[st], ph ^ 1);
+                        tc::mbar_expect_tx(&s.qd_full[st], 2 * BOX_BYTES);
+                        uint8_t* dst = base + BW_QD_OFF + st * 2 * BOX_BYTES;
+                        tc::tma_load_3d(&tmQKV, &s.qd_full[st], dst, h * HD, t * QT, b_);
+                        tc::tma_load_3d(&tmDO, &s.qd_full[st], dst + BOX_BYTES, h * HD, t * QT, b_);
+                    }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ===================== MMA issuer =====================
+        if (lane == 0) {
+            uint32_t kvn = 0, blk = 0, pdsph = 0;
+            const uint32_t ka = tc::smem_u32(base + BW_KV_OFF), va = ka + BOX_BYTES;
+            const uint32_t pa = tc::smem_u32(base + BW_P_OFF), dsa = tc::smem_u32(base + BW_DS_OFF);
+            const uint32_t id_t = tc::idesc_bf16(QT, HD, 1, 1);   // A MN-major (P / dS transposed), B MN-major
+            const uint32_t id_q = tc::idesc_bf16(QT, HD, 0, 1);   // A K-major (dS), B MN-major (K)
+            for (int b_ = gi; b_ < p.B_; b_ += p.groups) {
+                for (int kb = 0; kb < p.nkb; ++kb, ++kvn) {
+                    const int nkeys = min(QT, p.Npad - kb * QT);
+                    const uint32_t id_s = tc::idesc_bf16(QT, nkeys, 0, 0);
+                    tc::mbar_wait(s.kv_full, kvn & 1);
+                    for (int t = 0; t < p.nq; ++t, ++blk) {
+                        const int st = blk & 1; const uint32_t ph = (blk >> 1) & 1;
+                        tc::mbar_wait(&s.qd_full[st], ph);
+                        tc::tc_fence_after();
+                        const uint32_t qa = tc::smem_u32(base + BW_QD_OFF + st * 2 * BOX_BYTES), doa = qa + BOX_BYTES;
+#pragma unroll
+                        for (int k = 0; k < 2; ++k)
+                            tc::umma_bf16(tmem + BW_S, tc::smem_desc_sw64(qa + k * 32, 0, 512),
+                                          tc::smem_desc_sw64(ka + k * 32, 0, 512), id_s, k);
+#pragma unroll
+                        for (int k = 0; k < 2; ++k)
+                            tc::umma_bf16(tmem + BW_DP, tc::smem_desc_sw64(doa + k * 32, 0, 512),
+                                          tc::smem_desc_sw64(va + k * 32, 0, 512), id_s, k);
+                        tc::umma_commit(s.s_full);
+                        tc::mbar_wait(s.pds_full, pdsph); pdsph ^= 1;
+                        tc::tc_fence_after();
+#pragma unroll
+                        for (int ks = 0; ks < 8; ++ks)   // reduce over the 128 queries of the tile
+                            tc::umma_bf16(tmem + BW_DV, tc::smem_desc_sw128(pa + ks * 2048, 16384, 1024),
+                                          tc::smem_desc_sw64(doa + ks * 1024, 0, 512), id_t, (t > 0 || ks > 0) ? 1u : 0u);
+#pragma unroll
+                        for (int ks = 0; ks < 8; ++ks)
+                            tc::umma_bf16(tmem + BW_DK, tc::smem_desc_sw128(dsa + ks * 2048, 16384, 1024),
+                                          tc::smem_desc_sw64(qa + ks * 1024, 0, 512), id_t, (t > 0 || ks > 0) ? 1u : 0u);
+                        for (int ks = 0; ks < nkeys / 16; ++ks)   // reduce over the keys of the block
+                            tc::umma_bf16(tmem + BW_DQ + t * HD,
+                                          tc::smem_desc_sw128(dsa + (ks >> 2) * 16384 + (ks & 3) * 32, 0, 1024),
+                                          tc::smem_desc_sw64(ka + ks * 1024, 0, 512), id_q, (kb > 0 || ks > 0) ? 1u : 0u);
+                        tc::umma_commit(&s.qd_empty[st]);
+                    }
+                    tc::umma_commit(s.dkv_full);
+                    tc::umma_commit(s.kv_empty);
+                }
+                tc::umma_commit(s.dq_full);
+            }
+        }
+    } else if (warp == 2) {
+        // ===================== aux: region ids of the item's window =====================
+        int it = 0;
+        for (int b_ = gi; b_ < p.B_; b_ += p.groups, ++it) {
+            const int st = it & 1; const uint32_t ph = (it >> 1) & 1;
+            tc::mbar_wait(&s.aux_empty[st], ph ^ 1);
+            int diff = 0;
+            if (p.region) {
+                const uint8_t* rg = p.region + (long long)(b_ % p.nW) * p.N;
+                const uint8_t r0 = rg[0];
+                for (int n = lane; n < p.N; n += 32) {
+                    const uint8_t r = rg[n];
+                    s.reg[st][n] = r;
+                    diff |= (r != r0);
+                }
+            }
+            diff = __any_sync(0xffffffffu, diff);
+            if (lane == 0) s.masked[st] = diff;
+            __syncwarp();
+            if (lane == 0) tc::mbar_arrive(&s.aux_full[st]);
+        }
+    } else if (warp >= 4) {
+        // ===================== softmax / dS / epilogue warps =====================
+        const int q = warp & 3, half = (warp - 4) >> 2;
+        const int row = q * 32 + lane;
+        const uint32_t lane_base = (uint32_t)(q * 32) << 16;
+        float* hist = s.hist + (size_t)(warp - 4) * p.Lpad;
+        float* my_delta = s.delta + half * 512;
+        float* my_lse2 = s.lse2 + half * 512;
+        uint8_t* ptile = base + BW_P_OFF + half * 16384;    // this warp's 64-key chunk
+        uint8_t* dstile = base + BW_DS_OFF + half * 16384;
+        int it = 0; uint32_t sph = 0, dkvph = 0, dqph = 0;
+        for (int b_ = gi; b_ < p.B_; b_ += p.groups, ++it) {
+            const int st = it & 1; const uint32_t ph = (it >> 1) & 1;
+            tc::mbar_wait(&s.aux_full[st], ph);
+            const bool masked = s.masked[st] != 0;
+            const uint8_t* reg = s.reg[st];
+            for (int kb = 0; kb < p.nkb; ++kb) {
+                const int nkeys = min(QT, p.Npad - kb * QT);
+                const int cbeg = half * 64, cend = min(cbeg + 64, nkeys);   // my columns inside the block
+                for (int t = 0; t < p.nq; ++t) {
+                    const int i = t * QT + row;
+                    const bool valid = i < p.N;
+                    const bool warp_valid = t * QT + q * 32 < p.N;
+                    float delta_i, nl2;
+                    if (kb == 0) {
+                        delta_i = 0.f; nl2 = 0.f;
+                        if (valid) {
+                            const uint4* op = reinterpret_cast<const uint4*>(p.out + ((long long)b_ * p.N + i) * C + h * HD);
+                            const uint4* dp = reinterpret_cast<const uint4*>(p.dout + ((long long)b_ * p.N + i) * C + h * HD);
+#pragma unroll
+                            for (int v = 0; v < 4; ++v) {
+                                const uint4 a = __ldg(op + v), b = __ldg(dp + v);
+                                const uint32_t aw[4] = {a.x, a.y, a.z, a.w}, bw[4] = {b.x, b.y, b.z, b.w};
+#pragma unroll
+                                for (int e = 0; e < 4; ++e) {
+                                    const float2 x = tc::unpack_bf16(aw[e]), y = tc::unpack_bf16(bw[e]);
+                                    delta_i = fmaf(x.x, y.x, delta_i);
+                                    delta_i = fmaf(x.y, y.y, delta_i);
+                                }
+                            }
+                            nl2 = -p.lse[((long long)b_ * p.nH + h) * p.N + i] * LOG2E;
+                        }
+                        my_delta[i] = delta_i;
+                        my_lse2[i] = nl2;
+                    } else {
+                        delta_i = my_delta[i];
+                        nl2 = my_lse2[i];
+                    }
+                    const int ic = valid ? i : p.N - 1;
+                    const int rci = s.rc[ic];
+                    const uint8_t regi = masked ? reg[ic] : 0;
+                    tc::mbar_wait(s.s_full, sph); sph ^= 1;
+                    tc::tc_fence_after();
+                    if (!warp_valid) {
+                        // rows beyond the window: contribute zeros to the reductions over queries
+                        for (int u = 0; u < 8; ++u) {
+                            *reinterpret_cast<uint4*>(ptile + sw128_off(row, u)) = make_uint4(0, 0, 0, 0);
+                            *reinterpret_cast<uint4*>(dstile + sw128_off(row, u)) = make_uint4(0, 0, 0, 0);
+                        }
+                    } else {
+                        for (int c = cbeg; c < cend; c += 16) {
+                            uint32_t rs[16], rd[16];
+                            tc::tmem_ld_32x16(tmem + lane_base + BW_S + c, rs);
+                            tc::tmem_ld_32x16(tmem + lane_base + BW_DP + c, rd);
+                            tc::tmem_ld_wait();
+                            uint32_t pw[8], dw[8];
+#pragma unroll
+                            for (int e = 0; e < 16; e += 2) {
+                                float pv[2], dv[2];
+#pragma unroll
+                                for (int u = 0; u < 2; ++u) {
+                                    const int j = kb * QT + c + e + u;
+                                    const bool ok = valid && j < p.N;
+                                    const int jc = j < p.N ? j : p.N - 1;
+                                    const int idx = rci + s.cc[jc];
+                                    float v = fmaf(__uint_as_float(rs[e + u]), p.scale_log2, s.tab[idx]) + nl2;
+                                    if (masked) v += (reg[jc] != regi) ? -100.0f * LOG2E : 0.0f;
+                                    const float pe = ok ? tc::ex2_approx(v) : 0.f;
+                                    const float ds = pe * (__uint_as_float(rd[e + u]) - delta_i);
+                                    if (ok) hist[idx] += ds;   // lanes of a warp hit distinct entries
+                                    pv[u] = pe;
+                                    dv[u] = ds;
+                                }
+                                pw[e / 2] = tc::pack_bf16(pv[0], pv[1]);
+                                dw[e / 2] = tc::pack_bf16(dv[0], dv[1]);
+                            }
+                            const int u0 = (c - cbeg) / 8;
+                            *reinterpret_cast<uint4*>(ptile + sw128_off(row, u0)) = make_uint4(pw[0], pw[1], pw[2], pw[3]);
+                            *reinterpret_cast<uint4*>(ptile + sw128_off(row, u0 + 1)) = make_uint4(pw[4], pw[5], pw[6], pw[7]);
+                            *reinterpret_cast<uint4*>(dstile + sw128_off(row, u0)) = make_uint4(dw[0], dw[1], dw[2], dw[3]);
+                            *reinterpret_cast<uint4*>(dstile + sw128_off(row, u0 + 1)) = make_uint4(dw[4], dw[5], dw[6], dw[7]);
+                        }
+                    }
+                    tc::fence_proxy_async();   // generic-proxy smem writes -> visible to the tensor core
+                    tc::tc_fence_before();
+                    __syncwarp();
+                    if (lane == 0) tc::mbar_arrive(s.pds_full);
+                }
+                // ---- dK (half 0) / dV (half 1) of this key block
+                tc::mbar_wait(s.dkv_full, dkvph); dkvph ^= 1;
+                tc::tc_fence_after();
+                {
+                    const int key = kb * QT + row;
+                    uint32_t lo[16], hi[16];
+                    const uint32_t col = half == 0 ? BW_DK : BW_DV;
+                    tc::tmem_ld_32x16(tmem + lane_base + col, lo);
+                    tc::tmem_ld_32x16(tmem + lane_base + col + 16, hi);
+                    tc::tmem_ld_wait();
+                    if (key < p.N) {
+                        const float sc = half == 0 ? p.scale : 1.0f;
+                        uint4* dst = reinterpret_cast<uint4*>(p.dqkv + (((long long)b_ * p.N + key) * 3 + 1 + half) * C + h * HD);
+                        uint4 u;
+                        u.x = tc::pack_bf16(__uint_as_float(lo[0]) * sc, __uint_as_float(lo[1]) * sc);
+                        u.y = tc::pack_bf16(__uint_as_float(lo[2]) * sc, __uint_as_float(lo[3]) * sc);
+                        u.z = tc::pack_bf16(__uint_as_float(lo[4]) * sc, __uint_as_float(lo[5]) * sc);
+                        u.w = tc::pack_bf16(__uint_as_float(lo[6]) * sc, __uint_as_float(lo[7]) * sc);
+                        dst[0] = u;
+                        u.x = tc::pack_bf16(__uint_as_float(lo[8]) * sc, __uint_as_float(lo[9]) * sc);
+                        u.y = tc::pack_bf16(__uint_as_float(lo[10]) * sc, __uint_as_float(lo[11]) * sc);
+                        u.z = tc::pack_bf16(__uint_as_float(lo[12]) * sc, __uint_as_float(lo[13]) * sc);
+                        u.w = tc::pack_bf16(__uint_as_float(lo[14]) * sc, __uint_as_float(lo[15]) * sc);
+                        dst[1] = u;
+                        u.x = tc::pack_bf16(__uint_as_float(hi[0]) * sc, __uint_as_float(hi[1]) * sc);
+                        u.y = tc::pack_bf16(__uint_as_float(hi[2]) * sc, __uint_as_float(hi[3]) * sc);
+                        u.z = tc::pack_bf16(__uint_as_float(hi[4]) * sc, __uint_as_float(hi[5]) * sc);
+                        u.w = tc::pack_bf16(__uint_as_float(hi[6]) * sc, __uint_as_float(hi[7]) * sc);
+                        dst[2] = u;
+                        u.x = tc::pack_bf16(__uint_as_float(hi[8]) * sc, __uint_as_float(hi[9]) * sc);
+                        u.y = tc::pack_bf16(__uint_as_float(hi[10]) * sc, __uint_as_float(hi[11]) * sc);
+                        u.z = tc::pack_bf16(__uint_as_float(hi[12]) * sc, __uint_as_float(hi[13]) * sc);
+                        u.w = tc::pack_bf16(__uint_as_float(hi[14]) * sc, __uint_as_float(hi[15]) * sc);
+                        dst[3] = u;
+                    }
+                }
+                tc::tc_fence_before();
+            }
+            // ---- dQ of every query tile (16 columns per half)
+            tc::mbar_wait(s.dq_full, dqph); dqph ^= 1;
+            tc::tc_fence_after();
+            for (int t = 0; t < p.nq; ++t) {
+                const int i = t * QT + row;
+                uint32_t o[16];
+                tc::tmem_ld_32x16(tmem + lane_base + BW_DQ + t * HD + half * 16, o);
+                tc::tmem_ld_wait();
+                if (i < p.N) {
+                    uint4* dst = reinterpret_cast<uint4*>(p.dqkv + (((long long)b_ * p.N + i) * 3) * C + h * HD + half * 16);
+                    uint4 u;
+                    u.x = tc::pack_bf16(__uint_as_float(o[0]) * p.scale, __uint_as_float(o[1]) * p.scale);
+                    u.y = tc::pack_bf16(__uint_as_float(o[2]) * p.scale, __uint_as_float(o[3]) * p.scale);
+                    u.z = tc::pack_bf16(__uint_as_float(o[4]) * p.scale, __uint_as_float(o[5]) * p.scale);
+                    u.w = tc::pack_bf16(__uint_as_float(o[6]) * p.scale, __uint_as_float(o[7]) * p.scale);
+                    dst[0] = u;
+                    u.x = tc::pack_bf16(__uint_as_float(o[8]) * p.scale, __uint_as_float(o[9]) * p.scale);
+                    u.y = tc::pack_bf16(__uint_as_float(o[10]) * p.scale, __uint_as_float(o[11]) * p.scale);
+                    u.z = tc::pack_bf16(__uint_as_float(o[12]) * p.scale, __uint_as_float(o[13]) * p.scale);
+                    u.w = tc::pack_bf16(__uint_as_float(o[14]) * p.scale, __uint_as_float(o[15]) * p.scale);
+                    dst[1] = u;
+                }
+            }
+            tc::tc_fence_before();
+            __syncwarp();
+            if (lane == 0) tc::mbar_arrive(&s.aux_empty[st]);
+        }
+    }
+
+    tc::tc_fence_before();
+    __syncthreads();
+    // flush the eight private histograms of this CTA in a fixed order
+    {
+        float* part = p.dbias_part + ((long long)gi * p.nH + h) * p.L;
+        for (int l = threadIdx.x; l < p.L; l += NTHREADS) {
+            float t = 0.f;
+#pragma unroll
+            for (int w8 = 0; w8 < 8; ++w8) t += s.hist[(size_t)w8 * p.Lpad + l];
+            part[l] = t;
+        }
+    }
+    if (warp == 1) {
+        tc::tc_fence_after();
+        tc::tmem_dealloc(tmem, TMEM_COLS);
+    }
+}
+
+__global__ void tc_dbias_reduce_kernel(const float* __restrict__ part, int groups, int nH, int L, float* __restrict__ out) {
+    const int idx = blockIdx.x * blockDim.x + threadIdx.x;   // out layout (L, nH)
+    if (idx >= L * nH) return;
+    const int l = idx / nH, h = idx % nH;
+    float t = 0.f;
+    for (int g = 0; g < groups; ++g) t += part[((long long)g * nH + h) * L + l];
+    out[idx] = t;
+}
+
+int bwd_groups(int B_, int nH) {
+    int g = kNumSMs / nH;
+    if (g < 1) g = 1;
+    if (g > B_) g = B_;
+    return g;
+}
+
+}  // namespace
+
+size_t tc_attn_bwd_workspace(int B_, int N, int nH, int hd, int L) {
+    (void)N; (void)hd;
+    if (nH > kNumSMs) return 0;
+    return (size_t)bwd_groups(B_, nH) * nH * L * sizeof(float);
+}
+
+int tc_attn_bwd(const void* qkv, const void* out, const void* dout, const float* lse, const void* table,
+                const int32_t* rowcode, const int32_t* colcode, const uint8_t* region, void* dqkv, float* dbias,
+                int B_, int nW, int N, int nH, int hd, int L, float scale, void* ws, size_t ws_bytes, cudaStream_t st) {
+    const int Lpad = (L + 3) / 4 * 4;
+    const size_t smem = bwd_smem_bytes(Lpad);
+    if (hd != HD || N > 448 || N < 1 || nH > kNumSMs || smem > 227 * 1024 || !aligned16(qkv) || !aligned16(out) ||
+        !aligned16(dout) || !aligned16(dqkv)) {
+        set_error("tcgen05 window attention bwd: needs head_dim 32, N <= 448, bias table fitting shared memory "
+                  "(hd=%d N=%d L=%d smem=%zu)", hd, N, L, smem);
+        return VSW_ERR_UNSUPPORTED;
+    }
+    const int groups = bwd_groups(B_, nH);
+    if (ws_bytes < (size_t)groups * nH * L * sizeof(float)) { set_error("tcgen05 attention bwd: workspace too small"); return VSW_ERR_WORKSPACE; }
+    const int C = nH * HD;
+    CUtensorMap tmQKV, tmDO;
+    if (!make_tmap_3d_bf16(&tmQKV, qkv, B_, N, 3 * C, 3 * C, (uint64_t)N * 3 * C, QT, HD, 64)) return VSW_ERR_CUDA;
+    if (!make_tmap_3d_bf16(&tmDO, dout, B_, N, C, C, (uint64_t)N * C, QT, HD, 64)) return VSW_ERR_CUDA;
+    BwdParams p{};
+    p.table = (const __nv_bfloat16*)table; p.rowcode = rowcode; p.colcode = colcode; p.region = region;
+    p.out = (const __nv_bfloat16*)out; p.dout = (const __nv_bfloat16*)dout; p.lse = lse;
+    p.dqkv = (__nv_bfloat16*)dqkv; p.dbias_part = (float*)ws;
+    p.B_ = B_; p.nW = nW; p.N = N; p.nH = nH; p.L = L; p.Lpad = Lpad; p.groups = groups;
+    p.scale = scale; p.scale_log2 = scale * LOG2E;
+    p.Npad = (N + 15) / 16 * 16; p.nq = (N + QT - 1) / QT; p.nkb = (p.Npad + QT - 1) / QT;
+    static bool configured = false;
+    if (!configured) {
+        cudaError_t e = cudaFuncSetAttribute(attn_bwd_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+        if (e != cudaSuccess) { set_error("attn bwd: cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return VSW_ERR_CUDA; }
+        configured = true;
+    }
+    attn_bwd_tc_kernel<<<groups * nH, NTHREADS, smem, st>>>(tmQKV, tmDO, p);
+    int rc = check_launch("attn_bwd_tc");
+    if (rc) return rc;
+    tc_dbias_reduce_kernel<<<ceil_div((long long)L * nH, 256), 256, 0, st>>>((const float*)ws, groups, nH, L, dbias);
+    return check_launch("attn_dbias_reduce_tc");
+}
+
+}  // namespace vsw

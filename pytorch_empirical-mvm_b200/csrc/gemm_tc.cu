@@ -55,6 +55,27 @@ bool make_tmap_2d_bf16(CUtensorMap* out, const void* base, uint64_t rows, uint64
     return true;
 }
 
+bool make_tmap_3d_bf16(CUtensorMap* out, const void* base, uint64_t batch, uint64_t rows, uint64_t cols,
+                       uint64_t row_stride_elems, uint64_t batch_stride_elems, uint32_t box_rows, uint32_t box_cols,
+                       int swizzle_bytes) {
+    auto fn = get_encode_fn();
+    if (!fn) { set_error("cuTensorMapEncodeTiled entry point not available"); return false; }
+    cuuint64_t gdim[3] = {cols, rows, batch};
+    cuuint64_t gstride[2] = {row_stride_elems * 2, batch_stride_elems * 2};
+    cuuint32_t box[3] = {box_cols, box_rows, 1};
+    cuuint32_t estr[3] = {1, 1, 1};
+    CUresult r = fn(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(base), gdim, gstride, box, estr,
+                    CU_TENSOR_MAP_INTERLEAVE_NONE,
+                    swizzle_bytes == 64 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_128B,
+                    CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+        set_error("cuTensorMapEncodeTiled(3d) failed (%d) batch=%llu rows=%llu cols=%llu", (int)r,
+                  (unsigned long long)batch, (unsigned long long)rows, (unsigned long long)cols);
+        return false;
+    }
+    return true;
+}
+
 // ---------------------------------------------------------------------------------------------
 // kernel
 // ---------------------------------------------------------------------------------------------
