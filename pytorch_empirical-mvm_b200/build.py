@@ -32,7 +32,7 @@ def _headers_digest():
     h = hashlib.sha256()
     for root in (CSRC, INCLUDE):
         for f in sorted(os.listdir(root)):
-            if f.endswith((".cuh", ".h")):
+            if f.endswith((".cuh", ".h", ".inl")):
                 h.update(open(os.path.join(root, f), "rb").read())
     h.update(" ".join(FLAGS).encode())
     return h.hexdigest()

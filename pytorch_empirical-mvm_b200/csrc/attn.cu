@@ -40,8 +40,8 @@ extern "C" size_t vsw_window_attn_bwd_workspace(int B_, int N, int nH, int hd, i
 extern "C" int vsw_window_attn_bwd(const void* qkv, const void* out, const void* dout, const float* lse,
                                    const void* bias_table, const int32_t* rowcode, const int32_t* colcode,
                                    const uint8_t* region, const void* dense_mask, void* dqkv, float* dbias_table,
-                                   int B_, int nW, int N, int nH, int hd, int L, float scale, int dtype, void* ws,
-                                   size_t ws_bytes, void* stream) {
+                                   int B_, int nW, int N, int nH, int hd, int L, float scale, int window_planes,
+                                   int dtype, void* ws, size_t ws_bytes, void* stream) {
     VSW_ATTN_CHECK("vsw_window_attn_bwd");
     VSW_REQUIRE(out && dout && lse && dqkv && dbias_table && ws, VSW_ERR_ARG, "vsw_window_attn_bwd: NULL pointer");
     VSW_REQUIRE(ws_bytes >= vsw_window_attn_bwd_workspace(B_, N, nH, hd, L), VSW_ERR_WORKSPACE,
@@ -49,7 +49,7 @@ extern "C" int vsw_window_attn_bwd(const void* qkv, const void* out, const void*
     cudaStream_t st = (cudaStream_t)stream;
     if (attn_want_tc(dtype, hd, dense_mask)) {
         int rc = tc_attn_bwd(qkv, out, dout, lse, bias_table, rowcode, colcode, region, dqkv, dbias_table, B_, nW, N,
-                             nH, hd, L, scale, ws, ws_bytes, st);
+                             nH, hd, L, scale, window_planes, ws, ws_bytes, st);
         if (rc != VSW_ERR_UNSUPPORTED || backend() == VSW_GEMM_TCGEN05) return rc;
     }
     return simt_attn_bwd(qkv, out, dout, lse, bias_table, rowcode, colcode, region, dense_mask, dqkv, dbias_table, B_,

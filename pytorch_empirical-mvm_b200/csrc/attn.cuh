@@ -21,6 +21,7 @@ int tc_attn_fwd(const void* qkv, const void* table, const int32_t* rowcode, cons
 size_t tc_attn_bwd_workspace(int B_, int N, int nH, int hd, int L);
 int tc_attn_bwd(const void* qkv, const void* out, const void* dout, const float* lse, const void* table,
                 const int32_t* rowcode, const int32_t* colcode, const uint8_t* region, void* dqkv, float* dbias,
-                int B_, int nW, int N, int nH, int hd, int L, float scale, void* ws, size_t ws_bytes, cudaStream_t st);
+                int B_, int nW, int N, int nH, int hd, int L, float scale, int planes, void* ws, size_t ws_bytes,
+                cudaStream_t st);
 
 }  // namespace vsw

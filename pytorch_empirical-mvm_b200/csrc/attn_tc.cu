@@ -12,6 +12,7 @@
 //                    P is written back to TMEM as packed bf16, aliasing S
 //   O = P V          tcgen05.mma (TS: A = P from TMEM, B = V MN-major from smem), 128 x 32 fp32 in TMEM
 //   epilogue         O / rowsum -> bf16 -> global, log-sum-exp -> global (for the recompute backward)
+#include <stdlib.h>
 #include "attn.cuh"
 #include "tc_common.cuh"
 
@@ -24,16 +25,20 @@ constexpr int MAXROWS = 512;                  // smem rows per operand
 constexpr int OPER_BYTES = MAXROWS * HD * 2;  // 32 KB
 constexpr int STAGE_BYTES = 3 * OPER_BYTES;   // Q, K, V
 constexpr int BOX_BYTES = QT * HD * 2;        // 8 KB per TMA box
-constexpr int NTHREADS = 384;                 // warp 0 TMA, 1 MMA, 2 aux, 3 idle, 4..11 softmax
+constexpr int NTHREADS = 384;                 // backward: warp 0 TMA, 1 MMA, 2 aux, 3 idle, 4..11 softmax
+constexpr int NPARTS = 3;                     // forward: column parts per row (3 softmax warps per TMEM lane quadrant)
+constexpr int NSUB = 2;                       // forward: P.V hand-off granularity (sub-batches per part)
+constexpr int FWD_THREADS = 128 + NPARTS * 128;  // warp 0 TMA, 1 MMA, 2 aux, 3 idle, 4.. softmax
 constexpr int S_COL = 0, O_COL = 480, TMEM_COLS = 512;
 constexpr float LOG2E = 1.4426950408889634f, LN2 = 0.6931471805599453f;
 
 struct FwdParams {
-    const __nv_bfloat16* table; const int32_t* rowcode; const int32_t* colcode; const uint8_t* region;
+    const __nv_bfloat16* qkv; const __nv_bfloat16* table; const int32_t* rowcode; const int32_t* colcode; const uint8_t* region;
     __nv_bfloat16* out; float* lse;
     int B_, nW, N, nH, L, Lpad;
     float scale_log2;
-    int Npad, nq, split;
+    int Npad, nq;
+    long long* dbg;   // optional per-phase cycle counters (profiling builds only)
 };
 
 struct Smem {
@@ -43,6 +48,7 @@ struct Smem {
     int* rc; int* cc;
     float* xmax; float* xsum;   // [2][128]
     float* maxbias; int* masked;  // [2]
+    float* k2max;                 // [2] max_j |k_j|^2 of the staged item
     uint64_t* qkv_full; uint64_t* qkv_empty; uint64_t* aux_full; uint64_t* aux_empty;  // [2] each
     uint64_t* s_full; uint64_t* p_full; uint64_t* o_full;
     uint32_t* tmem_slot;
@@ -56,31 +62,154 @@ __device__ __forceinline__ Smem carve(uint8_t* base, int Lpad) {
     s.tab[1] = (float*)p; p += (size_t)Lpad * 4;
     s.rc = (int*)p; p += MAXROWS * 4;
     s.cc = (int*)p; p += MAXROWS * 4;
-    s.xmax = (float*)p; p += 2 * QT * 4;
-    s.xsum = (float*)p; p += 2 * QT * 4;
+    s.xmax = (float*)p; p += 4 * QT * 4;
+    s.xsum = (float*)p; p += 4 * QT * 4;
     s.maxbias = (float*)p; p += 8;
     s.masked = (int*)p; p += 8;
+    s.k2max = (float*)p; p += 16;
     s.qkv_full = (uint64_t*)p; p += 16;
     s.qkv_empty = (uint64_t*)p; p += 16;
     s.aux_full = (uint64_t*)p; p += 16;
     s.aux_empty = (uint64_t*)p; p += 16;
     s.s_full = (uint64_t*)p; p += 8;
-    s.p_full = (uint64_t*)p; p += 8;
+    s.p_full = (uint64_t*)p; p += 32;   // [4]: one per quarter of the key range
     s.o_full = (uint64_t*)p; p += 8;
-    s.tmem_slot = (uint32_t*)p; p += 8;
+    s.tmem_slot = (uint32_t*)p; p += 16;   // (+8 pad: keeps the region-id arrays 16-byte aligned)
     s.reg[0] = p; p += MAXROWS;
     s.reg[1] = p; p += MAXROWS;
     return s;
 }
 size_t fwd_smem_bytes(int Lpad) {
-    return 1024 + 2 * (size_t)STAGE_BYTES + 2 * (size_t)Lpad * 4 + 2 * MAXROWS * 4 + 4 * QT * 4 + 16 + 4 * 16 + 3 * 8 + 8 +
+    return 1024 + 2 * (size_t)STAGE_BYTES + 2 * (size_t)Lpad * 4 + 2 * MAXROWS * 4 + 8 * QT * 4 + 32 + 4 * 16 + 3 * 8 + 8 + 24 + 8 +
            2 * MAXROWS + 64;
 }
 
-__global__ void __launch_bounds__(NTHREADS, 1)
+
+// ---- softmax helpers -------------------------------------------------------------------------
+constexpr float MASKV = -100.0f * LOG2E;   // the reference's additive -100 (video_swin.py:304-306), in log2 units
+
+// 16 consecutive ints / bytes from 16-byte aligned shared memory
+__device__ __forceinline__ void lds16i(uint32_t addr, uint32_t (&v)[16]) {
+    const uint4 a = tc::lds_u4(addr), b = tc::lds_u4(addr + 16), c = tc::lds_u4(addr + 32), d = tc::lds_u4(addr + 48);
+    v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+    v[8] = c.x; v[9] = c.y; v[10] = c.z; v[11] = c.w; v[12] = d.x; v[13] = d.y; v[14] = d.z; v[15] = d.w;
+}
+// per-byte "region differs" flags of 16 keys: 0xFF where reg[j] != regi
+__device__ __forceinline__ void neq16(uint32_t reg16_addr, uint32_t regi4, uint32_t (&w)[4]) {
+    const uint4 r = tc::lds_u4(reg16_addr);
+    w[0] = __vcmpne4(r.x, regi4); w[1] = __vcmpne4(r.y, regi4); w[2] = __vcmpne4(r.z, regi4); w[3] = __vcmpne4(r.w, regi4);
+}
+__device__ __forceinline__ float mask_add(float v, const uint32_t (&w)[4], int e) {
+    return (w[e >> 2] & (0xFFu << (8 * (e & 3)))) ? v + MASKV : v;
+}
+
+// squared L2 norm of one head row (32 bf16 = 64 B, 16-byte aligned) in global memory
+__device__ __forceinline__ float row_norm2(const __nv_bfloat16* rowp) {
+    const uint4* v4 = reinterpret_cast<const uint4*>(rowp);
+    float acc = 0.f;
+#pragma unroll
+    for (int v = 0; v < 4; ++v) {
+        const uint4 a = __ldg(v4 + v);
+        const uint32_t w[4] = {a.x, a.y, a.z, a.w};
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+            const float2 x = tc::unpack_bf16(w[e]);
+            acc = fmaf(x.x, x.x, acc);
+            acc = fmaf(x.y, x.y, acc);
+        }
+    }
+    return acc;
+}
+
+// The Npad key columns of a row are cut into NPARTS parts (one softmax warp each), each part into NSUB
+// sub-batches (the granularity at which P is handed to the P.V MMAs); all boundaries are multiples of 16.
+__device__ __forceinline__ int part_bound(int Npad, int part) { return ((((Npad >> 4) * part) / NPARTS) << 4); }
+__device__ __forceinline__ int sub_bound(int Npad, int part, int sub) {
+    const int beg = part_bound(Npad, part), nck = (part_bound(Npad, part + 1) - beg) >> 4;
+    return beg + (((nck * sub) / NSUB) << 4);
+}
+
+// ---- forward softmax over the full chunks [cbeg, cfull) of one row, software-pipelined TMEM loads --------
+// pass 1: row max (raw accumulator when !MASKED: the caller scales afterwards; scaled + mask when MASKED)
+template <bool MASKED>
+__device__ __forceinline__ float fwd_rowmax(uint32_t srow, int cbeg, int cfull, uint32_t reg_a, uint32_t regi4,
+                                            float scale_log2) {
+    float mx = -INFINITY;
+    if (cbeg >= cfull) return mx;
+    uint32_t a[16], b[16];
+    auto body = [&](const uint32_t (&r)[16], int c) {
+        if (MASKED) {
+            uint32_t nq4[4];
+            neq16(reg_a + c, regi4, nq4);
+#pragma unroll
+            for (int e = 0; e < 16; ++e) mx = fmaxf(mx, mask_add(__uint_as_float(r[e]) * scale_log2, nq4, e));
+        } else {
+#pragma unroll
+            for (int e = 0; e < 16; ++e) mx = fmaxf(mx, __uint_as_float(r[e]));
+        }
+    };
+    tc::tmem_ld_32x16(srow + cbeg, a);
+    tc::tmem_ld_wait();
+    for (int c = cbeg; c < cfull; c += 32) {
+        const bool hb = c + 16 < cfull, ha = c + 32 < cfull;
+        if (hb) tc::tmem_ld_32x16(srow + c + 16, b);
+        body(a, c);
+        if (hb) {
+            tc::tmem_ld_wait();
+            if (ha) tc::tmem_ld_32x16(srow + c + 32, a);
+            body(b, c + 16);
+            if (ha) tc::tmem_ld_wait();
+        }
+    }
+    return mx;
+}
+
+// pass 2: p = exp2(acc*scale_log2 + bias[rowcode+colcode] (+mask) - max) -> packed bf16 back into TMEM, returns row sum
+template <bool MASKED>
+__device__ __forceinline__ float fwd_exp(uint32_t srow, uint32_t prow, int cbase, int cbeg, int cfull, uint32_t tabrow,
+                                         uint32_t cc_a, uint32_t reg_a, uint32_t regi4, float scale_log2, float nm) {
+    float sum = 0.f;
+    if (cbeg >= cfull) return sum;
+    uint32_t a[16], b[16];
+    auto body = [&](const uint32_t (&r)[16], int c) {
+        uint32_t cj[16], nq4[4];
+        lds16i(cc_a + c * 4, cj);
+        if (MASKED) neq16(reg_a + c, regi4, nq4);
+        float tb[16];
+#pragma unroll
+        for (int e = 0; e < 16; ++e) tb[e] = tc::lds_f32(tabrow + cj[e]);
+        uint32_t pw[8];
+#pragma unroll
+        for (int e = 0; e < 16; e += 2) {
+            float v0 = fmaf(__uint_as_float(r[e]), scale_log2, tb[e]) + nm;
+            float v1 = fmaf(__uint_as_float(r[e + 1]), scale_log2, tb[e + 1]) + nm;
+            if (MASKED) { v0 = mask_add(v0, nq4, e); v1 = mask_add(v1, nq4, e + 1); }
+            const float p0 = tc::ex2_approx(v0), p1 = tc::ex2_approx(v1);
+            sum += p0 + p1;
+            pw[e / 2] = tc::pack_bf16(p0, p1);
+        }
+        tc::tmem_st_32x8(prow + (c - cbase) / 2, pw);
+    };
+    tc::tmem_ld_32x16(srow + cbeg, a);
+    tc::tmem_ld_wait();
+    for (int c = cbeg; c < cfull; c += 32) {
+        const bool hb = c + 16 < cfull, ha = c + 32 < cfull;
+        if (hb) tc::tmem_ld_32x16(srow + c + 16, b);
+        body(a, c);
+        if (hb) {
+            tc::tmem_ld_wait();
+            if (ha) tc::tmem_ld_32x16(srow + c + 32, a);
+            body(b, c + 16);
+            if (ha) tc::tmem_ld_wait();
+        }
+    }
+    return sum;
+}
+
+__global__ void __launch_bounds__(FWD_THREADS, 1)
 attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const FwdParams p) {
     extern __shared__ uint8_t smem_raw[];
-    uint8_t* base = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    uint8_t* base = smem_raw + ((1024u - (tc::smem_u32(smem_raw) & 1023u)) & 1023u);   // keeps the shared address space
     const Smem s = carve(base, p.Lpad);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int C = p.nH * HD;
@@ -90,13 +219,17 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const FwdParams p)
         tc::prefetch_tmap(&tmQKV);
         for (int i = 0; i < 2; ++i) {
             tc::mbar_init(&s.qkv_full[i], 1); tc::mbar_init(&s.qkv_empty[i], 1);
-            tc::mbar_init(&s.aux_full[i], 1); tc::mbar_init(&s.aux_empty[i], 8);
+            tc::mbar_init(&s.aux_full[i], 1); tc::mbar_init(&s.aux_empty[i], 4 * NPARTS);
         }
-        tc::mbar_init(s.s_full, 1); tc::mbar_init(s.p_full, 8); tc::mbar_init(s.o_full, 1);
+        tc::mbar_init(s.s_full, 1); tc::mbar_init(s.o_full, 1);
+        for (int i = 0; i < NSUB; ++i) tc::mbar_init(&s.p_full[i], 4 * NPARTS);
         tc::fence_barrier_init();
     }
     if (warp == 1) tc::tmem_alloc(s.tmem_slot, TMEM_COLS);
-    for (int n = threadIdx.x; n < p.N; n += NTHREADS) { s.rc[n] = p.rowcode[n]; s.cc[n] = p.colcode[n]; }
+    for (int n = threadIdx.x; n < MAXROWS; n += FWD_THREADS) {   // cc holds BYTE offsets into the fp32 table copy
+        s.rc[n] = n < p.N ? p.rowcode[n] : 0;
+        s.cc[n] = n < p.N ? p.colcode[n] * 4 : 0;
+    }
     tc::tc_fence_before();
     __syncthreads();
     tc::tc_fence_after();
@@ -144,14 +277,24 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const FwdParams p)
                 };
                 issue_qk(0);
                 for (int t = 0; t < p.nq; ++t) {
-                    tc::mbar_wait(s.p_full, pph); pph ^= 1;
-                    tc::tc_fence_after();
-                    for (int kc = 0; kc < p.Npad / 16; ++kc) {
-                        const int key0 = kc * 16;
-                        const int pcol = key0 < p.split ? key0 / 2 : p.split + (key0 - p.split) / 2;
-                        tc::umma_bf16_ts(tmem + O_COL, tmem + S_COL + pcol, tc::smem_desc_sw64(va + key0 * 64, 0, 512),
-                                         idesc_pv, kc);
+                    // P.V is issued quarter by quarter while the softmax warps are still producing the rest of P
+                    uint32_t acc_pv = 0;
+                    const uint32_t vdesc0_hi = (uint32_t)(tc::smem_desc_sw64(va, 0, 512) >> 32);
+                    for (int qq = 0; qq < NSUB; ++qq) {
+                        tc::mbar_wait(&s.p_full[qq], pph);
+                        tc::tc_fence_after();
+#pragma unroll
+                        for (int part = 0; part < NPARTS; ++part) {
+                            const int k00 = part_bound(p.Npad, part);
+                            const int kb0 = sub_bound(p.Npad, part, qq), kb1 = sub_bound(p.Npad, part, qq + 1);
+                            for (int key0 = kb0; key0 < kb1; key0 += 16) {
+                                const uint64_t vd = ((uint64_t)vdesc0_hi << 32) | (((va + key0 * 64) & 0x3FFFFu) >> 4);
+                                tc::umma_bf16_ts(tmem + O_COL, tmem + S_COL + k00 + (key0 - k00) / 2, vd, idesc_pv, acc_pv);
+                                acc_pv = 1;
+                            }
+                        }
                     }
+                    pph ^= 1;
                     tc::umma_commit(s.o_full);
                     if (t + 1 < p.nq) issue_qk(t + 1);
                 }
@@ -183,17 +326,21 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const FwdParams p)
                 }
             }
             diff = __any_sync(0xffffffffu, diff);
-            if (lane == 0) { s.maxbias[st] = mb; s.masked[st] = diff; }
+            float k2 = 0.f;   // max_j |k_j|^2: with |q_i| it bounds the scores of row i (Cauchy-Schwarz)
+            for (int n = lane; n < p.N; n += 32)
+                k2 = fmaxf(k2, row_norm2(p.qkv + (((long long)b_ * p.N + n) * 3 + 1) * C + h * HD));
+            k2 = warp_max(k2);
+            if (lane == 0) { s.maxbias[st] = mb; s.masked[st] = diff; s.k2max[st] = k2; }
             __syncwarp();
             if (lane == 0) tc::mbar_arrive(&s.aux_full[st]);
         }
     } else if (warp >= 4) {
         // ===================== softmax + epilogue warps =====================
-        const int q = warp & 3, half = (warp - 4) >> 2;
+        const int q = warp & 3, half = (warp - 4) >> 2;   // `half` = column part of this warp (0..NPARTS-1)
         const int row = q * 32 + lane;
         const uint32_t lane_base = (uint32_t)(q * 32) << 16;
-        const int cbeg = half == 0 ? 0 : p.split, cend = half == 0 ? p.split : p.Npad;
-        const int pbase = half == 0 ? 0 : p.split;   // P (packed bf16) column base, aliases S
+        const int cbeg = part_bound(p.Npad, half), cend = part_bound(p.Npad, half + 1);
+        const int pbase = cbeg;   // P (packed bf16) column base, aliases the part's own S columns
         int it = 0; uint32_t sph = 0, oph = 0;
         for (int w = blockIdx.x; w < items; w += gridDim.x, ++it) {
             const int st = it & 1; const uint32_t ph = (it >> 1) & 1;
@@ -201,73 +348,116 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const FwdParams p)
             tc::mbar_wait(&s.aux_full[st], ph);
             const bool masked = s.masked[st] != 0;
             const float mb = s.maxbias[st];
+            const float k2max = s.k2max[st];
             const float* tab = s.tab[st];
             const uint8_t* reg = s.reg[st];
+            const uint32_t reg_a = tc::smem_u32(reg), cc_a = tc::smem_u32(s.cc);
             for (int t = 0; t < p.nq; ++t) {
                 const int i = t * QT + row;
                 const bool valid = i < p.N;
                 const int ic = valid ? i : p.N - 1;
                 const int rci = s.rc[ic];
                 const uint8_t regi = masked ? reg[ic] : 0;
+                // Single-pass softmax when it is provably safe: |s_ij| <= |q_i| max_j|k_j| scale =: bound, so with
+                // m = bound every exponent lies in [-2 bound - bias range, 0]; for bound <= 50 (log2 units) nothing
+                // can underflow fp32/bf16.  Otherwise (huge logits) fall back to the exact two-pass row max.
+                const float bound = sqrtf(row_norm2(p.qkv + (((long long)b_ * p.N + ic) * 3) * C + h * HD) * k2max) * p.scale_log2;
+                const bool fast = __all_sync(0xffffffffu, bound <= 50.0f);
+                long long t_a = clock64();
                 tc::mbar_wait(s.s_full, sph); sph ^= 1;
                 tc::tc_fence_after();
-                // ---- pass 1: row max of scale*S (+mask); the bias is bounded by its per-head maximum
+                long long t_b = clock64();
+                // ---- pass 1: row max of the raw scores (+ exact mask term in masked windows); the bias is
+                //      bounded by its per-head maximum `mb`, so mx below is an upper bound of the true row max
+                const bool warp_rows = t * QT + q * 32 < p.N;   // warp-uniform: any valid row in this warp?
+                const int cfull = min(cend, p.N & ~15);          // chunks below cfull have no padded columns
+                const uint32_t regi4 = (uint32_t)regi * 0x01010101u;
                 float mx = -INFINITY;
-                for (int c = cbeg; c < cend; c += 16) {
-                    uint32_t r[16];
-                    tc::tmem_ld_32x16(tmem + lane_base + S_COL + c, r);
-                    tc::tmem_ld_wait();
-                    const bool tail = c + 16 > p.N;
+                if (fast) {
+                    mx = bound + mb;
+                } else {
+                if (warp_rows) {
+                    const uint32_t srow = tmem + lane_base + S_COL;
+                    mx = masked ? fwd_rowmax<true>(srow, cbeg, cfull, reg_a, regi4, p.scale_log2)
+                                : fwd_rowmax<false>(srow, cbeg, cfull, reg_a, regi4, p.scale_log2);
+                    for (int c = max(cbeg, cfull); c < cend; c += 16) {   // chunk with columns >= N
+                        uint32_t r[16];
+                        tc::tmem_ld_32x16(tmem + lane_base + S_COL + c, r);
+                        tc::tmem_ld_wait();
 #pragma unroll
-                    for (int e = 0; e < 16; ++e) {
-                        float v = __uint_as_float(r[e]) * p.scale_log2;
-                        if (masked) v += (reg[min(c + e, p.N - 1)] != regi) ? -100.0f * LOG2E : 0.0f;
-                        if (!tail || c + e < p.N) mx = fmaxf(mx, v);
+                        for (int e = 0; e < 16; ++e) {
+                            if (c + e < p.N) {
+                                float v = __uint_as_float(r[e]);
+                                if (masked) v = v * p.scale_log2 + ((reg[c + e] != regi) ? MASKV : 0.f);
+                                mx = fmaxf(mx, v);
+                            }
+                        }
                     }
+                    if (!masked) mx *= p.scale_log2;   // scale > 0: max commutes with the scaling
                 }
                 s.xmax[half * QT + row] = mx;
-                tc::named_bar_sync(1 + q, 64);
-                mx = fmaxf(mx, s.xmax[(half ^ 1) * QT + row]) + mb;
-                // ---- pass 2: p = exp2(s - max) -> packed bf16 into TMEM (aliasing S), row sum in fp32
-                float sum = 0.f;
-                for (int c = cbeg; c < cend; c += 16) {
-                    uint32_t r[16];
-                    tc::tmem_ld_32x16(tmem + lane_base + S_COL + c, r);
-                    tc::tmem_ld_wait();
-                    const bool tail = c + 16 > p.N;
-                    uint32_t pw[8];
+                tc::named_bar_sync(1 + q, 32 * NPARTS);
 #pragma unroll
-                    for (int e = 0; e < 16; e += 2) {
-                        float pv[2];
-#pragma unroll
-                        for (int u = 0; u < 2; ++u) {
-                            const int j = c + e + u;
-                            const int jc = tail ? min(j, p.N - 1) : j;
-                            float v = fmaf(__uint_as_float(r[e + u]), p.scale_log2, tab[rci + s.cc[jc]]) - mx;
-                            if (masked) v += (reg[jc] != regi) ? -100.0f * LOG2E : 0.0f;
-                            float pe = tc::ex2_approx(v);
-                            if (tail && j >= p.N) pe = 0.f;
-                            pv[u] = pe;
-                            sum += pe;
-                        }
-                        pw[e / 2] = tc::pack_bf16(pv[0], pv[1]);
-                    }
-                    tc::tmem_st_32x8(tmem + lane_base + S_COL + pbase + (c - cbeg) / 2, pw);
+                for (int k = 0; k < NPARTS; ++k) mx = fmaxf(mx, s.xmax[k * QT + row]);
+                mx += mb;
                 }
-                tc::tmem_st_wait();
-                s.xsum[half * QT + row] = sum;
-                tc::tc_fence_before();
-                __syncwarp();
-                if (lane == 0) tc::mbar_arrive(s.p_full);
+                long long t_c = clock64();
+                // ---- pass 2: p = exp2(s - max) -> packed bf16 into TMEM (aliasing S), row sum in fp32.
+                //      Done in four key-range quarters; after each one the MMA warp may start that part of P.V
+                float sum = 0.f;
+                const uint32_t tabrow = tc::smem_u32(tab + rci);
+                const float nm = -mx;
+                const uint32_t srow = tmem + lane_base + S_COL, prow = srow + pbase;
+                for (int qq = 0; qq < NSUB; ++qq) {
+                    const int qb = sub_bound(p.Npad, half, qq), qe = sub_bound(p.Npad, half, qq + 1);
+                    if (warp_rows) {
+                        const int qf = min(qe, cfull);
+                        sum += masked ? fwd_exp<true>(srow, prow, cbeg, qb, qf, tabrow, cc_a, reg_a, regi4, p.scale_log2, nm)
+                                      : fwd_exp<false>(srow, prow, cbeg, qb, qf, tabrow, cc_a, reg_a, regi4, p.scale_log2, nm);
+                        for (int c = max(qb, cfull); c < qe; c += 16) {   // chunk with columns >= N
+                            uint32_t r[16];
+                            tc::tmem_ld_32x16(srow + c, r);
+                            tc::tmem_ld_wait();
+                            uint32_t pw[8];
+#pragma unroll
+                            for (int e = 0; e < 16; e += 2) {
+                                float pv[2];
+#pragma unroll
+                                for (int u = 0; u < 2; ++u) {
+                                    const int j = c + e + u;
+                                    float pe = 0.f;
+                                    if (j < p.N) {
+                                        float v = fmaf(__uint_as_float(r[e + u]), p.scale_log2, tc::lds_f32(tabrow + s.cc[j])) + nm;
+                                        if (masked && reg[j] != regi) v += MASKV;
+                                        pe = tc::ex2_approx(v);
+                                    }
+                                    pv[u] = pe;
+                                    sum += pe;
+                                }
+                                pw[e / 2] = tc::pack_bf16(pv[0], pv[1]);
+                            }
+                            tc::tmem_st_32x8(prow + (c - cbeg) / 2, pw);
+                        }
+                    }
+                    tc::tmem_st_wait();
+                    if (qq == NSUB - 1) s.xsum[half * QT + row] = sum;
+                    tc::tc_fence_before();
+                    __syncwarp();
+                    if (lane == 0) tc::mbar_arrive(&s.p_full[qq]);
+                }
+                long long t_d = clock64();
                 // ---- epilogue: O / l -> bf16 -> global; lse
                 tc::mbar_wait(s.o_full, oph); oph ^= 1;
                 tc::tc_fence_after();
-                const float l = s.xsum[row] + s.xsum[QT + row];
+                long long t_e = clock64();
+                float l = 0.f;
+#pragma unroll
+                for (int k = 0; k < NPARTS; ++k) l += s.xsum[k * QT + row];
                 const float inv = __fdividef(1.0f, l);
                 uint32_t o[16];
-                tc::tmem_ld_32x16(tmem + lane_base + O_COL + half * 16, o);
+                tc::tmem_ld_32x16(tmem + lane_base + O_COL + (half & 1) * 16, o);
                 tc::tmem_ld_wait();
-                if (valid) {
+                if (valid && half < 2) {
                     __nv_bfloat16* dst = p.out + ((long long)b_ * p.N + i) * C + h * HD + half * 16;
                     uint4 u0, u1;
                     u0.x = tc::pack_bf16(__uint_as_float(o[0]) * inv, __uint_as_float(o[1]) * inv);
@@ -283,6 +473,10 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const FwdParams p)
                     if (half == 0) p.lse[((long long)b_ * p.nH + h) * p.N + i] = (mx + __log2f(l)) * LN2;
                 }
                 tc::tc_fence_before();  // O reads complete before the next tile's p_full arrive lets PV overwrite O
+                if (p.dbg && blockIdx.x == 0 && threadIdx.x == 128) {
+                    long long t_f = clock64();
+                    p.dbg[0] += t_b - t_a; p.dbg[1] += t_c - t_b; p.dbg[2] += t_d - t_c; p.dbg[3] += t_e - t_d; p.dbg[4] += t_f - t_e; p.dbg[5] += 1;
+                }
             }
             __syncwarp();
             if (lane == 0) tc::mbar_arrive(&s.aux_empty[st]);
@@ -315,13 +509,27 @@ int tc_attn_fwd(const void* qkv, const void* table, const int32_t* rowcode, cons
     CUtensorMap tm;
     if (!make_tmap_3d_bf16(&tm, qkv, B_, N, 3 * C, 3 * C, (uint64_t)N * 3 * C, QT, HD, 64)) return VSW_ERR_CUDA;
     FwdParams p{};
-    p.table = (const __nv_bfloat16*)table; p.rowcode = rowcode; p.colcode = colcode; p.region = region;
+    p.qkv = (const __nv_bfloat16*)qkv; p.table = (const __nv_bfloat16*)table; p.rowcode = rowcode; p.colcode = colcode; p.region = region;
     p.out = (__nv_bfloat16*)out; p.lse = lse;
     p.B_ = B_; p.nW = nW; p.N = N; p.nH = nH; p.L = L; p.Lpad = Lpad;
     p.scale_log2 = scale * LOG2E;
     p.Npad = (N + 15) / 16 * 16;
     p.nq = (N + QT - 1) / QT;
-    p.split = (p.Npad / 64) * 32;
+    {
+        static long long* dbg = nullptr;
+        static bool init = false;
+        if (!init) {
+            init = true;
+            if (getenv("VSW_ATTN_DEBUG")) { cudaMalloc(&dbg, 64); cudaMemset(dbg, 0, 64); }
+        }
+        p.dbg = dbg;
+        if (dbg && getenv("VSW_ATTN_DEBUG_DUMP")) {
+            long long h[8];
+            cudaMemcpy(h, dbg, 64, cudaMemcpyDeviceToHost);
+            if (h[5]) fprintf(stderr, "[vsw attn fwd] tiles=%lld avg cycles: wait_s=%lld pass1=%lld pass2=%lld wait_o=%lld epi=%lld\n", h[5], h[0]/h[5], h[1]/h[5], h[2]/h[5], h[3]/h[5], h[4]/h[5]);
+            cudaMemset(dbg, 0, 64);
+        }
+    }
     static bool configured = false;
     if (!configured) {
         cudaError_t e = cudaFuncSetAttribute(attn_fwd_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
@@ -330,7 +538,7 @@ int tc_attn_fwd(const void* qkv, const void* table, const int32_t* rowcode, cons
     }
     const int items = B_ * nH;
     const int grid = items < kNumSMs ? items : kNumSMs;
-    attn_fwd_tc_kernel<<<grid, NTHREADS, smem, st>>>(tm, p);
+    attn_fwd_tc_kernel<<<grid, FWD_THREADS, smem, st>>>(tm, p);
     return check_launch("attn_fwd_tc");
 }
 

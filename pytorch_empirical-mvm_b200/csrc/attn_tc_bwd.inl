@@ -26,13 +26,17 @@ struct BwdParams {
     int B_, nW, N, nH, L, Lpad, groups;
     float scale, scale_log2;
     int Npad, nq, nkb;
+    long long* dbg;
+    int wd, hw, boxhw;   // key permutation: column c' = hw_index * wd + plane (plane = temporal slab of the window)
 };
 
 struct BwdSmem {
     float* tab; float* hist;          // [Lpad], [8][Lpad]
     float* delta; float* lse2;        // [2][512] each (one copy per column half)
     int* rc; int* cc;                 // [512]
-    uint8_t* reg[2]; int* masked;     // region ids per item (double-buffered)
+    uint8_t* reg[2]; int* masked;     // region ids per item in COLUMN order (double-buffered)
+    uint8_t* regq[2];                 // region ids per item in QUERY (natural) order
+    int* batched;                     // 1 if the wd keys of one spatial position never share a histogram entry within a warp
     uint64_t *kv_full, *kv_empty, *qd_full, *qd_empty, *s_full, *pds_full, *dkv_full, *dq_full, *aux_full, *aux_empty;
     uint32_t* tmem_slot;
 };
@@ -59,20 +63,23 @@ __device__ __forceinline__ BwdSmem bwd_carve(uint8_t* base, int Lpad) {
     s.tmem_slot = (uint32_t*)p; p += 8;
     s.reg[0] = p; p += 512;
     s.reg[1] = p; p += 512;
+    s.regq[0] = p; p += 512;
+    s.regq[1] = p; p += 512;
+    s.batched = (int*)p; p += 16;
     return s;
 }
 size_t bwd_smem_bytes(int Lpad) {
-    return 1024 + BW_MISC_OFF + (size_t)9 * Lpad * 4 + 4 * 512 * 4 + 2 * 512 * 4 + 15 * 8 + 16 + 1024 + 64;
+    return 1024 + BW_MISC_OFF + (size_t)9 * Lpad * 4 + 4 * 512 * 4 + 2 * 512 * 4 + 15 * 8 + 16 + 2048 + 16 + 64;
 }
 
 // byte offset of the 16-byte unit holding keys [8u, 8u+8) of query row i inside a 128B-swizzled chunk
 __device__ __forceinline__ uint32_t sw128_off(int row, int unit) { return row * 128 + ((unit ^ (row & 7)) << 4); }
 
 __global__ void __launch_bounds__(NTHREADS, 1)
-attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant__ CUtensorMap tmDO,
-                   const BwdParams p) {
+attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant__ CUtensorMap tmKV,
+                   const __grid_constant__ CUtensorMap tmDO, const BwdParams p) {
     extern __shared__ uint8_t smem_raw[];
-    uint8_t* base = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    uint8_t* base = smem_raw + ((1024u - (tc::smem_u32(smem_raw) & 1023u)) & 1023u);   // keeps the shared address space
     const BwdSmem s = bwd_carve(base, p.Lpad);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int C = p.nH * HD;
@@ -80,6 +87,7 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_const
 
     if (warp == 0 && lane == 0) {
         tc::prefetch_tmap(&tmQKV);
+        tc::prefetch_tmap(&tmKV);
         tc::prefetch_tmap(&tmDO);
         tc::mbar_init(s.kv_full, 1); tc::mbar_init(s.kv_empty, 1);
         for (int i = 0; i < 2; ++i) {
@@ -91,9 +99,12 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_const
     }
     if (warp == 1) tc::tmem_alloc(s.tmem_slot, TMEM_COLS);
     // one-time shared-memory state: codes, bias column (x log2e), zeroed histograms and P/dS tiles
+    if (threadIdx.x == 0) *s.batched = 1;
     for (int n = threadIdx.x; n < 512; n += NTHREADS) {
         s.rc[n] = n < p.N ? p.rowcode[n] : 0;
-        s.cc[n] = n < p.N ? p.colcode[n] : 0;
+        // column c' of the permuted key order holds key j = plane * hw + spatial index
+        const int sp = n / p.wd, pl = n - sp * p.wd;
+        s.cc[n] = sp < p.hw ? p.colcode[pl * p.hw + sp] * 4 : 0;   // BYTE offsets into the fp32 table / histogram rows
     }
     for (int l = threadIdx.x; l < p.L; l += NTHREADS)
         s.tab[l] = __bfloat162float(p.table[(long long)l * p.nH + h]) * LOG2E;
@@ -103,8 +114,29 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_const
     tc::fence_proxy_async();
     tc::tc_fence_before();
     __syncthreads();
+    // Validate the batched histogram update: the wd keys of one spatial position must map to wd entries a
+    // constant stride apart, and no two rows of one (aligned) warp may be a multiple of that stride apart.
+    if (p.wd > 1) {
+        const int stride = (s.cc[1] - s.cc[0]) / 4;   // colcode(plane 1) - colcode(plane 0)
+        bool ok = stride != 0;
+        for (int n = threadIdx.x; n < p.hw * p.wd && ok; n += NTHREADS) {
+            const int sp = n / p.wd, pl = n - sp * p.wd;
+            ok = (s.cc[n] - s.cc[sp * p.wd]) == 4 * pl * stride;
+        }
+        for (int i = threadIdx.x; i < p.N && ok; i += NTHREADS) {
+            const int blk_end = min(p.N, (i | 31) + 1);
+            for (int i2 = i + 1; i2 < blk_end; ++i2)
+                if ((s.rc[i2] - s.rc[i]) % stride == 0) { ok = false; break; }
+        }
+        if (!ok) *s.batched = 0;
+    } else if (threadIdx.x == 0) {
+        *s.batched = 0;
+    }
+    __syncthreads();
     tc::tc_fence_after();
     const uint32_t tmem = *s.tmem_slot;
+    // valid columns of key block kb (the block's padded columns are all at its end)
+    auto block_cols = [&](int kb) { return (min(p.hw, (kb + 1) * p.boxhw) - kb * p.boxhw) * p.wd; };
 
     if (warp == 0) {
         // ===================== TMA producer =====================
@@ -114,8 +146,8 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_const
                 for (int kb = 0; kb < p.nkb; ++kb, ++kvn) {
                     tc::mbar_wait(s.kv_empty, (kvn & 1) ^ 1);
                     tc::mbar_expect_tx(s.kv_full, 2 * BOX_BYTES);
-                    tc::tma_load_3d(&tmQKV, s.kv_full, base + BW_KV_OFF, C + h * HD, kb * QT, b_);
-                    tc::tma_load_3d(&tmQKV, s.kv_full, base + BW_KV_OFF + BOX_BYTES, 2 * C + h * HD, kb * QT, b_);
+                    tc::tma_load_4d(&tmKV, s.kv_full, base + BW_KV_OFF, C + h * HD, 0, kb * p.boxhw, b_);
+                    tc::tma_load_4d(&tmKV, s.kv_full, base + BW_KV_OFF + BOX_BYTES, 2 * C + h * HD, 0, kb * p.boxhw, b_);
                     for (int t = 0; t < p.nq; ++t, ++blk) {
                         const int st = blk & 1; const uint32_t ph = (blk >> 1) & 1;
                         tc::mbar_wait(&s.qd_empty[st], ph ^ 1);
@@ -137,7 +169,7 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_const
             const uint32_t id_q = tc::idesc_bf16(QT, HD, 0, 1);   // A K-major (dS), B MN-major (K)
             for (int b_ = gi; b_ < p.B_; b_ += p.groups) {
                 for (int kb = 0; kb < p.nkb; ++kb, ++kvn) {
-                    const int nkeys = min(QT, p.Npad - kb * QT);
+                    const int nkeys = (block_cols(kb) + 15) & ~15;
                     const uint32_t id_s = tc::idesc_bf16(QT, nkeys, 0, 0);
                     tc::mbar_wait(s.kv_full, kvn & 1);
                     for (int t = 0; t < p.nq; ++t, ++blk) {
@@ -186,9 +218,11 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_const
             if (p.region) {
                 const uint8_t* rg = p.region + (long long)(b_ % p.nW) * p.N;
                 const uint8_t r0 = rg[0];
-                for (int n = lane; n < p.N; n += 32) {
-                    const uint8_t r = rg[n];
+                for (int n = lane; n < 512; n += 32) {
+                    const int sp = n / p.wd, pl = n - sp * p.wd;
+                    const uint8_t r = sp < p.hw ? rg[pl * p.hw + sp] : r0;   // column (permuted key) order
                     s.reg[st][n] = r;
+                    s.regq[st][n] = n < p.N ? rg[n] : r0;                   // query order
                     diff |= (r != r0);
                 }
             }
@@ -213,8 +247,10 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_const
             tc::mbar_wait(&s.aux_full[st], ph);
             const bool masked = s.masked[st] != 0;
             const uint8_t* reg = s.reg[st];
+            const bool batched = *s.batched != 0;
             for (int kb = 0; kb < p.nkb; ++kb) {
-                const int nkeys = min(QT, p.Npad - kb * QT);
+                const int nv = block_cols(kb);                 // valid columns of this key block
+                const int nkeys = (nv + 15) & ~15;
                 const int cbeg = half * 64, cend = min(cbeg + 64, nkeys);   // my columns inside the block
                 for (int t = 0; t < p.nq; ++t) {
                     const int i = t * QT + row;
@@ -247,9 +283,11 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_const
                     }
                     const int ic = valid ? i : p.N - 1;
                     const int rci = s.rc[ic];
-                    const uint8_t regi = masked ? reg[ic] : 0;
+                    const uint8_t regi = masked ? s.regq[st][ic] : 0;
+                    long long t_a = clock64();
                     tc::mbar_wait(s.s_full, sph); sph ^= 1;
                     tc::tc_fence_after();
+                    long long t_b = clock64();
                     if (!warp_valid) {
                         // rows beyond the window: contribute zeros to the reductions over queries
                         for (int u = 0; u < 8; ++u) {
@@ -257,7 +295,71 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_const
                             *reinterpret_cast<uint4*>(dstile + sw128_off(row, u)) = make_uint4(0, 0, 0, 0);
                         }
                     } else {
-                        for (int c = cbeg; c < cend; c += 16) {
+                        const uint32_t tabrow = tc::smem_u32(s.tab + rci), histrow = tc::smem_u32(hist + rci);
+                        const uint32_t cc_a = tc::smem_u32(s.cc), reg_a = tc::smem_u32(reg);
+                        const uint32_t pt_a = tc::smem_u32(ptile), ds_a = tc::smem_u32(dstile);
+                        const uint32_t regi4 = (uint32_t)regi * 0x01010101u;
+                        const float nl2v = valid ? nl2 : -INFINITY;          // invalid rows: P = dS = 0
+                        const int k0 = kb * QT;
+                        const int cfull = min(cend, nv & ~15);   // chunks without padded columns
+                        for (int c = cbeg; c < cfull; c += 16) {
+                            uint32_t rs[16], rd[16], nq4[4], cj[16];
+                            tc::tmem_ld_32x16(tmem + lane_base + BW_S + c, rs);
+                            tc::tmem_ld_32x16(tmem + lane_base + BW_DP + c, rd);
+                            lds16i(cc_a + (k0 + c) * 4, cj);
+                            if (masked) neq16(reg_a + k0 + c, regi4, nq4);
+                            float tb[16], dsv[16];
+#pragma unroll
+                            for (int e = 0; e < 16; ++e) tb[e] = tc::lds_f32(tabrow + cj[e]);
+                            tc::tmem_ld_wait();
+                            uint32_t pw[8], dw[8];
+#pragma unroll
+                            for (int e = 0; e < 16; e += 2) {
+                                float v0 = fmaf(__uint_as_float(rs[e]), p.scale_log2, tb[e]) + nl2v;
+                                float v1 = fmaf(__uint_as_float(rs[e + 1]), p.scale_log2, tb[e + 1]) + nl2v;
+                                if (masked) { v0 = mask_add(v0, nq4, e); v1 = mask_add(v1, nq4, e + 1); }
+                                const float p0 = tc::ex2_approx(v0), p1 = tc::ex2_approx(v1);
+                                dsv[e] = p0 * (__uint_as_float(rd[e]) - delta_i);
+                                dsv[e + 1] = p1 * (__uint_as_float(rd[e + 1]) - delta_i);
+                                pw[e / 2] = tc::pack_bf16(p0, p1);
+                                dw[e / 2] = tc::pack_bf16(dsv[e], dsv[e + 1]);
+                            }
+                            if (valid) {
+                                // d(bias table): at one column step the 32 rows of the warp hit 32 distinct entries, but
+                                // (row i, col j) and (row i+1, col j+1) share one, so steps must stay ordered -- except for
+                                // the wd columns of one spatial position (consecutive in the permuted key order), which are
+                                // a constant plane stride apart and never collide inside a warp (validated at kernel start).
+                                if (batched && p.wd == 8) {
+#pragma unroll
+                                    for (int g = 0; g < 16; g += 8) {
+                                        float hv[8];
+#pragma unroll
+                                        for (int e = 0; e < 8; ++e) hv[e] = tc::lds_f32(histrow + cj[g + e]);
+#pragma unroll
+                                        for (int e = 0; e < 8; ++e) tc::sts_f32(histrow + cj[g + e], hv[e] + dsv[g + e]);
+                                    }
+                                } else if (batched && p.wd == 4) {
+#pragma unroll
+                                    for (int g = 0; g < 16; g += 4) {
+                                        float hv[4];
+#pragma unroll
+                                        for (int e = 0; e < 4; ++e) hv[e] = tc::lds_f32(histrow + cj[g + e]);
+#pragma unroll
+                                        for (int e = 0; e < 4; ++e) tc::sts_f32(histrow + cj[g + e], hv[e] + dsv[g + e]);
+                                    }
+                                } else {
+#pragma unroll
+                                    for (int e = 0; e < 16; ++e)
+                                        tc::sts_f32(histrow + cj[e], tc::lds_f32(histrow + cj[e]) + dsv[e]);
+                                }
+                            }
+                            const int u0 = (c - cbeg) / 8;
+                            tc::sts_u4(pt_a + sw128_off(row, u0), make_uint4(pw[0], pw[1], pw[2], pw[3]));
+                            tc::sts_u4(pt_a + sw128_off(row, u0 + 1), make_uint4(pw[4], pw[5], pw[6], pw[7]));
+                            tc::sts_u4(ds_a + sw128_off(row, u0), make_uint4(dw[0], dw[1], dw[2], dw[3]));
+                            tc::sts_u4(ds_a + sw128_off(row, u0 + 1), make_uint4(dw[4], dw[5], dw[6], dw[7]));
+                        }
+                        for (int c = max(cbeg, cfull); c < cend; c += 16) {   // chunk with columns >= N
                             uint32_t rs[16], rd[16];
                             tc::tmem_ld_32x16(tmem + lane_base + BW_S + c, rs);
                             tc::tmem_ld_32x16(tmem + lane_base + BW_DP + c, rd);
@@ -268,15 +370,16 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_const
                                 float pv[2], dv[2];
 #pragma unroll
                                 for (int u = 0; u < 2; ++u) {
-                                    const int j = kb * QT + c + e + u;
-                                    const bool ok = valid && j < p.N;
-                                    const int jc = j < p.N ? j : p.N - 1;
-                                    const int idx = rci + s.cc[jc];
-                                    float v = fmaf(__uint_as_float(rs[e + u]), p.scale_log2, s.tab[idx]) + nl2;
-                                    if (masked) v += (reg[jc] != regi) ? -100.0f * LOG2E : 0.0f;
-                                    const float pe = ok ? tc::ex2_approx(v) : 0.f;
-                                    const float ds = pe * (__uint_as_float(rd[e + u]) - delta_i);
-                                    if (ok) hist[idx] += ds;   // lanes of a warp hit distinct entries
+                                    const int j = k0 + c + e + u;   // column index (permuted key order)
+                                    float pe = 0.f, ds = 0.f;
+                                    if (valid && c + e + u < nv) {
+                                        const int off = s.cc[j];
+                                        float v = fmaf(__uint_as_float(rs[e + u]), p.scale_log2, tc::lds_f32(tabrow + off)) + nl2;
+                                        if (masked && reg[j] != regi) v += MASKV;
+                                        pe = tc::ex2_approx(v);
+                                        ds = pe * (__uint_as_float(rd[e + u]) - delta_i);
+                                        tc::sts_f32(histrow + off, tc::lds_f32(histrow + off) + ds);
+                                    }
                                     pv[u] = pe;
                                     dv[u] = ds;
                                 }
@@ -294,12 +397,19 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_const
                     tc::tc_fence_before();
                     __syncwarp();
                     if (lane == 0) tc::mbar_arrive(s.pds_full);
+                    if (p.dbg && blockIdx.x == 0 && threadIdx.x == 128) {
+                        long long t_c = clock64();
+                        p.dbg[0] += t_b - t_a; p.dbg[1] += t_c - t_b; p.dbg[2] += 1;
+                    }
                 }
                 // ---- dK (half 0) / dV (half 1) of this key block
+                long long t_d = clock64();
                 tc::mbar_wait(s.dkv_full, dkvph); dkvph ^= 1;
                 tc::tc_fence_after();
+                if (p.dbg && blockIdx.x == 0 && threadIdx.x == 128) { p.dbg[3] += clock64() - t_d; p.dbg[4] += 1; }
                 {
-                    const int key = kb * QT + row;
+                    // TMEM lane `row` of the block = column c' -> key (plane c' % wd, spatial kb*boxhw + c' / wd)
+                    const int key = row < nv ? (row % p.wd) * p.hw + kb * p.boxhw + row / p.wd : p.N;
                     uint32_t lo[16], hi[16];
                     const uint32_t col = half == 0 ? BW_DK : BW_DV;
                     tc::tmem_ld_32x16(tmem + lane_base + col, lo);
@@ -406,7 +516,8 @@ size_t tc_attn_bwd_workspace(int B_, int N, int nH, int hd, int L) {
 
 int tc_attn_bwd(const void* qkv, const void* out, const void* dout, const float* lse, const void* table,
                 const int32_t* rowcode, const int32_t* colcode, const uint8_t* region, void* dqkv, float* dbias,
-                int B_, int nW, int N, int nH, int hd, int L, float scale, void* ws, size_t ws_bytes, cudaStream_t st) {
+                int B_, int nW, int N, int nH, int hd, int L, float scale, int planes, void* ws, size_t ws_bytes,
+                cudaStream_t st) {
     const int Lpad = (L + 3) / 4 * 4;
     const size_t smem = bwd_smem_bytes(Lpad);
     if (hd != HD || N > 448 || N < 1 || nH > kNumSMs || smem > 227 * 1024 || !aligned16(qkv) || !aligned16(out) ||
@@ -418,23 +529,48 @@ int tc_attn_bwd(const void* qkv, const void* out, const void* dout, const float*
     const int groups = bwd_groups(B_, nH);
     if (ws_bytes < (size_t)groups * nH * L * sizeof(float)) { set_error("tcgen05 attention bwd: workspace too small"); return VSW_ERR_WORKSPACE; }
     const int C = nH * HD;
-    CUtensorMap tmQKV, tmDO;
+    // key permutation (plane-minor) when the window depth is a power of two that divides N; else natural order
+    int wd = (planes == 8 || planes == 4 || planes == 2) && N % planes == 0 ? planes : 1;
+    const int hw = N / wd, boxhw = QT / wd;
+    CUtensorMap tmQKV, tmKV, tmDO;
     if (!make_tmap_3d_bf16(&tmQKV, qkv, B_, N, 3 * C, 3 * C, (uint64_t)N * 3 * C, QT, HD, 64)) return VSW_ERR_CUDA;
     if (!make_tmap_3d_bf16(&tmDO, dout, B_, N, C, C, (uint64_t)N * C, QT, HD, 64)) return VSW_ERR_CUDA;
+    {
+        const uint64_t dims[4] = {(uint64_t)3 * C, (uint64_t)wd, (uint64_t)hw, (uint64_t)B_};
+        const uint64_t strides[4] = {1, (uint64_t)hw * 3 * C, (uint64_t)3 * C, (uint64_t)N * 3 * C};
+        const uint32_t box[4] = {HD, (uint32_t)wd, (uint32_t)boxhw, 1};
+        if (!make_tmap_nd_bf16(&tmKV, qkv, 4, dims, strides, box, 64)) return VSW_ERR_CUDA;
+    }
     BwdParams p{};
     p.table = (const __nv_bfloat16*)table; p.rowcode = rowcode; p.colcode = colcode; p.region = region;
     p.out = (const __nv_bfloat16*)out; p.dout = (const __nv_bfloat16*)dout; p.lse = lse;
     p.dqkv = (__nv_bfloat16*)dqkv; p.dbias_part = (float*)ws;
     p.B_ = B_; p.nW = nW; p.N = N; p.nH = nH; p.L = L; p.Lpad = Lpad; p.groups = groups;
     p.scale = scale; p.scale_log2 = scale * LOG2E;
-    p.Npad = (N + 15) / 16 * 16; p.nq = (N + QT - 1) / QT; p.nkb = (p.Npad + QT - 1) / QT;
+    p.Npad = (N + 15) / 16 * 16; p.nq = (N + QT - 1) / QT;
+    p.wd = wd; p.hw = hw; p.boxhw = boxhw; p.nkb = (hw + boxhw - 1) / boxhw;
+    {
+        static long long* dbg = nullptr;
+        static bool init = false;
+        if (!init) {
+            init = true;
+            if (getenv("VSW_ATTN_DEBUG")) { cudaMalloc(&dbg, 64); cudaMemset(dbg, 0, 64); }
+        }
+        p.dbg = dbg;
+        if (dbg && getenv("VSW_ATTN_DEBUG_DUMP")) {
+            long long h[8];
+            cudaMemcpy(h, dbg, 64, cudaMemcpyDeviceToHost);
+            fprintf(stderr, "[vsw attn bwd] blocks=%lld avg cycles: wait_s=%lld softmax=%lld ; kb epilogues=%lld wait_dkv=%lld\n", h[2], h[0]/(h[2]+1), h[1]/(h[2]+1), h[4], h[3]/(h[4]+1));
+            cudaMemset(dbg, 0, 64);
+        }
+    }
     static bool configured = false;
     if (!configured) {
         cudaError_t e = cudaFuncSetAttribute(attn_bwd_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
         if (e != cudaSuccess) { set_error("attn bwd: cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return VSW_ERR_CUDA; }
         configured = true;
     }
-    attn_bwd_tc_kernel<<<groups * nH, NTHREADS, smem, st>>>(tmQKV, tmDO, p);
+    attn_bwd_tc_kernel<<<groups * nH, NTHREADS, smem, st>>>(tmQKV, tmKV, tmDO, p);
     int rc = check_launch("attn_bwd_tc");
     if (rc) return rc;
     tc_dbias_reduce_kernel<<<ceil_div((long long)L * nH, 256), 256, 0, st>>>((const float*)ws, groups, nH, L, dbias);

@@ -78,6 +78,14 @@ __device__ __forceinline__ void tma_load_3d(const CUtensorMap* m, uint64_t* bar,
         : "memory");
 }
 
+// 4-D tiled load
+__device__ __forceinline__ void tma_load_4d(const CUtensorMap* m, uint64_t* bar, void* dst, int c0, int c1, int c2, int c3) {
+    asm volatile(
+        "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+        ::"r"(smem_u32(dst)), "l"((uint64_t)m), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+        : "memory");
+}
+
 // ---------------------------------------------------------------------------------------------
 // device: TMEM + tcgen05
 // ---------------------------------------------------------------------------------------------
@@ -146,6 +154,22 @@ __device__ __forceinline__ void tmem_st_32x8(uint32_t taddr, const uint32_t (&r)
         "tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};"
         ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7])
         : "memory");
+}
+// explicit shared-memory accesses by 32-bit shared address (the compiler cannot always prove that a pointer
+// carved out of the dynamic shared array is in the shared window and would emit slower generic LD/ST)
+__device__ __forceinline__ float lds_f32(uint32_t a) {
+    float v;
+    asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(a));
+    return v;
+}
+__device__ __forceinline__ void sts_f32(uint32_t a, float v) { asm volatile("st.shared.f32 [%0], %1;" ::"r"(a), "f"(v) : "memory"); }
+__device__ __forceinline__ uint4 lds_u4(uint32_t a) {
+    uint4 v;
+    asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(a));
+    return v;
+}
+__device__ __forceinline__ void sts_u4(uint32_t a, uint4 v) {
+    asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(a), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
 }
 __device__ __forceinline__ float ex2_approx(float x) {
     float y;
@@ -218,6 +242,9 @@ __device__ __forceinline__ float2 unpack_bf16(uint32_t u) {
 // ---------------------------------------------------------------------------------------------
 bool make_tmap_2d_bf16(CUtensorMap* out, const void* base, uint64_t rows, uint64_t cols, uint64_t row_stride_elems,
                        uint32_t box_rows, uint32_t box_cols);
+// generic rank-N bf16 tensor map (dims/strides innermost first, strides in ELEMENTS for dims 1..rank-1)
+bool make_tmap_nd_bf16(CUtensorMap* out, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_elems,
+                       const uint32_t* box, int swizzle_bytes);
 // 3-D (batch, rows, cols) bf16 tensor, box (1, box_rows, box_cols); swizzle_bytes in {64, 128}
 bool make_tmap_3d_bf16(CUtensorMap* out, const void* base, uint64_t batch, uint64_t rows, uint64_t cols,
                        uint64_t row_stride_elems, uint64_t batch_stride_elems, uint32_t box_rows, uint32_t box_cols,

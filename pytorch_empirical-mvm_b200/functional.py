@@ -235,7 +235,7 @@ def attn_fwd(qkv, table, rowcode, colcode, region, dense_mask, B_, nW, N, nH, hd
     return out, lse
 
 
-def attn_bwd(qkv, out, dout, lse, table, rowcode, colcode, region, dense_mask, B_, nW, N, nH, hd, scale):
+def attn_bwd(qkv, out, dout, lse, table, rowcode, colcode, region, dense_mask, B_, nW, N, nH, hd, scale, planes=0):
     dqkv = torch.empty_like(qkv)
     Lt = table.shape[0]
     dtable = _empty((Lt, nH), torch.float32, qkv.device)
@@ -244,7 +244,8 @@ def attn_bwd(qkv, out, dout, lse, table, rowcode, colcode, region, dense_mask, B
     t0 = PROFILER.begin() if PROFILER is not None else None
     L.check(L.lib().vsw_window_attn_bwd(L.ptr(qkv), L.ptr(out), L.ptr(dout), L.ptr(lse), L.ptr(table), L.ptr(rowcode),
                                         L.ptr(colcode), L.ptr(region), L.ptr(dense_mask), L.ptr(dqkv), L.ptr(dtable),
-                                        B_, nW, N, nH, hd, Lt, float(scale), L.dt(qkv), L.ptr(ws), wsb, L.stream()),
+                                        B_, nW, N, nH, hd, Lt, float(scale), int(planes), L.dt(qkv), L.ptr(ws), wsb,
+                                        L.stream()),
             "vsw_window_attn_bwd")
     if t0 is not None:  # dV, dP, dQ, dK = 8*N*N*hd useful flops (the S/P recompute is not counted)
         PROFILER.end("window_attn_bwd", t0, 8.0 * B_ * nH * N * N * hd, 8 * B_ * N * nH * hd * _esz(qkv))
@@ -301,7 +302,8 @@ class _AttnBranch(torch.autograd.Function):
         dwp, dbp = linear_wgrad(a_buf, o, M, C, C)
         del a_buf
         region = plan.region if (plan.shifted and dense_mask is None) else None
-        dqkv, dtable = attn_bwd(qkv, o, dO, lse, table, rowcode, colcode, region, dense_mask, B * nW, nW, N, nH, hd, scale)
+        dqkv, dtable = attn_bwd(qkv, o, dO, lse, table, rowcode, colcode, region, dense_mask, B * nW, nW, N, nH, hd, scale,
+                                planes=plan.ws[0])
         del dO
         dxw = linear_dgrad(dqkv, wqkv, M, 3 * C, C)
         dwq, dbq = linear_wgrad(dqkv, xw.view(M, C), M, 3 * C, C, need_bias=ctx.has_qkv_bias)

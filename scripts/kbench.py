@@ -1,0 +1,100 @@
+#!/usr/bin/env python
+"""Micro-benchmarks of individual vsw kernels at the Swin-B (B=32) shapes; CUDA-event timing.
+usage: python scripts/kbench.py [attn|linear|ln|all] [--iters N]"""
+import argparse
+import importlib
+import json
+import os
+import sys
+
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+vsw = importlib.import_module("pytorch_empirical-mvm_b200")
+VF, L = vsw.functional, vsw._lib
+
+
+def timeit(fn, iters=10, warm=3):
+    for _ in range(warm):
+        fn()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(iters):
+        fn()
+    e1.record()
+    torch.cuda.synchronize()
+    return e0.elapsed_time(e1) / iters
+
+
+def attn_case(B, grid, nH, shifted, iters):
+    window = (8, 7, 7)
+    shift = (4, 3, 3) if shifted else (0, 0, 0)
+    plan = VF.window_plan(grid, window, shift, "cuda")
+    nW, N = plan.nW, plan.N
+    B_ = B * nW
+    C = nH * 32
+    qkv = torch.randn(B_ * N, 3 * C, device="cuda").bfloat16()
+    table = (torch.randn(2535, nH, device="cuda") * 0.1).bfloat16()
+    att = vsw.WindowAttention3D(C, window, nH).cuda()
+    rc, cc = att.bias_codes(N)
+    region = plan.region if plan.shifted else None
+    out, lse = VF.attn_fwd(qkv, table, rc, cc, region, None, B_, nW, N, nH, 32, 32 ** -0.5)
+    dout = torch.randn_like(out)
+    tf = timeit(lambda: VF.attn_fwd(qkv, table, rc, cc, region, None, B_, nW, N, nH, 32, 32 ** -0.5), iters)
+    tb = timeit(lambda: VF.attn_bwd(qkv, out, dout, lse, table, rc, cc, region, None, B_, nW, N, nH, 32, 32 ** -0.5, planes=8), iters)
+    fl = 4.0 * B_ * nH * N * N * 32
+    return dict(kernel="window_attn", B_=B_, N=N, nH=nH, shifted=shifted, fwd_ms=tf, bwd_ms=tb,
+                fwd_tflops=fl / tf / 1e9, bwd_tflops=2 * fl / tb / 1e9,
+                fwd_us_per_item=tf * 1e3 / (B_ * nH) * 148, bwd_us_per_item=tb * 1e3 / (B_ * nH) * 148)
+
+
+def linear_case(M, N, K, iters):
+    x = torch.randn(M, K, device="cuda").bfloat16()
+    w = (torch.randn(N, K, device="cuda") * 0.02).bfloat16()
+    b = torch.zeros(N, device="cuda").bfloat16()
+    dy = torch.randn(M, N, device="cuda").bfloat16()
+    u = torch.empty(M, N, device="cuda", dtype=torch.bfloat16)
+    t_f = timeit(lambda: VF.linear_fwd(x, w, b, M, N, K), iters)
+    t_g = timeit(lambda: VF.linear_fwd(x, w, b, M, N, K, epi=L.EPI_GELU, aux_out=u), iters)
+    t_d = timeit(lambda: VF.linear_dgrad(dy, w, M, N, K), iters)
+    t_w = timeit(lambda: VF.linear_wgrad(dy, x, M, N, K), iters)
+    t_ref = timeit(lambda: torch.matmul(x, w.t()), iters)
+    fl = 2.0 * M * N * K
+    by = 2.0 * (M * K + N * K + M * N)
+    return dict(kernel="linear", M=M, N=N, K=K, fwd_ms=t_f, gelu_ms=t_g, dgrad_ms=t_d, wgrad_ms=t_w, cublas_ms=t_ref,
+                fwd_tflops=fl / t_f / 1e9, gelu_tflops=fl / t_g / 1e9, dgrad_tflops=fl / t_d / 1e9,
+                wgrad_tflops=fl / t_w / 1e9, cublas_tflops=fl / t_ref / 1e9, fwd_gbs=by / t_f / 1e6,
+                t_flop_ms=fl / 1373.6e9, t_byte_ms=by / 6545.6e6)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("what", nargs="?", default="all")
+    ap.add_argument("--iters", type=int, default=10)
+    ap.add_argument("--batch", type=int, default=32)
+    a = ap.parse_args()
+    B = a.batch
+    res = []
+    if a.what in ("attn", "all"):
+        for grid, nH in (((8, 56, 56), 4), ((8, 28, 28), 8), ((8, 14, 14), 16), ((8, 7, 7), 32)):
+            for sh in (False, True):
+                if sh and grid == (8, 7, 7):
+                    continue
+                res.append(attn_case(B, grid, nH, sh, a.iters))
+                print(json.dumps(res[-1]), flush=True)
+    if a.what in ("linear", "all"):
+        T = [25088, 6272, 1568, 392]
+        for s, C in enumerate((128, 256, 512, 1024)):
+            M = B * T[s]
+            for (N, K) in ((3 * C, C), (C, C), (4 * C, C), (C, 4 * C)):
+                res.append(linear_case(M, N, K, a.iters))
+                print(json.dumps(res[-1]), flush=True)
+    os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
+    with open(os.path.join(ROOT, "gpurun_out", f"kbench_{a.what}.json"), "w") as f:
+        json.dump(res, f, indent=1)
+
+
+if __name__ == "__main__":
+    main()
