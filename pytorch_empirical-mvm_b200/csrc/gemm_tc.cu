@@ -12,6 +12,7 @@
 // Fused epilogues: bias | bias+GELU(+pre-activation) | bias+drop-path scale+row scatter+residual |
 //                  dgrad (* GELU') | fp32 partial.
 #include <cudaTypedefs.h>
+#include <stdlib.h>
 #include <mutex>
 #include "gemm_simt.cuh"
 #include "gemm_tc.cuh"
@@ -157,6 +158,8 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     uint64_t* tfull = empty + STAGES;
     uint64_t* tempty = tfull + 2;
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
+    constexpr uint32_t STG_BYTES = 32 * 80;   // per-epilogue-warp transposition buffer (32 rows x 64 B, padded to 80 B)
+    const uint32_t stage_base = tc::smem_u32(smem + STAGES * STAGE_BYTES + 256);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int tiles = p.n_tiles_m * p.n_tiles_n;
@@ -264,6 +267,10 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 drow = (long long)b * p.dst_rows_per_batch + d;
                 if (p.rowscale) rsc = __ldg(p.rowscale + b);
             }
+            // Per 32-column chunk: TMEM -> registers (thread = row) -> fused epilogue math -> bf16 -> per-warp smem
+            // transposition buffer -> global stores in which 4 consecutive lanes write one 64-byte row segment (full
+            // sectors), instead of 32 lanes writing 16 bytes to 32 different rows.
+            const uint32_t stg = stage_base + (uint32_t)(warp - 2) * STG_BYTES;
 #pragma unroll 1
             for (int c = half; c < BN / 32; c += 2) {
                 uint32_t r32[32];
@@ -271,46 +278,83 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 tc::tmem_ld_32x32(tmem_base + acc * BN + c * 32 + ((uint32_t)(q * 32) << 16), r32);
                 tc::tmem_ld_wait();
                 const int col0 = n0 + c * 32;
-                if (row_ok) {
+                if (p.epi == TE_PARTIAL) {
+                    if (row_ok) {
 #pragma unroll
-                    for (int g = 0; g < 4; ++g) {
-                        const int col = col0 + g * 8;
-                        if (col < p.N) {
-                            float v[8];
-#pragma unroll
-                            for (int e = 0; e < 8; ++e) v[e] = __uint_as_float(r32[g * 8 + e]);
-                            if (p.epi == TE_PARTIAL) {
+                        for (int g = 0; g < 4; ++g) {
+                            const int col = col0 + g * 8;
+                            if (col < p.N) {
                                 float* dst = p.partial + ((long long)split * p.M + row) * p.N + col;
-                                *reinterpret_cast<float4*>(dst) = make_float4(v[0], v[1], v[2], v[3]);
-                                *reinterpret_cast<float4*>(dst + 4) = make_float4(v[4], v[5], v[6], v[7]);
-                            } else {
-                                if (p.bias) {
-                                    float bb[8];
-                                    ld8(p.bias + col, bb);
-#pragma unroll
-                                    for (int e = 0; e < 8; ++e) v[e] += bb[e];
-                                }
-                                const long long o = drow * p.ldc + col;
-                                if (p.epi == TE_GELU) {
-                                    if (p.aux_out) st8(p.aux_out + o, v);
-#pragma unroll
-                                    for (int e = 0; e < 8; ++e) v[e] = gelu_fast(v[e]);
-                                } else if (p.epi == TE_RESIDUAL) {
-                                    float rr[8];
-                                    ld8(p.res + o, rr);
-#pragma unroll
-                                    for (int e = 0; e < 8; ++e) v[e] = fmaf(rsc, v[e], rr[e]);
-                                } else if (p.epi == TE_DGRAD) {
-                                    if (p.gelu_pre) {
-                                        float u[8];
-                                        ld8(p.gelu_pre + o, u);
-#pragma unroll
-                                        for (int e = 0; e < 8; ++e) v[e] *= gelu_grad_fast(u[e]);
-                                    }
-                                }
-                                st8(p.out + o, v);
+                                *reinterpret_cast<float4*>(dst) = make_float4(__uint_as_float(r32[g * 8]), __uint_as_float(r32[g * 8 + 1]),
+                                                                              __uint_as_float(r32[g * 8 + 2]), __uint_as_float(r32[g * 8 + 3]));
+                                *reinterpret_cast<float4*>(dst + 4) = make_float4(__uint_as_float(r32[g * 8 + 4]), __uint_as_float(r32[g * 8 + 5]),
+                                                                                  __uint_as_float(r32[g * 8 + 6]), __uint_as_float(r32[g * 8 + 7]));
                             }
                         }
+                    }
+                    continue;
+                }
+                // ---- epilogue math in the thread-per-row layout; results packed to bf16 (16 words per thread)
+                uint32_t packed[16], packed_aux[16];
+#pragma unroll
+                for (int g = 0; g < 4; ++g) {
+                    const int col = col0 + g * 8;
+                    float v[8];
+#pragma unroll
+                    for (int e = 0; e < 8; ++e) v[e] = __uint_as_float(r32[g * 8 + e]);
+                    if (col < p.N) {
+                        if (p.bias) {
+                            float bb[8];
+                            ld8(p.bias + col, bb);
+#pragma unroll
+                            for (int e = 0; e < 8; ++e) v[e] += bb[e];
+                        }
+                        if (p.epi == TE_GELU) {
+                            if (p.aux_out) {
+#pragma unroll
+                                for (int e = 0; e < 4; ++e) packed_aux[g * 4 + e] = tc::pack_bf16(v[2 * e], v[2 * e + 1]);
+                            }
+#pragma unroll
+                            for (int e = 0; e < 8; ++e) v[e] = gelu_fast(v[e]);
+                        } else if (p.epi == TE_RESIDUAL) {
+                            if (row_ok) {
+                                float rr[8];
+                                ld8(p.res + drow * p.ldc + col, rr);
+#pragma unroll
+                                for (int e = 0; e < 8; ++e) v[e] = fmaf(rsc, v[e], rr[e]);
+                            }
+                        } else if (p.epi == TE_DGRAD) {
+                            if (p.gelu_pre && row_ok) {
+                                float u[8];
+                                ld8(p.gelu_pre + drow * p.ldc + col, u);
+#pragma unroll
+                                for (int e = 0; e < 8; ++e) v[e] *= gelu_grad_fast(u[e]);
+                            }
+                        }
+                    }
+#pragma unroll
+                    for (int e = 0; e < 4; ++e) packed[g * 4 + e] = tc::pack_bf16(v[2 * e], v[2 * e + 1]);
+                }
+                // ---- transposed, coalesced stores (one or two outputs)
+                const int npass = (p.epi == TE_GELU && p.aux_out) ? 2 : 1;
+                for (int pass = 0; pass < npass; ++pass) {
+                    const uint32_t* src = (npass == 2 && pass == 0) ? packed_aux : packed;
+                    __nv_bfloat16* outp = (npass == 2 && pass == 0) ? p.aux_out : p.out;
+                    __syncwarp();
+#pragma unroll
+                    for (int g = 0; g < 4; ++g)   // row `lane`, 16-byte unit g; row stride 80 B keeps the 8-lane phases conflict-free
+                        tc::sts_u4(stg + lane * 80 + g * 16, make_uint4(src[g * 4], src[g * 4 + 1], src[g * 4 + 2], src[g * 4 + 3]));
+                    __syncwarp();
+                    const int unit = lane & 3;
+                    const int colu = col0 + unit * 8;
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) {
+                        const int rl = k * 8 + (lane >> 2);            // local row 0..31
+                        const uint4 val = tc::lds_u4(stg + rl * 80 + unit * 16);
+                        // destination row of local row rl: fetched from the owning lane's registers
+                        const long long dr = __shfl_sync(0xffffffffu, drow, rl);
+                        const int okr = __shfl_sync(0xffffffffu, (int)row_ok, rl);
+                        if (okr && colu < p.N) *reinterpret_cast<uint4*>(outp + dr * p.ldc + colu) = val;
                     }
                 }
             }
@@ -359,7 +403,7 @@ __global__ void __launch_bounds__(256) gather_rows_kernel(const __nv_bfloat16* _
 template <int BN, bool A_MN, bool B_MN>
 int launch_tc(const CUtensorMap& tmA, const CUtensorMap& tmB, const TcParams& p, cudaStream_t st) {
     constexpr int STAGES = BN <= 128 ? 5 : 4;
-    constexpr size_t SMEM = (size_t)STAGES * (A_BYTES + BN * BK * 2) + 1024 + 256;
+    constexpr size_t SMEM = (size_t)STAGES * (A_BYTES + BN * BK * 2) + 1024 + 256 + NUM_EPI_WARPS * 32 * 80;
     auto kern = tc_gemm_kernel<BN, A_MN, B_MN, STAGES>;
     static bool configured = false;  // benign race: the attribute is idempotent
     if (!configured) {
@@ -377,6 +421,15 @@ bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 
 
 }  // namespace
 
+// N-tile: 256 halves the A-operand re-reads from L2 (the main loop is L2-bandwidth bound at 128x128), as long as
+// the tile count still fills the GPU
+static int pick_bn(int M, int N) {
+    if (getenv("VSW_GEMM_BN128")) return 128;
+    if (N % 256 != 0) return 128;
+    const long long tiles256 = (long long)ceil_div(M, BM) * (N / 256);
+    return tiles256 >= kNumSMs ? 256 : 128;
+}
+
 // ---------------------------------------------------------------------------------------------
 // forward
 // ---------------------------------------------------------------------------------------------
@@ -388,7 +441,7 @@ int tc_linear(const TcLinearArgs& a, cudaStream_t st) {
         return VSW_ERR_UNSUPPORTED;
     }
     CUtensorMap tmA, tmB;
-    const int BN = 128;
+    const int BN = pick_bn(a.M, a.N);
     if (!make_tmap_2d_bf16(&tmA, a.x, a.M, a.K, a.K, BM, BK)) return VSW_ERR_CUDA;
     if (!make_tmap_2d_bf16(&tmB, a.w, a.N, a.K, a.K, BN, BK)) return VSW_ERR_CUDA;
     TcParams p{};
@@ -398,7 +451,7 @@ int tc_linear(const TcLinearArgs& a, cudaStream_t st) {
     p.bias = (const __nv_bfloat16*)a.bias; p.out = (__nv_bfloat16*)a.y; p.aux_out = (__nv_bfloat16*)a.aux_out;
     p.res = (const __nv_bfloat16*)a.res; p.rowmap = a.rowmap; p.rowscale = a.rowscale;
     p.rows_per_batch = a.rows_per_batch; p.dst_rows_per_batch = a.dst_rows_per_batch; p.ldc = a.N;
-    return launch_tc<128, false, false>(tmA, tmB, p, st);
+    return BN == 256 ? launch_tc<256, false, false>(tmA, tmB, p, st) : launch_tc<128, false, false>(tmA, tmB, p, st);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -426,16 +479,18 @@ int tc_dgrad(const TcDgradArgs& a, cudaStream_t st) {
     if (!make_tmap_2d_bf16(&tmB, a.w, a.N, a.K, a.K, 64, 64)) return VSW_ERR_CUDA;     // MN-major: rows = reduction
     TcParams p{};
     p.M = a.M; p.N = a.K; p.K = a.N;
-    p.n_tiles_m = ceil_div(a.M, BM); p.n_tiles_n = ceil_div(a.K, 128); p.splits = 1; p.k_per_split = ceil_div(a.N, BK) * BK;
+    const int BN = pick_bn(a.M, a.K);
+    p.n_tiles_m = ceil_div(a.M, BM); p.n_tiles_n = ceil_div(a.K, BN); p.splits = 1; p.k_per_split = ceil_div(a.N, BK) * BK;
     p.epi = TE_DGRAD; p.out = (__nv_bfloat16*)a.dx; p.gelu_pre = (const __nv_bfloat16*)a.gelu_pre; p.ldc = a.K;
-    return launch_tc<128, false, true>(tmA, tmB, p, st);
+    return BN == 256 ? launch_tc<256, false, true>(tmA, tmB, p, st) : launch_tc<128, false, true>(tmA, tmB, p, st);
 }
 
 // ---------------------------------------------------------------------------------------------
 // wgrad: dw (N x K) = dy (M x N)^T x (M x K)
 // ---------------------------------------------------------------------------------------------
+static int wgrad_bn(int K) { return (K % 256 == 0 && !getenv("VSW_GEMM_BN128")) ? 256 : 128; }
 static void tc_wgrad_split(int M, int N, int K, int* splits, int* m_per_split) {
-    const long long tiles = (long long)ceil_div(N, BM) * ceil_div(K, 128);
+    const long long tiles = (long long)ceil_div(N, BM) * ceil_div(K, wgrad_bn(K));
     long long s = (2LL * kNumSMs + tiles - 1) / tiles;      // ~2 work items per SM
     const long long smax = (M + 511) / 512;                 // each split reduces >= 512 rows
     if (s > smax) s = smax;
@@ -466,9 +521,10 @@ int tc_wgrad(const void* dy, const void* x, void* dw, int M, int N, int K, int g
     if (!make_tmap_2d_bf16(&tmB, x, M, K, K, 64, 64)) return VSW_ERR_CUDA;   // MN-major B
     TcParams p{};
     p.M = N; p.N = K; p.K = M;
-    p.n_tiles_m = ceil_div(N, BM); p.n_tiles_n = ceil_div(K, 128); p.splits = splits; p.k_per_split = mps;
+    const int BN = wgrad_bn(K);
+    p.n_tiles_m = ceil_div(N, BM); p.n_tiles_n = ceil_div(K, BN); p.splits = splits; p.k_per_split = mps;
     p.epi = TE_PARTIAL; p.partial = (float*)ws; p.ldc = K;
-    int rc = launch_tc<128, true, true>(tmA, tmB, p, st);
+    int rc = BN == 256 ? launch_tc<256, true, true>(tmA, tmB, p, st) : launch_tc<128, true, true>(tmA, tmB, p, st);
     if (rc) return rc;
     return launch_partial_reduce((const float*)ws, splits, (long long)N * K, dw, grad_dtype, st);
 }
