@@ -1,0 +1,58 @@
+"""Data-parallel plumbing for the Video-Swin hot path (clips shard by rank, full weight
+replica, ONE exchange step -- the gradient all-reduce).  Pure torch.distributed (NCCL on GPUs, gloo in the CPU
+tests); there is no data-path collective.  bench.py uses DistributedDataParallel (bucketed all-reduce overlapped
+with backward, as the reference does, agent.py:200-201); the helpers here are the explicit, testable form of the
+same contract."""
+from __future__ import annotations
+
+from typing import Iterable, List
+
+import torch
+import torch.distributed as dist
+
+
+def clip_shard(n_clips: int, rank: int, world: int) -> slice:
+    """contiguous, balanced shard of a global batch of clips (first n_clips % world ranks get one extra)"""
+    base, extra = divmod(n_clips, world)
+    start = rank * base + min(rank, extra)
+    return slice(start, start + base + (1 if rank < extra else 0))
+
+
+def _buckets(params: List[torch.Tensor], bucket_bytes: int) -> List[List[torch.Tensor]]:
+    out, cur, size = [], [], 0
+    for p in reversed(params):  # gradients become ready last-layer first
+        if p.grad is None:
+            continue
+        if cur and (size + p.grad.numel() * p.grad.element_size() > bucket_bytes or p.grad.dtype != cur[0].grad.dtype):
+            out.append(cur)
+            cur, size = [], 0
+        cur.append(p)
+        size += p.grad.numel() * p.grad.element_size()
+    if cur:
+        out.append(cur)
+    return out
+
+
+def all_reduce_gradients(params: Iterable[torch.Tensor], world_size: int | None = None,
+                         bucket_bytes: int = 50 << 20) -> int:
+    """average ``.grad`` of every parameter over the process group with bucketed flat all-reduces
+    (all buckets are launched asynchronously, then waited).  Returns the number of collectives issued."""
+    if not dist.is_initialized():
+        return 0
+    world = world_size or dist.get_world_size()
+    if world == 1:
+        return 0
+    params = list(params)
+    work = []
+    for bucket in _buckets(params, bucket_bytes):
+        flat = torch.cat([p.grad.reshape(-1) for p in bucket])
+        work.append((dist.all_reduce(flat, op=dist.ReduceOp.SUM, async_op=True), flat, bucket))
+    for handle, flat, bucket in work:
+        handle.wait()
+        flat.div_(world)
+        off = 0
+        for p in bucket:
+            n = p.grad.numel()
+            p.grad.copy_(flat[off:off + n].view_as(p.grad))
+            off += n
+    return len(work)

@@ -1,0 +1,78 @@
+"""CPU, world_size 2, gloo: the data-parallel contract of the hot path -- clips shard by rank, weights are
+replicated, and after the gradient all-reduce every rank holds the gradients of the single-process run on the
+concatenated batch (the loss is a mean over clips).  The compute here is the CPU oracle; the GPU product path
+obeys the same contract through DDP in bench.py."""
+import importlib
+import os
+import sys
+
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _worker(rank, world, port, tmpdir):
+    sys.path.insert(0, ROOT)
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from oracle import swin3d_oracle as O
+        dp = importlib.import_module("pytorch_empirical-mvm_b200.dp")
+        torch.manual_seed(0)  # identical weights on every rank
+        cfg = O.SwinCfg(embed_dim=32, depths=(2,), num_heads=(1,), window_size=(2, 7, 7))
+        sd = O.make_state_dict(cfg, seed=5, ln_jitter=0.1)
+        params = {k: torch.nn.Parameter(v.clone()) for k, v in sd.items() if v.is_floating_point()}
+        full = dict(sd)
+        full.update(params)
+        n_clips = 5  # deliberately not a multiple of the world size
+        g = torch.Generator().manual_seed(1)
+        x = torch.randn(n_clips, 3, 2, 28, 28, generator=g)
+        R = torch.randn(n_clips, 32, 2, 7, 7, generator=g)
+        sl = dp.clip_shard(n_clips, rank, world)
+        # per-rank loss = sum over local clips / n_clips * world, so that the AVERAGE over ranks is the global mean loss
+        y = O.swin_forward(full, x[sl], cfg)
+        loss = (y * R[sl]).sum() / n_clips * world
+        loss.backward()
+        ncoll = dp.all_reduce_gradients(params.values(), bucket_bytes=64 << 10)
+        assert ncoll >= 2  # several buckets at this bucket size
+        if rank == 0:
+            ref = {k: torch.nn.Parameter(v.clone()) for k, v in sd.items() if v.is_floating_point()}
+            fr = dict(sd)
+            fr.update(ref)
+            ((O.swin_forward(fr, x, cfg) * R).sum() / n_clips).backward()
+            worst = max(float((params[k].grad - ref[k].grad).norm() / (ref[k].grad.norm() + 1e-30)) for k in ref)
+            assert worst < 1e-5, worst
+        # every rank ends with identical gradients
+        flat = torch.cat([p.grad.reshape(-1) for p in params.values()])
+        other = [torch.empty_like(flat) for _ in range(world)]
+        dist.all_gather(other, flat)
+        assert torch.equal(other[0], other[1])
+        with open(os.path.join(tmpdir, f"ok{rank}"), "w") as f:
+            f.write("ok")
+    finally:
+        dist.destroy_process_group()
+
+
+def test_clip_shard_covers_batch():
+    dp = importlib.import_module("pytorch_empirical-mvm_b200.dp")
+    for n in (1, 5, 32, 33):
+        for world in (1, 2, 4, 8):
+            seen = []
+            for r in range(world):
+                s = dp.clip_shard(n, r, world)
+                seen += list(range(n))[s]
+            assert seen == list(range(n))
+
+
+@pytest.mark.timeout(180)
+def test_two_rank_gradient_allreduce_matches_single_process(tmp_path):
+    import socket
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        port = s.getsockname()[1]
+    mp.spawn(_worker, args=(2, port, str(tmp_path)), nprocs=2, join=True)
+    assert os.path.exists(tmp_path / "ok0") and os.path.exists(tmp_path / "ok1")
