@@ -163,8 +163,14 @@ def main():
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     dist = None
+    saved_stdout = None
     if world > 1:
         import torch.distributed as dist
+        # NCCL prints its version banner to stdout; the contract is ONE JSON line there, so park stdout on stderr
+        # until the line is printed
+        sys.stdout.flush()
+        saved_stdout = os.dup(1)
+        os.dup2(2, 1)
         dist.init_process_group("nccl", device_id=dev)
     L.set_gemm_backend({"auto": L.GEMM_AUTO, "simt": L.GEMM_SIMT, "tcgen05": L.GEMM_TCGEN05}[args.backend])
 
@@ -293,7 +299,10 @@ def main():
             "step_frac_of_bf16_sustained": step_tflops / world / pk["tf_sustained"],
             "roofline": roofline, "kernel_families": families, "cpu_baseline": cpu,
         }
-        print(json.dumps(out))
+        if saved_stdout is not None:
+            sys.stdout.flush()
+            os.dup2(saved_stdout, 1)
+        print(json.dumps(out), flush=True)
     if dist is not None:
         dist.barrier()
         dist.destroy_process_group()
