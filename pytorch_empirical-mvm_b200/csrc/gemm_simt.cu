@@ -154,13 +154,60 @@ int launch_partial_reduce(const float* partial, int splits, long long elems, voi
     return check_launch("partial_reduce");
 }
 
-// ---- column sum (bias gradient) ----
-constexpr int kColsumSplits = 128;
+// ---- column sum (bias gradient): HBM-bound, 16-byte loads, fixed-order two-pass reduction ----
+constexpr int kColsumSplits = 296;   // 2 row-splits per SM
 size_t colsum_ws_bytes(int N) { return (size_t)kColsumSplits * N * sizeof(float); }
 
+// blockDim (TX, TY): thread (tx, ty) owns the 16-byte column vector tx of the block's column tile and every
+// (TY * gridDim.y)-th row; partials are combined over ty through shared memory in a fixed order.
 template <typename T>
 __global__ void __launch_bounds__(256) colsum_kernel(const T* __restrict__ dy, int M, int N, float* __restrict__ part) {
-    // blockDim (32, 8): thread column n = blockIdx.x*32 + tx; rows strided
+    constexpr int VN = Vec16<T>::N;
+    extern __shared__ float sm[];   // [TY][TX][VN]
+    const int nvec = N / VN;
+    const int vi = blockIdx.x * blockDim.x + threadIdx.x;
+    float a[VN];
+#pragma unroll
+    for (int e = 0; e < VN; ++e) a[e] = 0.f;
+    if (vi < nvec) {
+        const long long stride = (long long)gridDim.y * blockDim.y;
+        long long m = (long long)blockIdx.y * blockDim.y + threadIdx.y;
+        // 4 independent loads in flight per thread
+        for (; m + 3 * stride < M; m += 4 * stride) {
+            float v0[VN], v1[VN], v2[VN], v3[VN];
+            load_vec<T>(dy + m * N + (long long)vi * VN, v0);
+            load_vec<T>(dy + (m + stride) * N + (long long)vi * VN, v1);
+            load_vec<T>(dy + (m + 2 * stride) * N + (long long)vi * VN, v2);
+            load_vec<T>(dy + (m + 3 * stride) * N + (long long)vi * VN, v3);
+#pragma unroll
+            for (int e = 0; e < VN; ++e) a[e] += (v0[e] + v1[e]) + (v2[e] + v3[e]);
+        }
+        for (; m < M; m += stride) {
+            float v0[VN];
+            load_vec<T>(dy + m * N + (long long)vi * VN, v0);
+#pragma unroll
+            for (int e = 0; e < VN; ++e) a[e] += v0[e];
+        }
+    }
+    float* mine = sm + ((size_t)threadIdx.y * blockDim.x + threadIdx.x) * VN;
+#pragma unroll
+    for (int e = 0; e < VN; ++e) mine[e] = a[e];
+    __syncthreads();
+    if (threadIdx.y == 0 && vi < nvec) {
+        for (int ty = 1; ty < blockDim.y; ++ty) {
+            const float* o = sm + ((size_t)ty * blockDim.x + threadIdx.x) * VN;
+#pragma unroll
+            for (int e = 0; e < VN; ++e) a[e] += o[e];
+        }
+        float* p = part + (size_t)blockIdx.y * N + (size_t)vi * VN;
+#pragma unroll
+        for (int e = 0; e < VN; ++e) p[e] = a[e];
+    }
+}
+
+// scalar fallback for N not a multiple of the vector width
+template <typename T>
+__global__ void __launch_bounds__(256) colsum_scalar_kernel(const T* __restrict__ dy, int M, int N, float* __restrict__ part) {
     __shared__ float sm[8][33];
     const int n = blockIdx.x * 32 + threadIdx.x;
     float s = 0.f;
@@ -178,12 +225,29 @@ __global__ void __launch_bounds__(256) colsum_kernel(const T* __restrict__ dy, i
 }
 
 int launch_colsum(const void* dy, int M, int N, void* db, int dtype, int out_dtype, void* ws, cudaStream_t st) {
-    int splits = ceil_div(M, 8 * 16);
-    if (splits > kColsumSplits) splits = kColsumSplits;
-    if (splits < 1) splits = 1;
-    dim3 grid(ceil_div(N, 32), splits), block(32, 8);
-    VSW_DISPATCH_DTYPE(dtype, T, (colsum_kernel<T><<<grid, block, 0, st>>>((const T*)dy, M, N, (float*)ws)));
-    int rc = check_launch("colsum");
+    const int vn = dtype == VSW_F32 ? 4 : 8;
+    int rc;
+    int splits;
+    if (N % vn == 0) {
+        const int nvec = N / vn;
+        const int TX = nvec >= 32 ? 32 : 16, TY = 256 / TX;
+        const int xtiles = ceil_div(nvec, TX);
+        splits = ceil_div(M, TY * 8);
+        const int want = (2 * kNumSMs + xtiles - 1) / xtiles;
+        if (splits > want) splits = want;
+        if (splits > kColsumSplits) splits = kColsumSplits;
+        if (splits < 1) splits = 1;
+        dim3 grid(xtiles, splits), block(TX, TY);
+        const size_t smem = (size_t)256 * vn * sizeof(float);
+        VSW_DISPATCH_DTYPE(dtype, T, (colsum_kernel<T><<<grid, block, smem, st>>>((const T*)dy, M, N, (float*)ws)));
+    } else {
+        splits = ceil_div(M, 8 * 16);
+        if (splits > kColsumSplits) splits = kColsumSplits;
+        if (splits < 1) splits = 1;
+        dim3 grid(ceil_div(N, 32), splits), block(32, 8);
+        VSW_DISPATCH_DTYPE(dtype, T, (colsum_scalar_kernel<T><<<grid, block, 0, st>>>((const T*)dy, M, N, (float*)ws)));
+    }
+    rc = check_launch("colsum");
     if (rc) return rc;
     return launch_partial_reduce((const float*)ws, splits, N, db, out_dtype, st);
 }

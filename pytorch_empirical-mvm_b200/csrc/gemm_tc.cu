@@ -100,10 +100,10 @@ namespace {
 
 constexpr int BM = 128, BK = 64;
 constexpr int A_BYTES = BM * BK * 2;  // 16 KB
-constexpr int NUM_EPI_WARPS = 8;
+constexpr int NUM_EPI_WARPS = 16;   // 4 per TMEM lane quadrant: the fused epilogues are latency/MUFU bound, not issue bound
 constexpr int NUM_THREADS = 64 + NUM_EPI_WARPS * 32;
 
-enum TcEpi { TE_BIAS = 0, TE_GELU = 1, TE_RESIDUAL = 2, TE_DGRAD = 3, TE_PARTIAL = 4 };
+enum TcEpi { TE_BIAS = 0, TE_GELU = 1, TE_RESIDUAL = 2, TE_DGRAD = 3, TE_PARTIAL = 4, TE_DGRAD_GELU = 5 };
 
 struct TcParams {
     int M, N, K;                 // output M x N, reduction length K
@@ -113,6 +113,7 @@ struct TcParams {
     const int32_t* rowmap; const float* rowscale; int rows_per_batch, dst_rows_per_batch;
     const __nv_bfloat16* gelu_pre; float* partial;
     long long ldc;
+    long long* dbg;   // optional phase counters (VSW_GEMM_DEBUG)
 };
 
 // erf via Abramowitz-Stegun 7.1.26 (|err| <= 1.5e-7): 1 rcp + 1 ex2 + 6 fma instead of erff's branchy polynomial
@@ -143,7 +144,9 @@ __device__ __forceinline__ void st8(__nv_bfloat16* p, const float (&v)[8]) {
     *reinterpret_cast<uint4*>(p) = u;
 }
 
-template <int BN, bool A_MN, bool B_MN, int STAGES>
+// EPI is a COMPILE-TIME parameter: with a run-time switch the compiler if-converts the branches and every tile pays
+// for the GELU / GELU' math (MUFU-bound) whatever the epilogue is.
+template <int BN, bool A_MN, bool B_MN, int STAGES, int EPI>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const TcParams p) {
     constexpr int B_BYTES = BN * BK * 2;
@@ -158,7 +161,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     uint64_t* tfull = empty + STAGES;
     uint64_t* tempty = tfull + 2;
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
-    constexpr uint32_t STG_BYTES = 32 * 80;   // per-epilogue-warp transposition buffer (32 rows x 64 B, padded to 80 B)
+    constexpr uint32_t STG_BYTES = 32 * 64;   // per-epilogue-warp transposition buffer (32 rows x 64 B, XOR-swizzled 16-B units)
     const uint32_t stage_base = tc::smem_u32(smem + STAGES * STAGE_BYTES + 256);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -219,13 +222,17 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 const int split = w / tiles;
                 const int kbeg = split * p.k_per_split;
                 const int kend = min(p.K, kbeg + p.k_per_split);
+                long long m_a = clock64();
                 tc::mbar_wait(&tempty[acc], acc_phase ^ 1);
                 tc::tc_fence_after();
+                long long m_b = clock64(), m_wait_full = 0;
                 const uint32_t d_tmem = tmem_base + acc * BN;
                 uint32_t accumulate = 0;
                 for (int k0 = kbeg; k0 < kend; k0 += BK) {
+                    long long f_a = clock64();
                     tc::mbar_wait(&full[stage], phase);
                     tc::tc_fence_after();
+                    m_wait_full += clock64() - f_a;
                     const uint32_t aaddr = tc::smem_u32(smem + stage * STAGE_BYTES);
                     const uint32_t baddr = aaddr + A_BYTES;
 #pragma unroll
@@ -241,25 +248,28 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                     if (++stage == STAGES) { stage = 0; phase ^= 1; }
                 }
                 tc::umma_commit(&tfull[acc]);        // accumulator complete -> epilogue
+                if (p.dbg && blockIdx.x == 0) { p.dbg[0] += m_b - m_a; p.dbg[1] += m_wait_full; p.dbg[2] += clock64() - m_b; p.dbg[3] += 1; }
                 if (++acc == 2) { acc = 0; acc_phase ^= 1; }
             }
         }
     } else {
         // ================= epilogue warps =================
         const int q = warp & 3;                 // TMEM lane quadrant this warp may access
-        const int half = (warp - 2) >> 2;       // which interleaved 32-column chunks it owns
+        const int half = (warp - 2) >> 2;       // which interleaved 32-column chunks it owns (0..NUM_EPI_WARPS/4-1)
         int acc = 0; uint32_t acc_phase = 0;
         for (int w = blockIdx.x; w < total; w += gridDim.x) {
             const int split = w / tiles, t = w - split * tiles;
             const int m0 = (t / p.n_tiles_n) * BM, n0 = (t % p.n_tiles_n) * BN;
+            long long e_a = clock64(), dbg_ld = 0, dbg_math = 0, dbg_st = 0;
             tc::mbar_wait(&tfull[acc], acc_phase);
             tc::tc_fence_after();
+            long long e_b = clock64();
             const int row = m0 + q * 32 + lane;
             const bool row_in = row < p.M;
             long long drow = row;
             float rsc = 1.f;
             bool row_ok = row_in;
-            if (p.epi == TE_RESIDUAL && row_in) {
+            if (EPI == TE_RESIDUAL && row_in) {
                 const int b = row / p.rows_per_batch;
                 const int r = row - b * p.rows_per_batch;
                 int d = r;
@@ -272,13 +282,15 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             // sectors), instead of 32 lanes writing 16 bytes to 32 different rows.
             const uint32_t stg = stage_base + (uint32_t)(warp - 2) * STG_BYTES;
 #pragma unroll 1
-            for (int c = half; c < BN / 32; c += 2) {
+            for (int c = half; c < BN / 32; c += NUM_EPI_WARPS / 4) {
                 uint32_t r32[32];
                 __syncwarp();
+                long long c_a = clock64();
                 tc::tmem_ld_32x32(tmem_base + acc * BN + c * 32 + ((uint32_t)(q * 32) << 16), r32);
                 tc::tmem_ld_wait();
+                long long c_b = clock64();
                 const int col0 = n0 + c * 32;
-                if (p.epi == TE_PARTIAL) {
+                if constexpr (EPI == TE_PARTIAL) {
                     if (row_ok) {
 #pragma unroll
                         for (int g = 0; g < 4; ++g) {
@@ -292,8 +304,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                             }
                         }
                     }
-                    continue;
-                }
+                } else {
                 // ---- epilogue math in the thread-per-row layout; results packed to bf16 (16 words per thread)
                 uint32_t packed[16], packed_aux[16];
 #pragma unroll
@@ -309,22 +320,22 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 #pragma unroll
                             for (int e = 0; e < 8; ++e) v[e] += bb[e];
                         }
-                        if (p.epi == TE_GELU) {
+                        if constexpr (EPI == TE_GELU) {
                             if (p.aux_out) {
 #pragma unroll
                                 for (int e = 0; e < 4; ++e) packed_aux[g * 4 + e] = tc::pack_bf16(v[2 * e], v[2 * e + 1]);
                             }
 #pragma unroll
                             for (int e = 0; e < 8; ++e) v[e] = gelu_fast(v[e]);
-                        } else if (p.epi == TE_RESIDUAL) {
+                        } else if constexpr (EPI == TE_RESIDUAL) {
                             if (row_ok) {
                                 float rr[8];
                                 ld8(p.res + drow * p.ldc + col, rr);
 #pragma unroll
                                 for (int e = 0; e < 8; ++e) v[e] = fmaf(rsc, v[e], rr[e]);
                             }
-                        } else if (p.epi == TE_DGRAD) {
-                            if (p.gelu_pre && row_ok) {
+                        } else if constexpr (EPI == TE_DGRAD_GELU) {
+                            if (row_ok) {
                                 float u[8];
                                 ld8(p.gelu_pre + drow * p.ldc + col, u);
 #pragma unroll
@@ -335,32 +346,36 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 #pragma unroll
                     for (int e = 0; e < 4; ++e) packed[g * 4 + e] = tc::pack_bf16(v[2 * e], v[2 * e + 1]);
                 }
+                long long c_c = clock64();
                 // ---- transposed, coalesced stores (one or two outputs)
-                const int npass = (p.epi == TE_GELU && p.aux_out) ? 2 : 1;
+                const int npass = (EPI == TE_GELU && p.aux_out) ? 2 : 1;
                 for (int pass = 0; pass < npass; ++pass) {
                     const uint32_t* src = (npass == 2 && pass == 0) ? packed_aux : packed;
                     __nv_bfloat16* outp = (npass == 2 && pass == 0) ? p.aux_out : p.out;
                     __syncwarp();
 #pragma unroll
-                    for (int g = 0; g < 4; ++g)   // row `lane`, 16-byte unit g; row stride 80 B keeps the 8-lane phases conflict-free
-                        tc::sts_u4(stg + lane * 80 + g * 16, make_uint4(src[g * 4], src[g * 4 + 1], src[g * 4 + 2], src[g * 4 + 3]));
+                    for (int g = 0; g < 4; ++g)   // row `lane`, 16-byte unit g XOR-swizzled by the row pair: conflict-free both ways
+                        tc::sts_u4(stg + lane * 64 + ((g ^ ((lane >> 1) & 3)) << 4), make_uint4(src[g * 4], src[g * 4 + 1], src[g * 4 + 2], src[g * 4 + 3]));
                     __syncwarp();
                     const int unit = lane & 3;
                     const int colu = col0 + unit * 8;
 #pragma unroll
                     for (int k = 0; k < 4; ++k) {
                         const int rl = k * 8 + (lane >> 2);            // local row 0..31
-                        const uint4 val = tc::lds_u4(stg + rl * 80 + unit * 16);
+                        const uint4 val = tc::lds_u4(stg + rl * 64 + ((unit ^ ((rl >> 1) & 3)) << 4));
                         // destination row of local row rl: fetched from the owning lane's registers
                         const long long dr = __shfl_sync(0xffffffffu, drow, rl);
                         const int okr = __shfl_sync(0xffffffffu, (int)row_ok, rl);
                         if (okr && colu < p.N) *reinterpret_cast<uint4*>(outp + dr * p.ldc + colu) = val;
                     }
                 }
+                if (p.dbg && blockIdx.x == 0 && threadIdx.x == 64) { dbg_ld += c_b - c_a; dbg_math += c_c - c_b; dbg_st += clock64() - c_c; }
+                }
             }
             tc::tc_fence_before();
             __syncwarp();
             if (lane == 0) tc::mbar_arrive(&tempty[acc]);
+            if (p.dbg && blockIdx.x == 0 && threadIdx.x == 64) { p.dbg[4] += e_b - e_a; p.dbg[5] += clock64() - e_b; p.dbg[6] += 1; p.dbg[8] += dbg_ld; p.dbg[9] += dbg_math; p.dbg[10] += dbg_st; }
             if (++acc == 2) { acc = 0; acc_phase ^= 1; }
         }
     }
@@ -400,11 +415,30 @@ __global__ void __launch_bounds__(256) gather_rows_kernel(const __nv_bfloat16* _
     }
 }
 
-template <int BN, bool A_MN, bool B_MN>
-int launch_tc(const CUtensorMap& tmA, const CUtensorMap& tmB, const TcParams& p, cudaStream_t st) {
+long long* gemm_dbg_buffer(int bn, bool amn, bool bmn, const TcParams& p) {
+    static long long* dbg = nullptr;
+    static bool init = false;
+    static char last[128] = {0};
+    if (!init) {
+        init = true;
+        if (getenv("VSW_GEMM_DEBUG")) { cudaMalloc(&dbg, 128); cudaMemset(dbg, 0, 128); }
+    }
+    if (!dbg) return nullptr;
+    long long h[16];
+    cudaMemcpy(h, dbg, 128, cudaMemcpyDeviceToHost);
+    if (h[3]) fprintf(stderr, "[vsw gemm %s] tiles/cta=%lld  MMA thread: wait_tmem_empty=%lld wait_tma=%lld issue+rest=%lld | epilogue warp: wait_acc=%lld work=%lld (cycles per tile)\n",
+                      last, h[3], h[0] / h[3], h[1] / h[3], (h[2] - h[1]) / h[3], h[4] / (h[6] + 1), h[5] / (h[6] + 1));
+    if (h[3]) fprintf(stderr, "      epilogue split per tile: tmem_ld=%lld math=%lld stores=%lld\n", h[8] / (h[6] + 1), h[9] / (h[6] + 1), h[10] / (h[6] + 1));
+    cudaMemset(dbg, 0, 128);
+    snprintf(last, sizeof(last), "BN=%d A_MN=%d B_MN=%d M=%d N=%d K=%d epi=%d", bn, (int)amn, (int)bmn, p.M, p.N, p.K, p.epi);
+    return dbg;
+}
+
+template <int BN, bool A_MN, bool B_MN, int EPI>
+int launch_tc_epi(const CUtensorMap& tmA, const CUtensorMap& tmB, const TcParams& p, cudaStream_t st) {
     constexpr int STAGES = BN <= 128 ? 5 : 4;
-    constexpr size_t SMEM = (size_t)STAGES * (A_BYTES + BN * BK * 2) + 1024 + 256 + NUM_EPI_WARPS * 32 * 80;
-    auto kern = tc_gemm_kernel<BN, A_MN, B_MN, STAGES>;
+    constexpr size_t SMEM = (size_t)STAGES * (A_BYTES + BN * BK * 2) + 1024 + 256 + NUM_EPI_WARPS * 32 * 64;
+    auto kern = tc_gemm_kernel<BN, A_MN, B_MN, STAGES, EPI>;
     static bool configured = false;  // benign race: the attribute is idempotent
     if (!configured) {
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM);
@@ -413,8 +447,26 @@ int launch_tc(const CUtensorMap& tmA, const CUtensorMap& tmB, const TcParams& p,
     }
     const int total = p.n_tiles_m * p.n_tiles_n * p.splits;
     const int grid = total < kNumSMs ? total : kNumSMs;
-    kern<<<grid, NUM_THREADS, SMEM, st>>>(tmA, tmB, p);
+    TcParams q = p;
+    q.dbg = gemm_dbg_buffer(BN, A_MN, B_MN, p);
+    kern<<<grid, NUM_THREADS, SMEM, st>>>(tmA, tmB, q);
     return check_launch("tc_gemm");
+}
+
+template <int BN, bool A_MN, bool B_MN>
+int launch_tc(const CUtensorMap& tmA, const CUtensorMap& tmB, const TcParams& p, cudaStream_t st) {
+    if constexpr (A_MN && B_MN) {
+        return launch_tc_epi<BN, true, true, TE_PARTIAL>(tmA, tmB, p, st);
+    } else if constexpr (B_MN) {
+        return p.gelu_pre ? launch_tc_epi<BN, false, true, TE_DGRAD_GELU>(tmA, tmB, p, st)
+                          : launch_tc_epi<BN, false, true, TE_DGRAD>(tmA, tmB, p, st);
+    } else {
+        switch (p.epi) {
+            case TE_GELU: return launch_tc_epi<BN, false, false, TE_GELU>(tmA, tmB, p, st);
+            case TE_RESIDUAL: return launch_tc_epi<BN, false, false, TE_RESIDUAL>(tmA, tmB, p, st);
+            default: return launch_tc_epi<BN, false, false, TE_BIAS>(tmA, tmB, p, st);
+        }
+    }
 }
 
 bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
@@ -490,12 +542,22 @@ int tc_dgrad(const TcDgradArgs& a, cudaStream_t st) {
 // ---------------------------------------------------------------------------------------------
 static int wgrad_bn(int K) { return (K % 256 == 0 && !getenv("VSW_GEMM_BN128")) ? 256 : 128; }
 static void tc_wgrad_split(int M, int N, int K, int* splits, int* m_per_split) {
+    // work items = output tiles x splits of the reduction over the M rows.  Pick the split count (each split >= 512
+    // rows, at most ~4 items per SM) that wastes the fewest SM-slots in the last wave of the persistent grid.
     const long long tiles = (long long)ceil_div(N, BM) * ceil_div(K, wgrad_bn(K));
-    long long s = (2LL * kNumSMs + tiles - 1) / tiles;      // ~2 work items per SM
-    const long long smax = (M + 511) / 512;                 // each split reduces >= 512 rows
-    if (s > smax) s = smax;
-    if (s < 1) s = 1;
-    int mps = (int)((M + s - 1) / s);
+    long long smax = (M + 511) / 512;
+    const long long cap = (4LL * kNumSMs + tiles - 1) / tiles;
+    if (smax > cap) smax = cap;
+    if (smax < 1) smax = 1;
+    long long best = 1; double best_eff = -1.0;
+    for (long long s = 1; s <= smax; ++s) {
+        const long long items = tiles * s;
+        const long long waves = (items + kNumSMs - 1) / kNumSMs;
+        // efficiency of the last wave, slightly favouring more (shorter) items for balance
+        const double eff = (double)items / (double)(waves * kNumSMs) + 1e-3 * (double)s / (double)smax;
+        if (eff > best_eff) { best_eff = eff; best = s; }
+    }
+    int mps = (int)((M + best - 1) / best);
     mps = (mps + BK - 1) / BK * BK;
     *m_per_split = mps;
     *splits = (M + mps - 1) / mps;

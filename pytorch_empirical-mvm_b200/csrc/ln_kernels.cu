@@ -112,12 +112,14 @@ __global__ void __launch_bounds__(256) ln_fwd_kernel(const T* __restrict__ x, co
 // ------------------------------------------------------------------------------------------
 // backward (row part): dx = dres + rstd * (g - mean(g) - xhat * mean(g*xhat)),  g = dy*gamma
 // ------------------------------------------------------------------------------------------
-template <typename T, typename TDY, int LANES, int VPL, int GROUPS>
+// FUSE: also accumulate the column reductions (dgamma = sum dy*xhat, dbeta = sum dy) in registers -- each lane owns
+// the same column vectors for every row it visits -- and emit one fixed-order partial per block (part[block][2][Cw]).
+template <typename T, typename TDY, int LANES, int VPL, int GROUPS, bool FUSE>
 __global__ void __launch_bounds__(256) ln_bwd_kernel(const TDY* __restrict__ dy, const T* __restrict__ x,
                                                      const T* __restrict__ gamma, const float* __restrict__ mean,
                                                      const float* __restrict__ rstd, const int32_t* __restrict__ map,
                                                      const T* __restrict__ dres, T* __restrict__ dx, int B, int Tin,
-                                                     int Tout, int C) {
+                                                     int Tout, int C, float* __restrict__ part) {
     constexpr int VN = Vec16<T>::N;
     constexpr int RPW = 32 / LANES;
     const int Cw = C * GROUPS;
@@ -128,6 +130,11 @@ __global__ void __launch_bounds__(256) ln_bwd_kernel(const TDY* __restrict__ dy,
     const long long warp_global = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     const long long warp_stride = (long long)gridDim.x * (blockDim.x >> 5);
     const float inv_c = 1.0f / (float)Cw;
+    float ag[FUSE ? VPL : 1][VN], ab[FUSE ? VPL : 1][VN];
+#pragma unroll
+    for (int k = 0; k < (FUSE ? VPL : 1); ++k)
+#pragma unroll
+        for (int e = 0; e < VN; ++e) { ag[k][e] = 0.f; ab[k][e] = 0.f; }
 
     for (long long row0 = warp_global * RPW; row0 < nrows; row0 += warp_stride * RPW) {
         const long long row = row0 + sub;
@@ -187,6 +194,10 @@ __global__ void __launch_bounds__(256) ln_bwd_kernel(const TDY* __restrict__ dy,
                     s1 += g[k][e];
                     s2 += g[k][e] * xh[k][e];
                 }
+                if (FUSE && !(GROUPS == 1 && src < 0)) {   // zeroed (padded) output rows carry no gradient
+#pragma unroll
+                    for (int e = 0; e < VN; ++e) { ag[k][e] = fmaf(d[e], xh[k][e], ag[k][e]); ab[k][e] += d[e]; }
+                }
             }
         }
         const float c1 = group_sum<LANES>(s1) * inv_c;
@@ -203,8 +214,35 @@ __global__ void __launch_bounds__(256) ln_bwd_kernel(const TDY* __restrict__ dy,
 #pragma unroll
                     for (int e = 0; e < VN; ++e) o[e] += rr[e];
                 }
-                store_vec<T>(dx + off[k], o);
+                if (dx) store_vec<T>(dx + off[k], o);
             }
+        }
+    }
+    if (FUSE) {
+        // combine the row sub-groups of a warp, then the 8 warps of the block (fixed order), one partial per block
+        __shared__ float red[8][32 * 4 * 8 + 8];
+        const int warp = threadIdx.x >> 5;
+#pragma unroll
+        for (int pass = 0; pass < 2; ++pass) {
+#pragma unroll
+            for (int k = 0; k < VPL; ++k) {
+                const int vi = l + k * LANES;
+#pragma unroll
+                for (int e = 0; e < VN; ++e) {
+                    float v = pass == 0 ? ag[k][e] : ab[k][e];
+#pragma unroll
+                    for (int o = LANES; o < 32; o <<= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+                    if (sub == 0 && vi < nvec) red[warp][vi * VN + e] = v;
+                }
+            }
+            __syncthreads();
+            for (int c = threadIdx.x; c < Cw; c += blockDim.x) {
+                float t = 0.f;
+#pragma unroll
+                for (int w8 = 0; w8 < 8; ++w8) t += red[w8][c];
+                part[((size_t)blockIdx.x * 2 + pass) * Cw + c] = t;
+            }
+            __syncthreads();
         }
     }
 }
@@ -281,20 +319,30 @@ __global__ void __launch_bounds__(256) ln_colsum_kernel(const TDY* __restrict__ 
     }
 }
 
+// blockDim (32, 8): 32 columns per block, the partial rows strided over ty, fixed-order combine through smem
 __global__ void colsum_finish_kernel(const float* __restrict__ part, int splits, int Cw, float* __restrict__ dgamma,
                                      float* __restrict__ dbeta) {
-    const int c = blockIdx.x * blockDim.x + threadIdx.x;
-    if (c >= Cw) return;
+    __shared__ float sm[2][8][33];
+    const int c = blockIdx.x * 32 + threadIdx.x;
     float s1 = 0.f, s2 = 0.f;
-    for (int s = 0; s < splits; ++s) {
-        s1 += part[(size_t)s * 2 * Cw + c];
-        s2 += part[(size_t)s * 2 * Cw + Cw + c];
+    if (c < Cw)
+        for (int s = threadIdx.y; s < splits; s += 8) {
+            s1 += part[(size_t)s * 2 * Cw + c];
+            s2 += part[(size_t)s * 2 * Cw + Cw + c];
+        }
+    sm[0][threadIdx.y][threadIdx.x] = s1;
+    sm[1][threadIdx.y][threadIdx.x] = s2;
+    __syncthreads();
+    if (threadIdx.y == 0 && c < Cw) {
+        float t1 = 0.f, t2 = 0.f;
+#pragma unroll
+        for (int y = 0; y < 8; ++y) { t1 += sm[0][y][threadIdx.x]; t2 += sm[1][y][threadIdx.x]; }
+        if (dgamma) dgamma[c] = t1;
+        if (dbeta) dbeta[c] = t2;
     }
-    if (dgamma) dgamma[c] = s1;
-    if (dbeta) dbeta[c] = s2;
 }
 
-constexpr int kColSplits = 256;
+constexpr int kColSplits = 1184;   // 8 blocks per SM: partial rows of the fused row kernel
 
 // ------------------------------------------------------------------------------------------
 // host-side dispatch
@@ -359,22 +407,37 @@ static int launch_ln_bwd(const void* dy, const void* x, const void* gamma, const
     const int Cw = C * GROUPS;
     VSW_REQUIRE((C % VN) == 0 && pick_row_cfg(Cw / VN, &cfg), VSW_ERR_UNSUPPORTED,
                 "layernorm bwd: C=%d must be a multiple of %d", C, VN);
-    if (dx) {
-        const int grid = row_grid((long long)B * Tout, cfg.lanes);
-        VSW_ROW_DISPATCH(cfg, (ln_bwd_kernel<T, TDY, LANES, VPL, GROUPS><<<grid, 256, 0, st>>>(
-                                  (const TDY*)dy, (const T*)x, (const T*)gamma, mean, rstd, map, (const T*)dres, (T*)dx,
-                                  B, Tin, Tout, C)));
-        int rc = check_launch("ln_bwd");
-        if (rc) return rc;
-    }
-    if (dgamma || dbeta) {
+    const bool want_cols = dgamma || dbeta;
+    if (want_cols)
         VSW_REQUIRE(ws && ws_bytes >= (size_t)kColSplits * 2 * Cw * sizeof(float), VSW_ERR_WORKSPACE,
                     "layernorm bwd: workspace %zu < %zu", ws_bytes, (size_t)kColSplits * 2 * Cw * sizeof(float));
+    // fused column reductions when the per-lane accumulators fit in registers (<= 4 vectors per lane)
+    const bool fuse = want_cols && cfg.vpl <= 4 && Cw <= 1024;
+    if (dx || fuse) {
+        int grid = row_grid((long long)B * Tout, cfg.lanes);
+        if (fuse && grid > kColSplits) grid = kColSplits;
+        if (fuse) {
+            VSW_ROW_DISPATCH(cfg, (ln_bwd_kernel<T, TDY, LANES, (VPL <= 4 ? VPL : 1), GROUPS, true><<<grid, 256, 0, st>>>(
+                                      (const TDY*)dy, (const T*)x, (const T*)gamma, mean, rstd, map, (const T*)dres, (T*)dx,
+                                      B, Tin, Tout, C, (float*)ws)));
+        } else {
+            VSW_ROW_DISPATCH(cfg, (ln_bwd_kernel<T, TDY, LANES, VPL, GROUPS, false><<<grid, 256, 0, st>>>(
+                                      (const TDY*)dy, (const T*)x, (const T*)gamma, mean, rstd, map, (const T*)dres, (T*)dx,
+                                      B, Tin, Tout, C, nullptr)));
+        }
+        int rc = check_launch("ln_bwd");
+        if (rc) return rc;
+        if (fuse) {
+            colsum_finish_kernel<<<ceil_div(Cw, 32), dim3(32, 8), 0, st>>>((const float*)ws, grid, Cw, dgamma, dbeta);
+            return check_launch("ln_colsum_finish");
+        }
+    }
+    if (want_cols) {
         const int nvec = Cw / VN;
         const int TX = nvec >= 32 ? 32 : 16, TY = 256 / TX;
         long long nrows = (long long)B * Tout;
         int splits = (int)((nrows + TY - 1) / TY);
-        if (splits > kColSplits) splits = kColSplits;
+        if (splits > 256) splits = 256;
         if (splits < 1) splits = 1;
         dim3 grid(ceil_div(nvec, TX), splits), block(TX, TY);
         const size_t smem = (size_t)256 * 2 * VN * sizeof(float);
@@ -382,7 +445,7 @@ static int launch_ln_bwd(const void* dy, const void* x, const void* gamma, const
                                                                      (float*)ws, B, Tin, Tout, C);
         int rc = check_launch("ln_colsum");
         if (rc) return rc;
-        colsum_finish_kernel<<<ceil_div(Cw, 256), 256, 0, st>>>((const float*)ws, splits, Cw, dgamma, dbeta);
+        colsum_finish_kernel<<<ceil_div(Cw, 32), dim3(32, 8), 0, st>>>((const float*)ws, splits, Cw, dgamma, dbeta);
         rc = check_launch("ln_colsum_finish");
         if (rc) return rc;
     }
