@@ -75,6 +75,61 @@ size_t bwd_smem_bytes(int Lpad) {
 // byte offset of the 16-byte unit holding keys [8u, 8u+8) of query row i inside a 128B-swizzled chunk
 __device__ __forceinline__ uint32_t sw128_off(int row, int unit) { return row * 128 + ((unit ^ (row & 7)) << 4); }
 
+// ---- backward softmax / dS over the full 16-column chunks [cbeg, cfull) of one query row ------------------------------
+// MASKED and the histogram batch size G are compile-time so that the unmasked, plane-batched common case carries no
+// predicated mask arithmetic and no alternative histogram code.
+struct BwdCols {
+    uint32_t trow, cc_a, reg_a, tabrow, histrow, pt_a, ds_a, regi4;
+    float scale_log2, nl2v, delta_i;
+    int row, cbeg, cfull;
+    bool valid;
+};
+template <bool MASKED, int G>
+__device__ __forceinline__ void bwd_cols(const BwdCols& a) {
+    for (int c = a.cbeg; c < a.cfull; c += 16) {
+        uint32_t rs[16], rd[16], nq4[4], cj[16];
+        tc::tmem_ld_32x16(a.trow + BW_S + c, rs);
+        tc::tmem_ld_32x16(a.trow + BW_DP + c, rd);
+        lds16i(a.cc_a + c * 4, cj);
+        if (MASKED) neq16(a.reg_a + c, a.regi4, nq4);
+        float tb[16], dsv[16];
+#pragma unroll
+        for (int e = 0; e < 16; ++e) tb[e] = tc::lds_f32(a.tabrow + cj[e]);
+        tc::tmem_ld_wait();
+        uint32_t pw[8], dw[8];
+#pragma unroll
+        for (int e = 0; e < 16; e += 2) {
+            float v0 = fmaf(__uint_as_float(rs[e]), a.scale_log2, tb[e]) + a.nl2v;
+            float v1 = fmaf(__uint_as_float(rs[e + 1]), a.scale_log2, tb[e + 1]) + a.nl2v;
+            if (MASKED) { v0 = mask_add(v0, nq4, e); v1 = mask_add(v1, nq4, e + 1); }
+            const float p0 = tc::ex2_approx(v0), p1 = tc::ex2_approx(v1);
+            dsv[e] = p0 * (__uint_as_float(rd[e]) - a.delta_i);
+            dsv[e + 1] = p1 * (__uint_as_float(rd[e + 1]) - a.delta_i);
+            pw[e / 2] = tc::pack_bf16(p0, p1);
+            dw[e / 2] = tc::pack_bf16(dsv[e], dsv[e + 1]);
+        }
+        if (a.valid) {
+            // d(bias table): at one column step the 32 rows of the warp hit 32 distinct entries, but (row i, col j) and
+            // (row i+1, col j+1) share one, so steps must stay ordered -- except for the G columns of one spatial position
+            // (consecutive in the permuted key order), which are a constant plane stride apart and never collide inside a
+            // warp (validated at kernel start): those are updated as one batch (loads first, then stores).
+#pragma unroll
+            for (int g = 0; g < 16; g += G) {
+                float hv[G];
+#pragma unroll
+                for (int e = 0; e < G; ++e) hv[e] = tc::lds_f32(a.histrow + cj[g + e]);
+#pragma unroll
+                for (int e = 0; e < G; ++e) tc::sts_f32(a.histrow + cj[g + e], hv[e] + dsv[g + e]);
+            }
+        }
+        const int u0 = (c - a.cbeg) / 8;
+        tc::sts_u4(a.pt_a + sw128_off(a.row, u0), make_uint4(pw[0], pw[1], pw[2], pw[3]));
+        tc::sts_u4(a.pt_a + sw128_off(a.row, u0 + 1), make_uint4(pw[4], pw[5], pw[6], pw[7]));
+        tc::sts_u4(a.ds_a + sw128_off(a.row, u0), make_uint4(dw[0], dw[1], dw[2], dw[3]));
+        tc::sts_u4(a.ds_a + sw128_off(a.row, u0 + 1), make_uint4(dw[4], dw[5], dw[6], dw[7]));
+    }
+}
+
 __global__ void __launch_bounds__(NTHREADS, 1)
 attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant__ CUtensorMap tmKV,
                    const __grid_constant__ CUtensorMap tmDO, const BwdParams p) {
@@ -302,62 +357,15 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_const
                         const float nl2v = valid ? nl2 : -INFINITY;          // invalid rows: P = dS = 0
                         const int k0 = kb * QT;
                         const int cfull = min(cend, nv & ~15);   // chunks without padded columns
-                        for (int c = cbeg; c < cfull; c += 16) {
-                            uint32_t rs[16], rd[16], nq4[4], cj[16];
-                            tc::tmem_ld_32x16(tmem + lane_base + BW_S + c, rs);
-                            tc::tmem_ld_32x16(tmem + lane_base + BW_DP + c, rd);
-                            lds16i(cc_a + (k0 + c) * 4, cj);
-                            if (masked) neq16(reg_a + k0 + c, regi4, nq4);
-                            float tb[16], dsv[16];
-#pragma unroll
-                            for (int e = 0; e < 16; ++e) tb[e] = tc::lds_f32(tabrow + cj[e]);
-                            tc::tmem_ld_wait();
-                            uint32_t pw[8], dw[8];
-#pragma unroll
-                            for (int e = 0; e < 16; e += 2) {
-                                float v0 = fmaf(__uint_as_float(rs[e]), p.scale_log2, tb[e]) + nl2v;
-                                float v1 = fmaf(__uint_as_float(rs[e + 1]), p.scale_log2, tb[e + 1]) + nl2v;
-                                if (masked) { v0 = mask_add(v0, nq4, e); v1 = mask_add(v1, nq4, e + 1); }
-                                const float p0 = tc::ex2_approx(v0), p1 = tc::ex2_approx(v1);
-                                dsv[e] = p0 * (__uint_as_float(rd[e]) - delta_i);
-                                dsv[e + 1] = p1 * (__uint_as_float(rd[e + 1]) - delta_i);
-                                pw[e / 2] = tc::pack_bf16(p0, p1);
-                                dw[e / 2] = tc::pack_bf16(dsv[e], dsv[e + 1]);
+                        {
+                            const BwdCols bc{tmem + lane_base, cc_a + k0 * 4, reg_a + k0, tabrow, histrow, pt_a, ds_a, regi4,
+                                             p.scale_log2, nl2v, delta_i, row, cbeg, cfull, valid};
+                            const int gmode = batched ? p.wd : 1;
+                            if (masked) {
+                                if (gmode == 8) bwd_cols<true, 8>(bc); else if (gmode == 4) bwd_cols<true, 4>(bc); else bwd_cols<true, 1>(bc);
+                            } else {
+                                if (gmode == 8) bwd_cols<false, 8>(bc); else if (gmode == 4) bwd_cols<false, 4>(bc); else bwd_cols<false, 1>(bc);
                             }
-                            if (valid) {
-                                // d(bias table): at one column step the 32 rows of the warp hit 32 distinct entries, but
-                                // (row i, col j) and (row i+1, col j+1) share one, so steps must stay ordered -- except for
-                                // the wd columns of one spatial position (consecutive in the permuted key order), which are
-                                // a constant plane stride apart and never collide inside a warp (validated at kernel start).
-                                if (batched && p.wd == 8) {
-#pragma unroll
-                                    for (int g = 0; g < 16; g += 8) {
-                                        float hv[8];
-#pragma unroll
-                                        for (int e = 0; e < 8; ++e) hv[e] = tc::lds_f32(histrow + cj[g + e]);
-#pragma unroll
-                                        for (int e = 0; e < 8; ++e) tc::sts_f32(histrow + cj[g + e], hv[e] + dsv[g + e]);
-                                    }
-                                } else if (batched && p.wd == 4) {
-#pragma unroll
-                                    for (int g = 0; g < 16; g += 4) {
-                                        float hv[4];
-#pragma unroll
-                                        for (int e = 0; e < 4; ++e) hv[e] = tc::lds_f32(histrow + cj[g + e]);
-#pragma unroll
-                                        for (int e = 0; e < 4; ++e) tc::sts_f32(histrow + cj[g + e], hv[e] + dsv[g + e]);
-                                    }
-                                } else {
-#pragma unroll
-                                    for (int e = 0; e < 16; ++e)
-                                        tc::sts_f32(histrow + cj[e], tc::lds_f32(histrow + cj[e]) + dsv[e]);
-                                }
-                            }
-                            const int u0 = (c - cbeg) / 8;
-                            tc::sts_u4(pt_a + sw128_off(row, u0), make_uint4(pw[0], pw[1], pw[2], pw[3]));
-                            tc::sts_u4(pt_a + sw128_off(row, u0 + 1), make_uint4(pw[4], pw[5], pw[6], pw[7]));
-                            tc::sts_u4(ds_a + sw128_off(row, u0), make_uint4(dw[0], dw[1], dw[2], dw[3]));
-                            tc::sts_u4(ds_a + sw128_off(row, u0 + 1), make_uint4(dw[4], dw[5], dw[6], dw[7]));
                         }
                         for (int c = max(cbeg, cfull); c < cend; c += 16) {   // chunk with columns >= N
                             uint32_t rs[16], rd[16];
