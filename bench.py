@@ -270,8 +270,14 @@ def main():
         tensor_bound = v["flops"] > 0
         ach = (v["flops"] / (v["ms"] * 1e-3) / 1e12) if tensor_bound else (v["bytes"] / (v["ms"] * 1e-3) / 1e9)
         peak = pk["tf_sustained"] if tensor_bound else pk["hbm"]
+        traffic = None   # dram bytes per launch of that kernel family from the committed ncu --set full capture
+        tpath = os.path.join(ROOT, "profiles", "ncu_traffic.json")
+        if os.path.exists(tpath) and args.model == "swin_b" and B == 32:
+            with open(tpath) as f:
+                traffic = json.load(f).get(top, {}).get("avg_dram_bytes_per_launch")
         roofline = {"kernel": top, "bound": "tensor" if tensor_bound else "hbm", "achieved": ach, "peak": peak,
-                    "unit": "TFLOP/s" if tensor_bound else "GB/s", "frac": ach / peak, "traffic": None,
+                    "unit": "TFLOP/s" if tensor_bound else "GB/s", "frac": ach / peak, "traffic": traffic,
+                    "algorithmic_bytes_per_launch": v["bytes"] / max(1, v["launches"]),
                     "peak_source": pk["source"] + (" (sustained bf16)" if tensor_bound else ""),
                     "launches_per_step": v["launches"] // psteps,
                     "avg_launch_ms": v["ms"] / max(1, v["launches"])}
