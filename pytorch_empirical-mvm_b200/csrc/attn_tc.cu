@@ -22,12 +22,13 @@ namespace {
 constexpr int HD = 32;
 constexpr int QT = 128;                       // query rows per tile
 constexpr int MAXROWS = 512;                  // smem rows per operand
+constexpr int AUXROWS = 448;                  // per-token side arrays (N <= 448)
 constexpr int OPER_BYTES = MAXROWS * HD * 2;  // 32 KB
 constexpr int STAGE_BYTES = 3 * OPER_BYTES;   // Q, K, V
 constexpr int BOX_BYTES = QT * HD * 2;        // 8 KB per TMA box
 constexpr int NTHREADS = 384;                 // backward: warp 0 TMA, 1 MMA, 2 aux, 3 idle, 4..11 softmax
 constexpr int NPARTS = 3;                     // forward: column parts per row (3 softmax warps per TMEM lane quadrant)
-constexpr int NSUB = 2;                       // forward: P.V hand-off granularity (sub-batches per part)
+constexpr int NHALF = 2;                      // forward: the key range is processed as two independently pipelined halves
 constexpr int FWD_THREADS = 128 + NPARTS * 128;  // warp 0 TMA, 1 MMA, 2 aux, 3 idle, 4.. softmax
 constexpr int S_COL = 0, O_COL = 480, TMEM_COLS = 512;
 constexpr float LOG2E = 1.4426950408889634f, LN2 = 0.6931471805599453f;
@@ -38,6 +39,7 @@ struct FwdParams {
     int B_, nW, N, nH, L, Lpad;
     float scale_log2;
     int Npad, nq;
+    int h0;           // keys [0, h0) form half 0, [h0, Npad) half 1 (both multiples of 16)
     long long* dbg;   // optional per-phase cycle counters (profiling builds only)
 };
 
@@ -46,9 +48,10 @@ struct Smem {
     float* tab[2];
     uint8_t* reg[2];
     int* rc; int* cc;
-    float* xmax; float* xsum;   // [2][128]
+    float* xmax; float* xsum;   // xmax [4][128]; xsum [2 tile parities][4][128]
     float* maxbias; int* masked;  // [2]
     float* k2max;                 // [2] max_j |k_j|^2 of the staged item
+    float* q2[2];                 // [2][512] |q_i|^2 of the staged item
     uint64_t* qkv_full; uint64_t* qkv_empty; uint64_t* aux_full; uint64_t* aux_empty;  // [2] each
     uint64_t* s_full; uint64_t* p_full; uint64_t* o_full;
     uint32_t* tmem_slot;
@@ -60,10 +63,10 @@ __device__ __forceinline__ Smem carve(uint8_t* base, int Lpad) {
     uint8_t* p = base + 2 * STAGE_BYTES;
     s.tab[0] = (float*)p; p += (size_t)Lpad * 4;
     s.tab[1] = (float*)p; p += (size_t)Lpad * 4;
-    s.rc = (int*)p; p += MAXROWS * 4;
-    s.cc = (int*)p; p += MAXROWS * 4;
+    s.rc = (int*)p; p += AUXROWS * 4;
+    s.cc = (int*)p; p += AUXROWS * 4;
     s.xmax = (float*)p; p += 4 * QT * 4;
-    s.xsum = (float*)p; p += 4 * QT * 4;
+    s.xsum = (float*)p; p += 8 * QT * 4;
     s.maxbias = (float*)p; p += 8;
     s.masked = (int*)p; p += 8;
     s.k2max = (float*)p; p += 16;
@@ -71,17 +74,19 @@ __device__ __forceinline__ Smem carve(uint8_t* base, int Lpad) {
     s.qkv_empty = (uint64_t*)p; p += 16;
     s.aux_full = (uint64_t*)p; p += 16;
     s.aux_empty = (uint64_t*)p; p += 16;
-    s.s_full = (uint64_t*)p; p += 8;
-    s.p_full = (uint64_t*)p; p += 32;   // [4]: one per quarter of the key range
+    s.s_full = (uint64_t*)p; p += 16;   // [2]: one per key half
+    s.p_full = (uint64_t*)p; p += 16;   // [2]
     s.o_full = (uint64_t*)p; p += 8;
-    s.tmem_slot = (uint32_t*)p; p += 16;   // (+8 pad: keeps the region-id arrays 16-byte aligned)
-    s.reg[0] = p; p += MAXROWS;
-    s.reg[1] = p; p += MAXROWS;
+    s.tmem_slot = (uint32_t*)p; p += 8;
+    s.reg[0] = p; p += AUXROWS;
+    s.reg[1] = p; p += AUXROWS;
+    s.q2[0] = (float*)p; p += AUXROWS * 4;
+    s.q2[1] = (float*)p; p += AUXROWS * 4;
     return s;
 }
 size_t fwd_smem_bytes(int Lpad) {
-    return 1024 + 2 * (size_t)STAGE_BYTES + 2 * (size_t)Lpad * 4 + 2 * MAXROWS * 4 + 8 * QT * 4 + 32 + 4 * 16 + 3 * 8 + 8 + 24 + 8 +
-           2 * MAXROWS + 64;
+    return 1024 + 2 * (size_t)STAGE_BYTES + 2 * (size_t)Lpad * 4 + 2 * AUXROWS * 4 + 12 * QT * 4 + 32 + 4 * 16 + 16 + 16 + 8 + 8 +
+           2 * AUXROWS + 2 * AUXROWS * 4 + 16;
 }
 
 
@@ -121,13 +126,10 @@ __device__ __forceinline__ float row_norm2(const __nv_bfloat16* rowp) {
     return acc;
 }
 
-// The Npad key columns of a row are cut into NPARTS parts (one softmax warp each), each part into NSUB
-// sub-batches (the granularity at which P is handed to the P.V MMAs); all boundaries are multiples of 16.
-__device__ __forceinline__ int part_bound(int Npad, int part) { return ((((Npad >> 4) * part) / NPARTS) << 4); }
-__device__ __forceinline__ int sub_bound(int Npad, int part, int sub) {
-    const int beg = part_bound(Npad, part), nck = (part_bound(Npad, part + 1) - beg) >> 4;
-    return beg + (((nck * sub) / NSUB) << 4);
-}
+// The Npad key columns of a row are cut into two halves (S of one half is recomputed by the tensor core for the
+// next query tile while the softmax warps work on the other), each half into NPARTS parts (one softmax warp per
+// TMEM lane quadrant each); all boundaries are multiples of 16.  part_off = offset of part `part` inside a half.
+__device__ __forceinline__ int part_off(int len, int part) { return ((((len >> 4) * part) / NPARTS) << 4); }
 
 // ---- forward softmax over the full chunks [cbeg, cfull) of one row, software-pipelined TMEM loads --------
 // pass 1: row max (raw accumulator when !MASKED: the caller scales afterwards; scaled + mask when MASKED)
@@ -221,12 +223,12 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const FwdParams p)
             tc::mbar_init(&s.qkv_full[i], 1); tc::mbar_init(&s.qkv_empty[i], 1);
             tc::mbar_init(&s.aux_full[i], 1); tc::mbar_init(&s.aux_empty[i], 4 * NPARTS);
         }
-        tc::mbar_init(s.s_full, 1); tc::mbar_init(s.o_full, 1);
-        for (int i = 0; i < NSUB; ++i) tc::mbar_init(&s.p_full[i], 4 * NPARTS);
+        tc::mbar_init(s.o_full, 1);
+        for (int i = 0; i < NHALF; ++i) { tc::mbar_init(&s.s_full[i], 1); tc::mbar_init(&s.p_full[i], 4 * NPARTS); }
         tc::fence_barrier_init();
     }
     if (warp == 1) tc::tmem_alloc(s.tmem_slot, TMEM_COLS);
-    for (int n = threadIdx.x; n < MAXROWS; n += FWD_THREADS) {   // cc holds BYTE offsets into the fp32 table copy
+    for (int n = threadIdx.x; n < AUXROWS; n += FWD_THREADS) {   // cc holds BYTE offsets into the fp32 table copy
         s.rc[n] = n < p.N ? p.rowcode[n] : 0;
         s.cc[n] = n < p.N ? p.colcode[n] * 4 : 0;
     }
@@ -252,51 +254,49 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const FwdParams p)
         }
     } else if (warp == 1) {
         // ===================== MMA issuer =====================
+        // Per query tile the key range is handled as two halves with their own S accumulators, so the tensor
+        // core recomputes S of one half for the next tile while the softmax warps are busy with the other:
+        //   [P half 0 ready] O  = P0 V0 ; S0 = Q(t+1) K0^T      [P half 1 ready] O += P1 V1 ; S1 = Q(t+1) K1^T
         if (lane == 0) {
             int it = 0; uint32_t pph = 0;
             const uint32_t idesc_pv = tc::idesc_bf16(QT, HD, 0, 1);
-            const int n0len = p.Npad < 256 ? p.Npad : 256, n1len = p.Npad - n0len;
+            const int hbeg[NHALF] = {0, p.h0}, hlen[NHALF] = {p.h0, p.Npad - p.h0};
             for (int w = blockIdx.x; w < items; w += gridDim.x, ++it) {
                 const int st = it & 1; const uint32_t ph = (it >> 1) & 1;
                 tc::mbar_wait(&s.qkv_full[st], ph);
                 tc::tc_fence_after();
                 const uint32_t qa = tc::smem_u32(s.stage[st]), ka = qa + OPER_BYTES, va = ka + OPER_BYTES;
-                auto issue_qk = [&](int t) {
-#pragma unroll
-                    for (int k = 0; k < 2; ++k)
-                        tc::umma_bf16(tmem + S_COL, tc::smem_desc_sw64(qa + t * BOX_BYTES + k * 32, 0, 512),
-                                      tc::smem_desc_sw64(ka + k * 32, 0, 512), tc::idesc_bf16(QT, n0len, 0, 0), k);
-                    if (n1len > 0) {
+                const uint32_t vdesc0_hi = (uint32_t)(tc::smem_desc_sw64(va, 0, 512) >> 32);
+                auto issue_qk = [&](int t, int hh) {
+                    if (hlen[hh] > 0) {
 #pragma unroll
                         for (int k = 0; k < 2; ++k)
-                            tc::umma_bf16(tmem + S_COL + 256, tc::smem_desc_sw64(qa + t * BOX_BYTES + k * 32, 0, 512),
-                                          tc::smem_desc_sw64(ka + 256 * 64 + k * 32, 0, 512),
-                                          tc::idesc_bf16(QT, n1len, 0, 0), k);
+                            tc::umma_bf16(tmem + S_COL + hbeg[hh], tc::smem_desc_sw64(qa + t * BOX_BYTES + k * 32, 0, 512),
+                                          tc::smem_desc_sw64(ka + hbeg[hh] * 64 + k * 32, 0, 512),
+                                          tc::idesc_bf16(QT, hlen[hh], 0, 0), k);
                     }
-                    tc::umma_commit(s.s_full);
+                    tc::umma_commit(&s.s_full[hh]);
                 };
-                issue_qk(0);
+                issue_qk(0, 0);
+                issue_qk(0, 1);
                 for (int t = 0; t < p.nq; ++t) {
-                    // P.V is issued quarter by quarter while the softmax warps are still producing the rest of P
                     uint32_t acc_pv = 0;
-                    const uint32_t vdesc0_hi = (uint32_t)(tc::smem_desc_sw64(va, 0, 512) >> 32);
-                    for (int qq = 0; qq < NSUB; ++qq) {
-                        tc::mbar_wait(&s.p_full[qq], pph);
+                    for (int hh = 0; hh < NHALF; ++hh) {
+                        tc::mbar_wait(&s.p_full[hh], pph);
                         tc::tc_fence_after();
 #pragma unroll
                         for (int part = 0; part < NPARTS; ++part) {
-                            const int k00 = part_bound(p.Npad, part);
-                            const int kb0 = sub_bound(p.Npad, part, qq), kb1 = sub_bound(p.Npad, part, qq + 1);
-                            for (int key0 = kb0; key0 < kb1; key0 += 16) {
+                            const int k00 = hbeg[hh] + part_off(hlen[hh], part), k01 = hbeg[hh] + part_off(hlen[hh], part + 1);
+                            for (int key0 = k00; key0 < k01; key0 += 16) {
                                 const uint64_t vd = ((uint64_t)vdesc0_hi << 32) | (((va + key0 * 64) & 0x3FFFFu) >> 4);
                                 tc::umma_bf16_ts(tmem + O_COL, tmem + S_COL + k00 + (key0 - k00) / 2, vd, idesc_pv, acc_pv);
                                 acc_pv = 1;
                             }
                         }
+                        if (hh == NHALF - 1) tc::umma_commit(s.o_full);
+                        if (t + 1 < p.nq) issue_qk(t + 1, hh);
                     }
                     pph ^= 1;
-                    tc::umma_commit(s.o_full);
-                    if (t + 1 < p.nq) issue_qk(t + 1);
                 }
                 tc::umma_commit(&s.qkv_empty[st]);
             }
@@ -327,8 +327,11 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const FwdParams p)
             }
             diff = __any_sync(0xffffffffu, diff);
             float k2 = 0.f;   // max_j |k_j|^2: with |q_i| it bounds the scores of row i (Cauchy-Schwarz)
-            for (int n = lane; n < p.N; n += 32)
-                k2 = fmaxf(k2, row_norm2(p.qkv + (((long long)b_ * p.N + n) * 3 + 1) * C + h * HD));
+            for (int n = lane; n < p.N; n += 32) {
+                const __nv_bfloat16* rowp = p.qkv + (((long long)b_ * p.N + n) * 3) * C + h * HD;
+                k2 = fmaxf(k2, row_norm2(rowp + C));
+                s.q2[st][n] = row_norm2(rowp);
+            }
             k2 = warp_max(k2);
             if (lane == 0) { s.maxbias[st] = mb; s.masked[st] = diff; s.k2max[st] = k2; }
             __syncwarp();
@@ -336,11 +339,20 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const FwdParams p)
         }
     } else if (warp >= 4) {
         // ===================== softmax + epilogue warps =====================
-        const int q = warp & 3, half = (warp - 4) >> 2;   // `half` = column part of this warp (0..NPARTS-1)
+        const int q = warp & 3, part = (warp - 4) >> 2;   // TMEM lane quadrant, column part of this warp (0..NPARTS-1)
         const int row = q * 32 + lane;
         const uint32_t lane_base = (uint32_t)(q * 32) << 16;
-        const int cbeg = part_bound(p.Npad, half), cend = part_bound(p.Npad, half + 1);
-        const int pbase = cbeg;   // P (packed bf16) column base, aliases the part's own S columns
+        const uint32_t srow = tmem + lane_base + S_COL;
+        int cb[NHALF], ce[NHALF];                         // this warp's key columns inside each half
+        {
+            const int hbeg[NHALF] = {0, p.h0}, hlen[NHALF] = {p.h0, p.Npad - p.h0};
+#pragma unroll
+            for (int hh = 0; hh < NHALF; ++hh) {
+                cb[hh] = hbeg[hh] + part_off(hlen[hh], part);
+                ce[hh] = hbeg[hh] + part_off(hlen[hh], part + 1);
+            }
+        }
+        const int nfull = p.N & ~15;                      // chunks below nfull have no padded columns
         int it = 0; uint32_t sph = 0, oph = 0;
         for (int w = blockIdx.x; w < items; w += gridDim.x, ++it) {
             const int st = it & 1; const uint32_t ph = (it >> 1) & 1;
@@ -352,69 +364,116 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const FwdParams p)
             const float* tab = s.tab[st];
             const uint8_t* reg = s.reg[st];
             const uint32_t reg_a = tc::smem_u32(reg), cc_a = tc::smem_u32(s.cc);
+
+            // ---- epilogue of tile te: O / l -> bf16 -> global; lse.  Runs one tile late (after the first half of
+            //      the next tile's softmax) so the wait for the P.V MMAs is hidden; the next tile's P.V cannot
+            //      start before every warp has passed this point (it needs their p_full[0] arrival).
+            auto epilogue = [&](int te, float mxe) {
+                const int ie = te * QT + row;
+                long long t_d = clock64();
+                tc::mbar_wait(s.o_full, oph); oph ^= 1;
+                tc::tc_fence_after();
+                long long t_e = clock64();
+                const float* xs = s.xsum + (te & 1) * 4 * QT;
+                float l = 0.f;
+#pragma unroll
+                for (int k = 0; k < NPARTS; ++k) l += xs[k * QT + row];
+                const float inv = __fdividef(1.0f, l);
+                uint32_t o[16];
+                tc::tmem_ld_32x16(tmem + lane_base + O_COL + (part & 1) * 16, o);
+                tc::tmem_ld_wait();
+                if (ie < p.N && part < 2) {
+                    __nv_bfloat16* dst = p.out + ((long long)b_ * p.N + ie) * C + h * HD + part * 16;
+                    uint4 u0, u1;
+                    u0.x = tc::pack_bf16(__uint_as_float(o[0]) * inv, __uint_as_float(o[1]) * inv);
+                    u0.y = tc::pack_bf16(__uint_as_float(o[2]) * inv, __uint_as_float(o[3]) * inv);
+                    u0.z = tc::pack_bf16(__uint_as_float(o[4]) * inv, __uint_as_float(o[5]) * inv);
+                    u0.w = tc::pack_bf16(__uint_as_float(o[6]) * inv, __uint_as_float(o[7]) * inv);
+                    u1.x = tc::pack_bf16(__uint_as_float(o[8]) * inv, __uint_as_float(o[9]) * inv);
+                    u1.y = tc::pack_bf16(__uint_as_float(o[10]) * inv, __uint_as_float(o[11]) * inv);
+                    u1.z = tc::pack_bf16(__uint_as_float(o[12]) * inv, __uint_as_float(o[13]) * inv);
+                    u1.w = tc::pack_bf16(__uint_as_float(o[14]) * inv, __uint_as_float(o[15]) * inv);
+                    reinterpret_cast<uint4*>(dst)[0] = u0;
+                    reinterpret_cast<uint4*>(dst)[1] = u1;
+                    if (part == 0) p.lse[((long long)b_ * p.nH + h) * p.N + ie] = (mxe + __log2f(l)) * LN2;
+                }
+                tc::tc_fence_before();  // O reads complete before the next p_full arrive lets P.V overwrite O
+                if (p.dbg && blockIdx.x == 0 && threadIdx.x == 128) {
+                    long long t_f = clock64();
+                    p.dbg[3] += t_e - t_d; p.dbg[4] += t_f - t_e;
+                }
+            };
+
+            float mx_prev = 0.f;
             for (int t = 0; t < p.nq; ++t) {
                 const int i = t * QT + row;
                 const bool valid = i < p.N;
                 const int ic = valid ? i : p.N - 1;
                 const int rci = s.rc[ic];
                 const uint8_t regi = masked ? reg[ic] : 0;
+                const uint32_t regi4 = (uint32_t)regi * 0x01010101u;
+                const bool warp_rows = t * QT + q * 32 < p.N;   // warp-uniform: any valid row in this warp?
                 // Single-pass softmax when it is provably safe: |s_ij| <= |q_i| max_j|k_j| scale =: bound, so with
                 // m = bound every exponent lies in [-2 bound - bias range, 0]; for bound <= 50 (log2 units) nothing
                 // can underflow fp32/bf16.  Otherwise (huge logits) fall back to the exact two-pass row max.
-                const float bound = sqrtf(row_norm2(p.qkv + (((long long)b_ * p.N + ic) * 3) * C + h * HD) * k2max) * p.scale_log2;
+                const float bound = sqrtf(s.q2[st][ic] * k2max) * p.scale_log2;
                 const bool fast = __all_sync(0xffffffffu, bound <= 50.0f);
                 long long t_a = clock64();
-                tc::mbar_wait(s.s_full, sph); sph ^= 1;
+                tc::mbar_wait(&s.s_full[0], sph);
+                if (!fast) tc::mbar_wait(&s.s_full[1], sph);
                 tc::tc_fence_after();
                 long long t_b = clock64();
-                // ---- pass 1: row max of the raw scores (+ exact mask term in masked windows); the bias is
-                //      bounded by its per-head maximum `mb`, so mx below is an upper bound of the true row max
-                const bool warp_rows = t * QT + q * 32 < p.N;   // warp-uniform: any valid row in this warp?
-                const int cfull = min(cend, p.N & ~15);          // chunks below cfull have no padded columns
-                const uint32_t regi4 = (uint32_t)regi * 0x01010101u;
-                float mx = -INFINITY;
+                float mx;
                 if (fast) {
                     mx = bound + mb;
                 } else {
-                if (warp_rows) {
-                    const uint32_t srow = tmem + lane_base + S_COL;
-                    mx = masked ? fwd_rowmax<true>(srow, cbeg, cfull, reg_a, regi4, p.scale_log2)
-                                : fwd_rowmax<false>(srow, cbeg, cfull, reg_a, regi4, p.scale_log2);
-                    for (int c = max(cbeg, cfull); c < cend; c += 16) {   // chunk with columns >= N
-                        uint32_t r[16];
-                        tc::tmem_ld_32x16(tmem + lane_base + S_COL + c, r);
-                        tc::tmem_ld_wait();
+                    // ---- pass 1: row max of the raw scores (+ exact mask term in masked windows) over both halves;
+                    //      the bias is bounded by its per-head maximum `mb`, so mx is an upper bound of the true max
+                    mx = -INFINITY;
+                    if (warp_rows) {
 #pragma unroll
-                        for (int e = 0; e < 16; ++e) {
-                            if (c + e < p.N) {
-                                float v = __uint_as_float(r[e]);
-                                if (masked) v = v * p.scale_log2 + ((reg[c + e] != regi) ? MASKV : 0.f);
-                                mx = fmaxf(mx, v);
+                        for (int hh = 0; hh < NHALF; ++hh) {
+                            const int cfull = min(ce[hh], nfull);
+                            mx = fmaxf(mx, masked ? fwd_rowmax<true>(srow, cb[hh], cfull, reg_a, regi4, p.scale_log2)
+                                                  : fwd_rowmax<false>(srow, cb[hh], cfull, reg_a, regi4, p.scale_log2) * p.scale_log2);
+                            for (int c = max(cb[hh], cfull); c < ce[hh]; c += 16) {   // chunk with columns >= N
+                                uint32_t r[16];
+                                tc::tmem_ld_32x16(srow + c, r);
+                                tc::tmem_ld_wait();
+#pragma unroll
+                                for (int e = 0; e < 16; ++e) {
+                                    if (c + e < p.N) {
+                                        float v = __uint_as_float(r[e]) * p.scale_log2;
+                                        if (masked && reg[c + e] != regi) v += MASKV;
+                                        mx = fmaxf(mx, v);
+                                    }
+                                }
                             }
                         }
                     }
-                    if (!masked) mx *= p.scale_log2;   // scale > 0: max commutes with the scaling
-                }
-                s.xmax[half * QT + row] = mx;
-                tc::named_bar_sync(1 + q, 32 * NPARTS);
+                    s.xmax[part * QT + row] = mx;
+                    tc::named_bar_sync(1 + q, 32 * NPARTS);
 #pragma unroll
-                for (int k = 0; k < NPARTS; ++k) mx = fmaxf(mx, s.xmax[k * QT + row]);
-                mx += mb;
+                    for (int k = 0; k < NPARTS; ++k) mx = fmaxf(mx, s.xmax[k * QT + row]);
+                    tc::named_bar_sync(1 + q, 32 * NPARTS);   // xmax may be rewritten by the next tile
+                    mx += mb;
                 }
                 long long t_c = clock64();
-                // ---- pass 2: p = exp2(s - max) -> packed bf16 into TMEM (aliasing S), row sum in fp32.
-                //      Done in four key-range quarters; after each one the MMA warp may start that part of P.V
+                // ---- pass 2: p = exp2(s - max) -> packed bf16 into TMEM (aliasing S), row sum in fp32, half by half;
+                //      after each half the MMA warp runs that half of P.V and then the half's S for the next tile
                 float sum = 0.f;
                 const uint32_t tabrow = tc::smem_u32(tab + rci);
                 const float nm = -mx;
-                const uint32_t srow = tmem + lane_base + S_COL, prow = srow + pbase;
-                for (int qq = 0; qq < NSUB; ++qq) {
-                    const int qb = sub_bound(p.Npad, half, qq), qe = sub_bound(p.Npad, half, qq + 1);
+#pragma unroll
+                for (int hh = 0; hh < NHALF; ++hh) {
+                    if (hh == 1 && fast) { tc::mbar_wait(&s.s_full[1], sph); tc::tc_fence_after(); }
+                    const int qb = cb[hh], qe = ce[hh];
+                    const uint32_t prow = srow + qb;   // P (packed bf16) aliases the part's own S columns
                     if (warp_rows) {
-                        const int qf = min(qe, cfull);
-                        sum += masked ? fwd_exp<true>(srow, prow, cbeg, qb, qf, tabrow, cc_a, reg_a, regi4, p.scale_log2, nm)
-                                      : fwd_exp<false>(srow, prow, cbeg, qb, qf, tabrow, cc_a, reg_a, regi4, p.scale_log2, nm);
-                        for (int c = max(qb, cfull); c < qe; c += 16) {   // chunk with columns >= N
+                        const int qf = min(qe, nfull);
+                        sum += masked ? fwd_exp<true>(srow, prow, qb, qb, qf, tabrow, cc_a, reg_a, regi4, p.scale_log2, nm)
+                                      : fwd_exp<false>(srow, prow, qb, qb, qf, tabrow, cc_a, reg_a, regi4, p.scale_log2, nm);
+                        for (int c = max(qb, qf); c < qe; c += 16) {   // chunk with columns >= N
                             uint32_t r[16];
                             tc::tmem_ld_32x16(srow + c, r);
                             tc::tmem_ld_wait();
@@ -436,48 +495,24 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const FwdParams p)
                                 }
                                 pw[e / 2] = tc::pack_bf16(pv[0], pv[1]);
                             }
-                            tc::tmem_st_32x8(prow + (c - cbeg) / 2, pw);
+                            tc::tmem_st_32x8(prow + (c - qb) / 2, pw);
                         }
                     }
+                    if (hh == 0 && t > 0) epilogue(t - 1, mx_prev);
                     tc::tmem_st_wait();
-                    if (qq == NSUB - 1) s.xsum[half * QT + row] = sum;
+                    if (hh == NHALF - 1) s.xsum[(t & 1) * 4 * QT + part * QT + row] = sum;
                     tc::tc_fence_before();
                     __syncwarp();
-                    if (lane == 0) tc::mbar_arrive(&s.p_full[qq]);
+                    if (lane == 0) tc::mbar_arrive(&s.p_full[hh]);
                 }
-                long long t_d = clock64();
-                // ---- epilogue: O / l -> bf16 -> global; lse
-                tc::mbar_wait(s.o_full, oph); oph ^= 1;
-                tc::tc_fence_after();
-                long long t_e = clock64();
-                float l = 0.f;
-#pragma unroll
-                for (int k = 0; k < NPARTS; ++k) l += s.xsum[k * QT + row];
-                const float inv = __fdividef(1.0f, l);
-                uint32_t o[16];
-                tc::tmem_ld_32x16(tmem + lane_base + O_COL + (half & 1) * 16, o);
-                tc::tmem_ld_wait();
-                if (valid && half < 2) {
-                    __nv_bfloat16* dst = p.out + ((long long)b_ * p.N + i) * C + h * HD + half * 16;
-                    uint4 u0, u1;
-                    u0.x = tc::pack_bf16(__uint_as_float(o[0]) * inv, __uint_as_float(o[1]) * inv);
-                    u0.y = tc::pack_bf16(__uint_as_float(o[2]) * inv, __uint_as_float(o[3]) * inv);
-                    u0.z = tc::pack_bf16(__uint_as_float(o[4]) * inv, __uint_as_float(o[5]) * inv);
-                    u0.w = tc::pack_bf16(__uint_as_float(o[6]) * inv, __uint_as_float(o[7]) * inv);
-                    u1.x = tc::pack_bf16(__uint_as_float(o[8]) * inv, __uint_as_float(o[9]) * inv);
-                    u1.y = tc::pack_bf16(__uint_as_float(o[10]) * inv, __uint_as_float(o[11]) * inv);
-                    u1.z = tc::pack_bf16(__uint_as_float(o[12]) * inv, __uint_as_float(o[13]) * inv);
-                    u1.w = tc::pack_bf16(__uint_as_float(o[14]) * inv, __uint_as_float(o[15]) * inv);
-                    reinterpret_cast<uint4*>(dst)[0] = u0;
-                    reinterpret_cast<uint4*>(dst)[1] = u1;
-                    if (half == 0) p.lse[((long long)b_ * p.nH + h) * p.N + i] = (mx + __log2f(l)) * LN2;
-                }
-                tc::tc_fence_before();  // O reads complete before the next tile's p_full arrive lets PV overwrite O
+                sph ^= 1;
+                mx_prev = mx;
                 if (p.dbg && blockIdx.x == 0 && threadIdx.x == 128) {
-                    long long t_f = clock64();
-                    p.dbg[0] += t_b - t_a; p.dbg[1] += t_c - t_b; p.dbg[2] += t_d - t_c; p.dbg[3] += t_e - t_d; p.dbg[4] += t_f - t_e; p.dbg[5] += 1;
+                    long long t_d = clock64();
+                    p.dbg[0] += t_b - t_a; p.dbg[1] += t_c - t_b; p.dbg[2] += t_d - t_c; p.dbg[5] += 1;
                 }
             }
+            epilogue(p.nq - 1, mx_prev);
             __syncwarp();
             if (lane == 0) tc::mbar_arrive(&s.aux_empty[st]);
         }
@@ -515,6 +550,7 @@ int tc_attn_fwd(const void* qkv, const void* table, const int32_t* rowcode, cons
     p.scale_log2 = scale * LOG2E;
     p.Npad = (N + 15) / 16 * 16;
     p.nq = (N + QT - 1) / QT;
+    p.h0 = ((p.Npad / 16 + 1) / 2) * 16;
     {
         static long long* dbg = nullptr;
         static bool init = false;
