@@ -115,7 +115,7 @@ __global__ void __launch_bounds__(256) ln_fwd_kernel(const T* __restrict__ x, co
 // FUSE: also accumulate the column reductions (dgamma = sum dy*xhat, dbeta = sum dy) in registers -- each lane owns
 // the same column vectors for every row it visits -- and emit one fixed-order partial per block (part[block][2][Cw]).
 template <typename T, typename TDY, int LANES, int VPL, int GROUPS, bool FUSE>
-__global__ void __launch_bounds__(256) ln_bwd_kernel(const TDY* __restrict__ dy, const T* __restrict__ x,
+__global__ void __launch_bounds__(256, (VPL == 1 ? 4 : (VPL == 2 ? 2 : 1))) ln_bwd_kernel(const TDY* __restrict__ dy, const T* __restrict__ x,
                                                      const T* __restrict__ gamma, const float* __restrict__ mean,
                                                      const float* __restrict__ rstd, const int32_t* __restrict__ map,
                                                      const T* __restrict__ dres, T* __restrict__ dx, int B, int Tin,
@@ -136,83 +136,88 @@ __global__ void __launch_bounds__(256) ln_bwd_kernel(const TDY* __restrict__ dy,
 #pragma unroll
         for (int e = 0; e < VN; ++e) { ag[k][e] = 0.f; ab[k][e] = 0.f; }
 
+    using PackT = Pack<T, VN>;
+    const T* res_src = dres ? dres : x;               // always-valid address for the (possibly absent) residual gradient
     for (long long row0 = warp_global * RPW; row0 < nrows; row0 += warp_stride * RPW) {
         const long long row = row0 + sub;
         const bool row_ok = row < nrows;
-        const int b = row_ok ? (int)(row / Tout) : 0;
-        const int r = row_ok ? (int)(row - (long long)b * Tout) : 0;
+        const long long rowc = row_ok ? row : 0;
+        const int b = (int)(rowc / Tout);
+        const int r = (int)(rowc - (long long)b * Tout);
         int src1 = r;
         if (GROUPS == 1 && map) src1 = map[r];
-        const float mu = row_ok ? mean[row] : 0.f, rs = row_ok ? rstd[row] : 0.f;
-        float xh[VPL][VN], g[VPL][VN];
+        const float mu = row_ok ? mean[rowc] : 0.f, rs = row_ok ? rstd[rowc] : 0.f;
+        // ---- phase 1: predicates and (clamped, always valid) addresses -- so that every global load of the row can be
+        //      issued unconditionally and back to back (one exposed memory latency per row instead of one per vector)
+        bool act[VPL], has_x[VPL];
         long long off[VPL];
-        float s1 = 0.f, s2 = 0.f;
+        int vic[VPL];
 #pragma unroll
         for (int k = 0; k < VPL; ++k) {
             const int vi = l + k * LANES;
-            off[k] = -1;
+            act[k] = row_ok && vi < nvec;
+            vic[k] = vi < nvec ? vi : 0;
+            int src = src1, col = vic[k] * VN;
+            if (GROUPS > 1) {
+                const int gi = vic[k] / vec_per_group;
+                src = map[(long long)r * GROUPS + gi];
+                col = (vic[k] - gi * vec_per_group) * VN;
+            }
+            has_x[k] = act[k] && src >= 0;
+            off[k] = has_x[k] ? ((long long)b * Tin + src) * C + col : 0;
+        }
+        // ---- phase 2: loads
+        float xh[VPL][VN], g[VPL][VN];
+        PackT rr[VPL];
 #pragma unroll
-            for (int e = 0; e < VN; ++e) { xh[k][e] = 0.f; g[k][e] = 0.f; }
-            if (row_ok && vi < nvec) {
-                int src = src1, col = vi * VN;
-                if (GROUPS > 1) {
-                    const int gi = vi / vec_per_group;
-                    src = map[(long long)r * GROUPS + gi];
-                    col = (vi - gi * vec_per_group) * VN;
+        for (int k = 0; k < VPL; ++k) {
+            constexpr int VD = Vec16<TDY>::N;
+            if constexpr (VD == VN) {
+                load_vec<TDY>(dy + rowc * Cw + vic[k] * VN, g[k]);
+            } else {
+#pragma unroll
+                for (int h = 0; h < VN / VD; ++h) {
+                    float dd[VD];
+                    load_vec<TDY>(dy + rowc * Cw + vic[k] * VN + h * VD, dd);
+#pragma unroll
+                    for (int e = 0; e < VD; ++e) g[k][h * VD + e] = dd[e];
                 }
-                float gm[VN], d[VN];
-                load_vec<T>(gamma + vi * VN, gm);
-                // dy row (width Cw) in TDY
-                {
-                    constexpr int VD = Vec16<TDY>::N;
-                    if constexpr (VD == VN) {
-                        load_vec<TDY>(dy + row * Cw + vi * VN, d);
-                    } else {
+            }
+            load_vec<T>(x + off[k], xh[k]);
+            rr[k] = *reinterpret_cast<const PackT*>(res_src + off[k]);
+        }
+        // ---- phase 3: row statistics of g = dy * gamma
+        float s1 = 0.f, s2 = 0.f;
 #pragma unroll
-                        for (int h = 0; h < VN / VD; ++h) {
-                            float dd[VD];
-                            load_vec<TDY>(dy + row * Cw + vi * VN + h * VD, dd);
+        for (int k = 0; k < VPL; ++k) {
+            float gm[VN];
+            load_vec<T>(gamma + vic[k] * VN, gm);
+            // padded INPUT group (GROUPS > 1, src < 0): x = 0 took part in the statistics
+            const bool pad_in = GROUPS > 1 && act[k] && !has_x[k];
+            const bool fuse_k = FUSE && act[k] && !(GROUPS == 1 && !has_x[k]);   // zeroed (padded) output rows carry no gradient
 #pragma unroll
-                            for (int e = 0; e < VD; ++e) d[h * VD + e] = dd[e];
-                        }
-                    }
-                }
-                if (src >= 0) {
-                    off[k] = ((long long)b * Tin + src) * C + col;
-                    float xv[VN];
-                    load_vec<T>(x + off[k], xv);
-#pragma unroll
-                    for (int e = 0; e < VN; ++e) xh[k][e] = (xv[e] - mu) * rs;
-                } else if (GROUPS > 1) {
-                    // padded INPUT group: x = 0 took part in the statistics
-#pragma unroll
-                    for (int e = 0; e < VN; ++e) xh[k][e] = (0.f - mu) * rs;
-                }
-#pragma unroll
-                for (int e = 0; e < VN; ++e) {
-                    g[k][e] = d[e] * gm[e];
-                    s1 += g[k][e];
-                    s2 += g[k][e] * xh[k][e];
-                }
-                if (FUSE && !(GROUPS == 1 && src < 0)) {   // zeroed (padded) output rows carry no gradient
-#pragma unroll
-                    for (int e = 0; e < VN; ++e) { ag[k][e] = fmaf(d[e], xh[k][e], ag[k][e]); ab[k][e] += d[e]; }
-                }
+            for (int e = 0; e < VN; ++e) {
+                const float d = act[k] ? g[k][e] : 0.f;
+                const float xv = has_x[k] ? (xh[k][e] - mu) * rs : (pad_in ? (0.f - mu) * rs : 0.f);
+                xh[k][e] = xv;
+                if (fuse_k) { ag[k][e] = fmaf(d, xv, ag[k][e]); ab[k][e] += d; }
+                const float gg = d * gm[e];
+                g[k][e] = gg;
+                s1 += gg;
+                s2 += gg * xv;
             }
         }
         const float c1 = group_sum<LANES>(s1) * inv_c;
         const float c2 = group_sum<LANES>(s2) * inv_c;
 #pragma unroll
         for (int k = 0; k < VPL; ++k) {
-            if (off[k] >= 0) {
+            if (has_x[k]) {
                 float o[VN];
 #pragma unroll
                 for (int e = 0; e < VN; ++e) o[e] = rs * (g[k][e] - c1 - xh[k][e] * c2);
                 if (dres) {
-                    float rr[VN];
-                    load_vec<T>(dres + off[k], rr);
 #pragma unroll
-                    for (int e = 0; e < VN; ++e) o[e] += rr[e];
+                    for (int e = 0; e < VN; ++e) o[e] += to_f<T>(rr[k].v[e]);
                 }
                 if (dx) store_vec<T>(dx + off[k], o);
             }
@@ -319,26 +324,28 @@ __global__ void __launch_bounds__(256) ln_colsum_kernel(const TDY* __restrict__ 
     }
 }
 
-// blockDim (32, 8): 32 columns per block, the partial rows strided over ty, fixed-order combine through smem
-__global__ void colsum_finish_kernel(const float* __restrict__ part, int splits, int Cw, float* __restrict__ dgamma,
-                                     float* __restrict__ dbeta) {
-    __shared__ float sm[2][8][33];
-    const int c = blockIdx.x * 32 + threadIdx.x;
+// blockDim (8, 128): 8 columns (one 32-byte sector per partial row) per block, the partial rows strided over ty,
+// fixed-order combine through shared memory.  Many small blocks: the partial matrix is read by the whole chip.
+constexpr int kFinTX = 8, kFinTY = 128;
+__global__ void __launch_bounds__(kFinTX * kFinTY)
+colsum_finish_kernel(const float* __restrict__ part, int splits, int Cw, float* __restrict__ dgamma,
+                     float* __restrict__ dbeta) {
+    __shared__ float sm[2][kFinTY][kFinTX + 1];
+    const int c = blockIdx.x * kFinTX + threadIdx.x;
     float s1 = 0.f, s2 = 0.f;
     if (c < Cw)
-        for (int s = threadIdx.y; s < splits; s += 8) {
+        for (int s = threadIdx.y; s < splits; s += kFinTY) {
             s1 += part[(size_t)s * 2 * Cw + c];
             s2 += part[(size_t)s * 2 * Cw + Cw + c];
         }
     sm[0][threadIdx.y][threadIdx.x] = s1;
     sm[1][threadIdx.y][threadIdx.x] = s2;
     __syncthreads();
-    if (threadIdx.y == 0 && c < Cw) {
-        float t1 = 0.f, t2 = 0.f;
-#pragma unroll
-        for (int y = 0; y < 8; ++y) { t1 += sm[0][y][threadIdx.x]; t2 += sm[1][y][threadIdx.x]; }
-        if (dgamma) dgamma[c] = t1;
-        if (dbeta) dbeta[c] = t2;
+    if (threadIdx.y < 2 && c < Cw) {   // row 0 of the block finishes dgamma, row 1 dbeta (serial, fixed order)
+        float t = 0.f;
+        for (int y = 0; y < kFinTY; ++y) t += sm[threadIdx.y][y][threadIdx.x];
+        float* out = threadIdx.y == 0 ? dgamma : dbeta;
+        if (out) out[c] = t;
     }
 }
 
@@ -415,11 +422,26 @@ static int launch_ln_bwd(const void* dy, const void* x, const void* gamma, const
     const bool fuse = want_cols && cfg.vpl <= 4 && Cw <= 1024;
     if (dx || fuse) {
         int grid = row_grid((long long)B * Tout, cfg.lanes);
-        if (fuse && grid > kColSplits) grid = kColSplits;
         if (fuse) {
-            VSW_ROW_DISPATCH(cfg, (ln_bwd_kernel<T, TDY, LANES, (VPL <= 4 ? VPL : 1), GROUPS, true><<<grid, 256, 0, st>>>(
-                                      (const TDY*)dy, (const T*)x, (const T*)gamma, mean, rstd, map, (const T*)dres, (T*)dx,
-                                      B, Tin, Tout, C, (float*)ws)));
+            // persistent sizing: one resident wave (register-limited occupancy x SMs), >= 4 rows per warp, so the
+            // per-block column-partial epilogue is amortised and no block waits for a second wave
+            VSW_ROW_DISPATCH(cfg, ({
+                auto kern = ln_bwd_kernel<T, TDY, LANES, (VPL <= 4 ? VPL : 1), GROUPS, true>;
+                static int resident = 0;
+                if (!resident) {
+                    int nb = 0;
+                    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, kern, 256, 0) != cudaSuccess || nb < 1) nb = 1;
+                    resident = nb * kNumSMs;
+                }
+                const long long rows_per_block = 8LL * (32 / LANES) * 4;
+                long long g = ((long long)B * Tout + rows_per_block - 1) / rows_per_block;
+                if (g > resident) g = resident;
+                if (g > kColSplits) g = kColSplits;
+                if (g < 1) g = 1;
+                grid = (int)g;
+                kern<<<grid, 256, 0, st>>>((const TDY*)dy, (const T*)x, (const T*)gamma, mean, rstd, map, (const T*)dres,
+                                           (T*)dx, B, Tin, Tout, C, (float*)ws);
+            }));
         } else {
             VSW_ROW_DISPATCH(cfg, (ln_bwd_kernel<T, TDY, LANES, VPL, GROUPS, false><<<grid, 256, 0, st>>>(
                                       (const TDY*)dy, (const T*)x, (const T*)gamma, mean, rstd, map, (const T*)dres, (T*)dx,
@@ -428,7 +450,7 @@ static int launch_ln_bwd(const void* dy, const void* x, const void* gamma, const
         int rc = check_launch("ln_bwd");
         if (rc) return rc;
         if (fuse) {
-            colsum_finish_kernel<<<ceil_div(Cw, 32), dim3(32, 8), 0, st>>>((const float*)ws, grid, Cw, dgamma, dbeta);
+            colsum_finish_kernel<<<ceil_div(Cw, kFinTX), dim3(kFinTX, kFinTY), 0, st>>>((const float*)ws, grid, Cw, dgamma, dbeta);
             return check_launch("ln_colsum_finish");
         }
     }
@@ -445,7 +467,7 @@ static int launch_ln_bwd(const void* dy, const void* x, const void* gamma, const
                                                                      (float*)ws, B, Tin, Tout, C);
         int rc = check_launch("ln_colsum");
         if (rc) return rc;
-        colsum_finish_kernel<<<ceil_div(Cw, 32), dim3(32, 8), 0, st>>>((const float*)ws, splits, Cw, dgamma, dbeta);
+        colsum_finish_kernel<<<ceil_div(Cw, kFinTX), dim3(kFinTX, kFinTY), 0, st>>>((const float*)ws, splits, Cw, dgamma, dbeta);
         rc = check_launch("ln_colsum_finish");
         if (rc) return rc;
     }

@@ -49,6 +49,10 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
         : "memory");
     return ok != 0;
 }
+// warpgroup-wide register re-partitioning (all 4 warps of an aligned warpgroup must execute it)
+template <int N> __device__ __forceinline__ void setmaxnreg_inc() { asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(N)); }
+template <int N> __device__ __forceinline__ void setmaxnreg_dec() { asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(N)); }
+
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
     for (uint32_t it = 0; it < (1u << 24); ++it)
         if (mbar_try_wait(bar, parity)) return;

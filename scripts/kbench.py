@@ -15,15 +15,30 @@ vsw = importlib.import_module("pytorch_empirical-mvm_b200")
 VF, L = vsw.functional, vsw._lib
 
 
+GRAPH = False
+
+
 def timeit(fn, iters=10, warm=3):
+    """ms per call; with GRAPH the calls are captured into one CUDA graph so host launch overhead is excluded."""
     for _ in range(warm):
         fn()
     torch.cuda.synchronize()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
-    for _ in range(iters):
-        fn()
-    e1.record()
+    if GRAPH:
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g):
+            for _ in range(iters):
+                fn()
+        g.replay()
+        torch.cuda.synchronize()
+        e0.record()
+        g.replay()
+        e1.record()
+    else:
+        e0.record()
+        for _ in range(iters):
+            fn()
+        e1.record()
     torch.cuda.synchronize()
     return e0.elapsed_time(e1) / iters
 
@@ -69,12 +84,34 @@ def linear_case(M, N, K, iters):
                 t_flop_ms=fl / 1373.6e9, t_byte_ms=by / 6545.6e6)
 
 
+def ln_case(B, grid, C, shifted, iters):
+    window = (8, 7, 7)
+    shift = (4, 3, 3) if shifted else (0, 0, 0)
+    plan = VF.window_plan(grid, window, shift, "cuda")
+    T = grid[0] * grid[1] * grid[2]
+    Tout = plan.nW * plan.N
+    x = torch.randn(B, T, C, device="cuda").bfloat16()
+    g = torch.ones(C, device="cuda").bfloat16(); b = torch.zeros(C, device="cuda").bfloat16()
+    res = {}
+    for name, gmap, To in (("plain", None, T), ("gather", plan.gather, Tout)):
+        y, mean, rstd = VF.ln_fwd(x, g, b, gmap, B, T, To, C)
+        dy = torch.randn_like(y); dres = torch.randn_like(x)
+        tf = timeit(lambda: VF.ln_fwd(x, g, b, gmap, B, T, To, C), iters)
+        tb = timeit(lambda: VF.ln_bwd(dy, x, g, mean, rstd, gmap, dres, B, T, To, C), iters)
+        fb = 2.0 * B * C * (T + To); bb = 2.0 * B * C * (To + 3 * T)
+        res[name] = dict(fwd_ms=tf, bwd_ms=tb, fwd_gbs=fb / tf / 1e6, bwd_gbs=bb / tb / 1e6)
+    return dict(kernel="ln", B=B, T=T, C=C, shifted=shifted, **{f"{k}_{m}": v for k, r in res.items() for m, v in r.items()})
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("what", nargs="?", default="all")
     ap.add_argument("--iters", type=int, default=10)
     ap.add_argument("--batch", type=int, default=32)
+    ap.add_argument("--graph", action="store_true", help="time CUDA-graph replays (no host launch overhead)")
     a = ap.parse_args()
+    global GRAPH
+    GRAPH = a.graph
     B = a.batch
     res = []
     if a.what in ("attn", "all"):
@@ -84,6 +121,10 @@ def main():
                     continue
                 res.append(attn_case(B, grid, nH, sh, a.iters))
                 print(json.dumps(res[-1]), flush=True)
+    if a.what in ("ln", "all"):
+        for grid, C in (((8, 56, 56), 128), ((8, 28, 28), 256), ((8, 14, 14), 512), ((8, 7, 7), 1024)):
+            res.append(ln_case(B, grid, C, grid != (8, 7, 7), a.iters))
+            print(json.dumps(res[-1]), flush=True)
     if a.what in ("linear", "all"):
         T = [25088, 6272, 1568, 392]
         for s, C in enumerate((128, 256, 512, 1024)):
