@@ -112,6 +112,7 @@ struct TcParams {
     const __nv_bfloat16* bias; __nv_bfloat16* out; __nv_bfloat16* aux_out; const __nv_bfloat16* res;
     const int32_t* rowmap; const float* rowscale; int rows_per_batch, dst_rows_per_batch;
     const __nv_bfloat16* gelu_pre; float* partial;
+    float* colsum;               // COLSUM kernels: per-split row sums of the A operand, [splits][M]
     long long ldc;
     long long* dbg;   // optional phase counters (VSW_GEMM_DEBUG)
 };
@@ -154,9 +155,16 @@ __device__ __forceinline__ void st8(__nv_bfloat16* p, const float (&v)[8]) {
 
 // EPI is a COMPILE-TIME parameter: with a run-time switch the compiler if-converts the branches and every tile pays
 // for the GELU / GELU' math (MUFU-bound) whatever the epilogue is.
-template <int BN, bool A_MN, bool B_MN, int STAGES, int EPI>
+//
+// COLSUM (wgrad only, A MN-major): four of the sixteen epilogue warps become "column-sum" warps that add up the A
+// tiles (= dy^T) of the first N-tile's work items straight from the TMA-filled shared-memory stages, so the bias
+// gradient sum_m dy[m, n] costs no second pass over dy.  They hold each stage (extra arrivals on `empty`) until read.
+template <int BN, bool A_MN, bool B_MN, int STAGES, int EPI, bool COLSUM = false>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const TcParams p) {
+    static_assert(!COLSUM || (A_MN && EPI == TE_PARTIAL), "COLSUM is a wgrad-only variant");
+    constexpr int CS_WARPS = COLSUM ? 4 : 0;
+    constexpr int EPI_WARPS = NUM_EPI_WARPS - CS_WARPS;
     constexpr int B_BYTES = BN * BK * 2;
     constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
     constexpr uint32_t TMEM_COLS = 2 * BN;  // power of two for BN in {64,128,256}
@@ -179,8 +187,8 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     if (warp == 0 && lane == 0) {
         tc::prefetch_tmap(&tmA);
         tc::prefetch_tmap(&tmB);
-        for (int s = 0; s < STAGES; ++s) { tc::mbar_init(&full[s], 1); tc::mbar_init(&empty[s], 1); }
-        for (int a = 0; a < 2; ++a) { tc::mbar_init(&tfull[a], 1); tc::mbar_init(&tempty[a], NUM_EPI_WARPS); }
+        for (int s = 0; s < STAGES; ++s) { tc::mbar_init(&full[s], 1); tc::mbar_init(&empty[s], 1 + CS_WARPS); }
+        for (int a = 0; a < 2; ++a) { tc::mbar_init(&tfull[a], 1); tc::mbar_init(&tempty[a], EPI_WARPS); }
         tc::fence_barrier_init();
     }
     if (warp == 1) tc::tmem_alloc(tmem_slot, TMEM_COLS);
@@ -260,10 +268,58 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 if (++acc == 2) { acc = 0; acc_phase ^= 1; }
             }
         }
+    } else if (COLSUM && warp >= 2 + EPI_WARPS) {
+        // ================= column-sum warps (COLSUM variant) =================
+        // A stage holds BM/64 boxes of 64 reduction rows x 128 B (64 bf16 of the A-row index, 128B-swizzled).  Thread
+        // (box bj, physical 16-byte chunk pch, row class rcl) reads rows rcl + 8 i: they all hold the same logical chunk
+        // pch ^ rcl, so the thread accumulates 8 fixed A-rows; 8 threads per (box, chunk) are combined at the end.
+        const int te = threadIdx.x - (2 + EPI_WARPS) * 32;   // 0..127
+        const int bj = te >> 6, pch = te & 7, rcl = (te >> 3) & 7;
+        float* scr = reinterpret_cast<float*>(smem + STAGES * STAGE_BYTES + 256);   // [128][8] (epilogue staging is unused by TE_PARTIAL)
+        int stage = 0; uint32_t phase = 0;
+        for (int w = blockIdx.x; w < total; w += gridDim.x) {
+            const int split = w / tiles, t = w - split * tiles;
+            const int m0 = (t / p.n_tiles_n) * BM;
+            const bool mine = (t % p.n_tiles_n) == 0;
+            const int kbeg = split * p.k_per_split;
+            const int kend = min(p.K, kbeg + p.k_per_split);
+            float cs[8];
+#pragma unroll
+            for (int e = 0; e < 8; ++e) cs[e] = 0.f;
+            for (int k0 = kbeg; k0 < kend; k0 += BK) {
+                tc::mbar_wait(&full[stage], phase);
+                if (mine) {
+                    const uint32_t sA = tc::smem_u32(smem + stage * STAGE_BYTES) + bj * 8192 + pch * 16;
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) {
+                        const uint4 v = tc::lds_u4(sA + (rcl + 8 * i) * 128);
+                        const float2 a = tc::unpack_bf16(v.x), b = tc::unpack_bf16(v.y), c = tc::unpack_bf16(v.z), d = tc::unpack_bf16(v.w);
+                        cs[0] += a.x; cs[1] += a.y; cs[2] += b.x; cs[3] += b.y; cs[4] += c.x; cs[5] += c.y; cs[6] += d.x; cs[7] += d.y;
+                    }
+                }
+                __syncwarp();
+                if (lane == 0) tc::mbar_arrive(&empty[stage]);
+                if (++stage == STAGES) { stage = 0; phase ^= 1; }
+            }
+            if (mine) {
+#pragma unroll
+                for (int e = 0; e < 8; ++e) scr[te * 8 + e] = cs[e];
+            }
+            tc::named_bar_sync(1, CS_WARPS * 32);
+            if (mine) {
+                // A-row n of the tile: box n / 64, logical chunk (n % 64) / 8, element n % 8; fixed summation order
+                const int nb = te >> 6, q8 = (te & 63) >> 3, e = te & 7;
+                float tsum = 0.f;
+#pragma unroll
+                for (int c = 0; c < 8; ++c) tsum += scr[(nb * 64 + c * 8 + (q8 ^ c)) * 8 + e];
+                if (m0 + te < p.M) p.colsum[(long long)split * p.M + m0 + te] = tsum;
+            }
+            tc::named_bar_sync(1, CS_WARPS * 32);
+        }
     } else {
         // ================= epilogue warps =================
         const int q = warp & 3;                 // TMEM lane quadrant this warp may access
-        const int half = (warp - 2) >> 2;       // which interleaved 32-column chunks it owns (0..NUM_EPI_WARPS/4-1)
+        const int half = (warp - 2) >> 2;       // which interleaved 32-column chunks it owns (0..EPI_WARPS/4-1)
         int acc = 0; uint32_t acc_phase = 0;
         for (int w = blockIdx.x; w < total; w += gridDim.x) {
             const int split = w / tiles, t = w - split * tiles;
@@ -290,7 +346,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             // sectors), instead of 32 lanes writing 16 bytes to 32 different rows.
             const uint32_t stg = stage_base + (uint32_t)(warp - 2) * STG_BYTES;
 #pragma unroll 1
-            for (int c = half; c < BN / 32; c += NUM_EPI_WARPS / 4) {
+            for (int c = half; c < BN / 32; c += EPI_WARPS / 4) {
                 uint32_t r32[32];
                 __syncwarp();
                 long long c_a = clock64();
@@ -442,11 +498,11 @@ long long* gemm_dbg_buffer(int bn, bool amn, bool bmn, const TcParams& p) {
     return dbg;
 }
 
-template <int BN, bool A_MN, bool B_MN, int EPI>
+template <int BN, bool A_MN, bool B_MN, int EPI, bool COLSUM = false>
 int launch_tc_epi(const CUtensorMap& tmA, const CUtensorMap& tmB, const TcParams& p, cudaStream_t st) {
     constexpr int STAGES = BN <= 128 ? 5 : 4;
     constexpr size_t SMEM = (size_t)STAGES * (A_BYTES + BN * BK * 2) + 1024 + 256 + NUM_EPI_WARPS * 32 * 64;
-    auto kern = tc_gemm_kernel<BN, A_MN, B_MN, STAGES, EPI>;
+    auto kern = tc_gemm_kernel<BN, A_MN, B_MN, STAGES, EPI, COLSUM>;
     static bool configured = false;  // benign race: the attribute is idempotent
     if (!configured) {
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM);
@@ -464,7 +520,8 @@ int launch_tc_epi(const CUtensorMap& tmA, const CUtensorMap& tmB, const TcParams
 template <int BN, bool A_MN, bool B_MN>
 int launch_tc(const CUtensorMap& tmA, const CUtensorMap& tmB, const TcParams& p, cudaStream_t st) {
     if constexpr (A_MN && B_MN) {
-        return launch_tc_epi<BN, true, true, TE_PARTIAL>(tmA, tmB, p, st);
+        return p.colsum ? launch_tc_epi<BN, true, true, TE_PARTIAL, true>(tmA, tmB, p, st)
+                        : launch_tc_epi<BN, true, true, TE_PARTIAL>(tmA, tmB, p, st);
     } else if constexpr (B_MN) {
         return p.gelu_pre ? launch_tc_epi<BN, false, true, TE_DGRAD_GELU>(tmA, tmB, p, st)
                           : launch_tc_epi<BN, false, true, TE_DGRAD>(tmA, tmB, p, st);
@@ -571,21 +628,40 @@ static void tc_wgrad_split(int M, int N, int K, int* splits, int* m_per_split) {
     *splits = (M + mps - 1) / mps;
 }
 
+// fixed-order reduction of the split partials: dw (elemsW values) and, optionally, db (elemsB values)
+template <typename TO>
+__global__ void wgrad_reduce_kernel(const float* __restrict__ partial, int splits, long long elemsW, TO* __restrict__ dw,
+                                    const float* __restrict__ cpart, int elemsB, TO* __restrict__ db) {
+    const long long total = elemsW + elemsB;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        float s = 0.f;
+        if (i < elemsW) {
+            for (int k = 0; k < splits; ++k) s += partial[(long long)k * elemsW + i];
+            dw[i] = from_f<TO>(s);
+        } else {
+            const long long j = i - elemsW;
+            for (int k = 0; k < splits; ++k) s += cpart[(long long)k * elemsB + j];
+            db[j] = from_f<TO>(s);
+        }
+    }
+}
+
 size_t tc_wgrad_workspace(int M, int N, int K) {
     int s, mps;
     tc_wgrad_split(M, N, K, &s, &mps);
-    return (size_t)s * N * K * sizeof(float);
+    return (size_t)s * N * K * sizeof(float) + (size_t)s * N * sizeof(float);
 }
 
-int tc_wgrad(const void* dy, const void* x, void* dw, int M, int N, int K, int grad_dtype, void* ws, size_t ws_bytes,
-             cudaStream_t st) {
+// dw = dy^T x and (db != nullptr) db = column sums of dy, both from ONE pass over dy
+int tc_wgrad(const void* dy, const void* x, void* dw, void* db, int M, int N, int K, int grad_dtype, void* ws,
+             size_t ws_bytes, cudaStream_t st) {
     if ((K % 8) || (N % 8) || !aligned16(dy) || !aligned16(x) || !aligned16(ws)) {
         set_error("tcgen05 wgrad: needs K %% 8 == 0, N %% 8 == 0 and 16-byte aligned pointers");
         return VSW_ERR_UNSUPPORTED;
     }
     int splits, mps;
     tc_wgrad_split(M, N, K, &splits, &mps);
-    if (ws_bytes < (size_t)splits * N * K * sizeof(float)) { set_error("tcgen05 wgrad: workspace too small"); return VSW_ERR_WORKSPACE; }
+    if (ws_bytes < tc_wgrad_workspace(M, N, K)) { set_error("tcgen05 wgrad: workspace too small"); return VSW_ERR_WORKSPACE; }
     CUtensorMap tmA, tmB;
     if (!make_tmap_2d_bf16(&tmA, dy, M, N, N, 64, 64)) return VSW_ERR_CUDA;  // MN-major A: rows = reduction (m)
     if (!make_tmap_2d_bf16(&tmB, x, M, K, K, 64, 64)) return VSW_ERR_CUDA;   // MN-major B
@@ -594,9 +670,17 @@ int tc_wgrad(const void* dy, const void* x, void* dw, int M, int N, int K, int g
     const int BN = wgrad_bn(K);
     p.n_tiles_m = ceil_div(N, BM); p.n_tiles_n = ceil_div(K, BN); p.splits = splits; p.k_per_split = mps;
     p.epi = TE_PARTIAL; p.partial = (float*)ws; p.ldc = K;
+    float* cpart = (float*)ws + (size_t)splits * N * K;
+    p.colsum = db ? cpart : nullptr;
     int rc = BN == 256 ? launch_tc<256, true, true>(tmA, tmB, p, st) : launch_tc<128, true, true>(tmA, tmB, p, st);
     if (rc) return rc;
-    return launch_partial_reduce((const float*)ws, splits, (long long)N * K, dw, grad_dtype, st);
+    const long long elemsW = (long long)N * K, total = elemsW + (db ? N : 0);
+    int blocks = (int)((total + 255) / 256);
+    if (blocks > kNumSMs * 8) blocks = kNumSMs * 8;
+    VSW_DISPATCH_DTYPE(grad_dtype, TO,
+                       (wgrad_reduce_kernel<TO><<<blocks, 256, 0, st>>>((const float*)ws, splits, elemsW, (TO*)dw, cpart,
+                                                                         db ? N : 0, (TO*)db)));
+    return check_launch("wgrad_reduce");
 }
 
 }  // namespace vsw

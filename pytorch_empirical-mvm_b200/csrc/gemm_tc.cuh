@@ -23,7 +23,7 @@ struct TcDgradArgs {
 int tc_linear(const TcLinearArgs& a, cudaStream_t st);
 int tc_dgrad(const TcDgradArgs& a, cudaStream_t st);
 size_t tc_wgrad_workspace(int M, int N, int K);
-int tc_wgrad(const void* dy, const void* x, void* dw, int M, int N, int K, int grad_dtype, void* ws, size_t ws_bytes,
-             cudaStream_t st);
+int tc_wgrad(const void* dy, const void* x, void* dw, void* db, int M, int N, int K, int grad_dtype, void* ws,
+             size_t ws_bytes, cudaStream_t st);
 
 }  // namespace vsw

@@ -107,8 +107,9 @@ extern "C" int vsw_linear_wgrad(const void* dy, const void* x, void* dw, void* d
     cudaStream_t st = (cudaStream_t)stream;
     int rc = VSW_ERR_UNSUPPORTED;
     if (want_tc(dtype)) {
-        rc = tc_wgrad(dy, x, dw, M, N, K, grad_dtype, ws, ws_bytes, st);
+        rc = tc_wgrad(dy, x, dw, db, M, N, K, grad_dtype, ws, ws_bytes, st);   // db: fused column sums of dy
         if (rc != VSW_OK && (rc != VSW_ERR_UNSUPPORTED || backend() == VSW_GEMM_TCGEN05)) return rc;
+        if (rc == VSW_OK) return VSW_OK;
     }
     if (rc == VSW_ERR_UNSUPPORTED) {
         int splits, mps;
