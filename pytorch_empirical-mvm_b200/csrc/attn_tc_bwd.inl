@@ -7,6 +7,10 @@
 //   dV_kb += P^T dO_t,  dK_kb += dS^T Q_t               A = P/dS (MN-major), B = dO_t/Q_t (MN-major)
 //   dQ_t  += dS K_kb                                    A = dS (K-major),    B = K_kb (MN-major)
 // dK/dV of the key block and dQ of all four query tiles stay in TMEM until complete (kb outer, t inner).
+// A short last query tile (N % 128 <= 8, e.g. 392 = 3 x 128 + 8) would cost a full softmax pass for 8 useful rows, so it
+// is processed TRANSPOSED: S^T = K_kb Q_tail^T and dP^T = V_kb dO_tail^T (128 keys x 16), thread = key, 8 queries each;
+// P^T / dS^T go to small un-swizzled K-major tiles (dV += P^T dO_tail, dK += dS^T Q_tail with K = 16), and dS is also
+// scattered into rows 0..7 of the regular dS tile for dQ_tail += dS K_kb.
 // A CTA is pinned to ONE head so its bias-table column and histograms persist across all its windows; the
 // per-CTA histograms are summed by a fixed-order second pass.
 namespace vsw {
@@ -18,6 +22,9 @@ constexpr int BW_P_OFF = 49152;                    // P  tile: 2 chunks x (128 r
 constexpr int BW_DS_OFF = 81920;                   // dS tile
 constexpr int BW_MISC_OFF = 114688;
 constexpr int BW_S = 0, BW_DP = 128, BW_DK = 256, BW_DV = 288, BW_DQ = 320;  // TMEM columns
+// transposed tail tile: P^T and dS^T (128 keys x 8 queries, 16 B per key) live inside the (then unused) P tile region,
+// each followed 4 KB later by a 2 KB zero chunk standing in for queries 8..15 of the K = 16 MMA
+constexpr int BW_TAIL_PT = 0, BW_TAIL_DST = 2048, BW_TAIL_LBO = 4096;
 
 struct BwdParams {
     const __nv_bfloat16* table; const int32_t* rowcode; const int32_t* colcode; const uint8_t* region;
@@ -26,6 +33,7 @@ struct BwdParams {
     int B_, nW, N, nH, L, Lpad, groups;
     float scale, scale_log2;
     int Npad, nq, nkb;
+    int ntail;        // > 0: the last query tile holds only ntail (<= 8) rows and is processed transposed (see below)
     long long* dbg;
     int wd, hw, boxhw;   // key permutation: column c' = hw_index * wd + plane (plane = temporal slab of the window)
 };
@@ -232,6 +240,32 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_const
                         tc::mbar_wait(&s.qd_full[st], ph);
                         tc::tc_fence_after();
                         const uint32_t qa = tc::smem_u32(base + BW_QD_OFF + st * 2 * BOX_BYTES), doa = qa + BOX_BYTES;
+                        if (p.ntail > 0 && t == p.nq - 1) {
+                            // ---- transposed tail tile: S^T = K_kb Q_tail^T, dP^T = V_kb dO_tail^T  (128 keys x 16 queries)
+                            const uint32_t id_st = tc::idesc_bf16(QT, 16, 0, 0);
+#pragma unroll
+                            for (int k = 0; k < 2; ++k)
+                                tc::umma_bf16(tmem + BW_S, tc::smem_desc_sw64(ka + k * 32, 0, 512),
+                                              tc::smem_desc_sw64(qa + k * 32, 0, 512), id_st, k);
+#pragma unroll
+                            for (int k = 0; k < 2; ++k)
+                                tc::umma_bf16(tmem + BW_DP, tc::smem_desc_sw64(va + k * 32, 0, 512),
+                                              tc::smem_desc_sw64(doa + k * 32, 0, 512), id_st, k);
+                            tc::umma_commit(s.s_full);
+                            tc::mbar_wait(s.pds_full, pdsph); pdsph ^= 1;
+                            tc::tc_fence_after();
+                            // P^T / dS^T: un-swizzled K-major tiles (8-row core matrices 128 B apart, second K chunk = zeros)
+                            tc::umma_bf16(tmem + BW_DV, tc::smem_desc(pa + BW_TAIL_PT, BW_TAIL_LBO, 128, 0),
+                                          tc::smem_desc_sw64(doa, 0, 512), id_q, t > 0 ? 1u : 0u);
+                            tc::umma_bf16(tmem + BW_DK, tc::smem_desc(pa + BW_TAIL_DST, BW_TAIL_LBO, 128, 0),
+                                          tc::smem_desc_sw64(qa, 0, 512), id_q, t > 0 ? 1u : 0u);
+                            for (int ks = 0; ks < nkeys / 16; ++ks)   // dQ_tail from rows 0..7 of the regular dS tile
+                                tc::umma_bf16(tmem + BW_DQ + t * HD,
+                                              tc::smem_desc_sw128(dsa + (ks >> 2) * 16384 + (ks & 3) * 32, 0, 1024),
+                                              tc::smem_desc_sw64(ka + ks * 1024, 0, 512), id_q, (kb > 0 || ks > 0) ? 1u : 0u);
+                            tc::umma_commit(&s.qd_empty[st]);
+                            continue;
+                        }
 #pragma unroll
                         for (int k = 0; k < 2; ++k)
                             tc::umma_bf16(tmem + BW_S, tc::smem_desc_sw64(qa + k * 32, 0, 512),
@@ -308,6 +342,88 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_const
                 const int nkeys = (nv + 15) & ~15;
                 const int cbeg = half * 64, cend = min(cbeg + 64, nkeys);   // my columns inside the block
                 for (int t = 0; t < p.nq; ++t) {
+                    if (p.ntail > 0 && t == p.nq - 1) {
+                        // ================= transposed tail tile: thread = key column `row`, queries tail0 .. tail0 + ntail =================
+                        const int tail0 = t * QT;
+                        if (kb == 0 && half == 0) {
+                            if (q == 0 && lane < 8) {   // delta / lse of the tail queries (thread = query)
+                                const int i = tail0 + lane;
+                                float delta_i = 0.f, nl2 = 0.f;
+                                if (i < p.N) {
+                                    const uint4* op = reinterpret_cast<const uint4*>(p.out + ((long long)b_ * p.N + i) * C + h * HD);
+                                    const uint4* dp = reinterpret_cast<const uint4*>(p.dout + ((long long)b_ * p.N + i) * C + h * HD);
+#pragma unroll
+                                    for (int v = 0; v < 4; ++v) {
+                                        const uint4 a = __ldg(op + v), b = __ldg(dp + v);
+                                        const uint32_t aw[4] = {a.x, a.y, a.z, a.w}, bw[4] = {b.x, b.y, b.z, b.w};
+#pragma unroll
+                                        for (int e = 0; e < 4; ++e) {
+                                            const float2 x = tc::unpack_bf16(aw[e]), y = tc::unpack_bf16(bw[e]);
+                                            delta_i = fmaf(x.x, y.x, delta_i);
+                                            delta_i = fmaf(x.y, y.y, delta_i);
+                                        }
+                                    }
+                                    nl2 = -p.lse[((long long)b_ * p.nH + h) * p.N + i] * LOG2E;
+                                }
+                                s.delta[i] = delta_i;
+                                s.lse2[i] = nl2;
+                            }
+                            tc::named_bar_sync(2, 128);   // the four half-0 warps
+                        }
+                        tc::mbar_wait(s.s_full, sph); sph ^= 1;
+                        tc::tc_fence_after();
+                        uint8_t* ptile = base + BW_P_OFF;
+                        if (half == 1) {
+                            // zero chunks (queries 8..15) of the two K = 16 operands
+                            *reinterpret_cast<uint4*>(ptile + BW_TAIL_PT + BW_TAIL_LBO + row * 16) = make_uint4(0, 0, 0, 0);
+                            *reinterpret_cast<uint4*>(ptile + BW_TAIL_DST + BW_TAIL_LBO + row * 16) = make_uint4(0, 0, 0, 0);
+                        } else {
+                            const int k0 = kb * QT;
+                            const int j = k0 + row;                 // column index (permuted key order)
+                            const bool key_ok = row < nv;
+                            uint32_t rs[16], rd[16];
+                            tc::tmem_ld_32x16(tmem + lane_base + BW_S, rs);
+                            tc::tmem_ld_32x16(tmem + lane_base + BW_DP, rd);
+                            const int ccj = key_ok ? s.cc[j] : 0;   // byte offset
+                            const uint8_t regj = (masked && key_ok) ? reg[j] : 0;
+                            const uint32_t tab_j = tc::smem_u32(s.tab) + ccj, hist_j = tc::smem_u32(hist) + ccj;
+                            uint8_t* dsreg = base + BW_DS_OFF + (row >> 6) * 16384 + (row & 7) * 2;   // regular dS tile, my key column
+                            const int unit = (row & 63) >> 3;
+                            tc::tmem_ld_wait();
+                            uint32_t pw[4], dw[4];
+#pragma unroll
+                            for (int e = 0; e < 8; e += 2) {
+                                float pv[2], dv[2];
+#pragma unroll
+                                for (int u = 0; u < 2; ++u) {
+                                    const int i = tail0 + e + u;
+                                    float pe = 0.f, ds = 0.f;
+                                    if (key_ok && e + u < p.ntail) {
+                                        const int rci = s.rc[i] * 4;
+                                        float v = fmaf(__uint_as_float(rs[e + u]), p.scale_log2, tc::lds_f32(tab_j + rci)) + s.lse2[i];
+                                        if (masked && s.regq[st][i] != regj) v += MASKV;
+                                        pe = tc::ex2_approx(v);
+                                        ds = pe * (__uint_as_float(rd[e + u]) - s.delta[i]);
+                                        // lanes = 32 distinct keys -> 32 distinct table entries for one query: plain read-modify-write
+                                        tc::sts_f32(hist_j + rci, tc::lds_f32(hist_j + rci) + ds);
+                                    }
+                                    pv[u] = pe;
+                                    dv[u] = ds;
+                                    // dS[query e+u][my key] into the regular (query-major, 128B-swizzled) dS tile for dQ_tail
+                                    *reinterpret_cast<__nv_bfloat16*>(dsreg + sw128_off(e + u, unit)) = __float2bfloat16_rn(ds);
+                                }
+                                pw[e / 2] = tc::pack_bf16(pv[0], pv[1]);
+                                dw[e / 2] = tc::pack_bf16(dv[0], dv[1]);
+                            }
+                            *reinterpret_cast<uint4*>(ptile + BW_TAIL_PT + row * 16) = make_uint4(pw[0], pw[1], pw[2], pw[3]);
+                            *reinterpret_cast<uint4*>(ptile + BW_TAIL_DST + row * 16) = make_uint4(dw[0], dw[1], dw[2], dw[3]);
+                        }
+                        tc::fence_proxy_async();
+                        tc::tc_fence_before();
+                        __syncwarp();
+                        if (lane == 0) tc::mbar_arrive(s.pds_full);
+                        continue;
+                    }
                     const int i = t * QT + row;
                     const bool valid = i < p.N;
                     const bool warp_valid = t * QT + q * 32 < p.N;
@@ -556,6 +672,7 @@ int tc_attn_bwd(const void* qkv, const void* out, const void* dout, const float*
     p.B_ = B_; p.nW = nW; p.N = N; p.nH = nH; p.L = L; p.Lpad = Lpad; p.groups = groups;
     p.scale = scale; p.scale_log2 = scale * LOG2E;
     p.Npad = (N + 15) / 16 * 16; p.nq = (N + QT - 1) / QT;
+    p.ntail = (N % QT != 0 && N % QT <= 8 && !getenv("VSW_ATTN_NO_TAIL")) ? N % QT : 0;
     p.wd = wd; p.hw = hw; p.boxhw = boxhw; p.nkb = (hw + boxhw - 1) / boxhw;
     {
         static long long* dbg = nullptr;
