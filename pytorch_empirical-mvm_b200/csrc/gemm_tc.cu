@@ -159,16 +159,29 @@ __device__ __forceinline__ void st8(__nv_bfloat16* p, const float (&v)[8]) {
 // COLSUM (wgrad only, A MN-major): four of the sixteen epilogue warps become "column-sum" warps that add up the A
 // tiles (= dy^T) of the first N-tile's work items straight from the TMA-filled shared-memory stages, so the bias
 // gradient sum_m dy[m, n] costs no second pass over dy.  They hold each stage (extra arrivals on `empty`) until read.
-template <int BN, bool A_MN, bool B_MN, int STAGES, int EPI, bool COLSUM = false>
+//
+// PAIR: two CTAs of a cluster (one TPC) work on one 256 x BN tile with cta_group::2 MMAs of M = 256: each CTA loads its own
+// 128 A rows and only HALF of the B tile (the tensor core reads the other half from the peer's shared memory), which cuts
+// the bytes every SM pulls through its L2 port per k-block from 48 KB to 32 KB -- the single-CTA 128 x 256 main loop is
+// bound by that port (~64 B/clk/SM), not by the tensor pipe.  Each CTA keeps its own 128 accumulator lanes, so the
+// epilogue is unchanged.  Barriers: `full` lives in the leader (both producers arrive + their bytes), `empty` / `tfull`
+// are multicast commits to both CTAs, `tempty` of the leader collects the epilogue warps of both CTAs.
+template <int BN, bool A_MN, bool B_MN, int STAGES, int EPI, bool COLSUM = false, bool PAIR = false>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const TcParams p) {
     static_assert(!COLSUM || (A_MN && EPI == TE_PARTIAL), "COLSUM is a wgrad-only variant");
+    static_assert(!(PAIR && COLSUM), "the column-sum warps need a CTA-local `full` barrier");
     constexpr int CS_WARPS = COLSUM ? 4 : 0;
     constexpr int EPI_WARPS = NUM_EPI_WARPS - CS_WARPS;
-    constexpr int B_BYTES = BN * BK * 2;
+    constexpr int BNL = PAIR ? BN / 2 : BN;           // B rows this CTA loads
+    constexpr int B_BYTES = BNL * BK * 2;
     constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
     constexpr uint32_t TMEM_COLS = 2 * BN;  // power of two for BN in {64,128,256}
-    constexpr uint32_t IDESC = tc::idesc_bf16(BM, BN, A_MN ? 1 : 0, B_MN ? 1 : 0);
+    constexpr uint32_t IDESC = tc::idesc_bf16(PAIR ? 2 * BM : BM, BN, A_MN ? 1 : 0, B_MN ? 1 : 0);
+    const uint32_t cta_rank = PAIR ? tc::cluster_ctarank() : 0u;
+    const int unit = PAIR ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;
+    const int n_units = PAIR ? (int)(gridDim.x >> 1) : (int)gridDim.x;
+    constexpr int TILE_M = PAIR ? 2 * BM : BM;        // rows of a work item
 
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = smem_raw + ((1024u - (tc::smem_u32(smem_raw) & 1023u)) & 1023u);   // keeps the shared address space
@@ -187,13 +200,13 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     if (warp == 0 && lane == 0) {
         tc::prefetch_tmap(&tmA);
         tc::prefetch_tmap(&tmB);
-        for (int s = 0; s < STAGES; ++s) { tc::mbar_init(&full[s], 1); tc::mbar_init(&empty[s], 1 + CS_WARPS); }
-        for (int a = 0; a < 2; ++a) { tc::mbar_init(&tfull[a], 1); tc::mbar_init(&tempty[a], EPI_WARPS); }
+        for (int s = 0; s < STAGES; ++s) { tc::mbar_init(&full[s], PAIR ? 2 : 1); tc::mbar_init(&empty[s], 1 + CS_WARPS); }
+        for (int a = 0; a < 2; ++a) { tc::mbar_init(&tfull[a], 1); tc::mbar_init(&tempty[a], (PAIR ? 2 : 1) * EPI_WARPS); }
         tc::fence_barrier_init();
     }
-    if (warp == 1) tc::tmem_alloc(tmem_slot, TMEM_COLS);
+    if (warp == 1) { if constexpr (PAIR) tc::tmem_alloc_2cta(tmem_slot, TMEM_COLS); else tc::tmem_alloc(tmem_slot, TMEM_COLS); }
     tc::tc_fence_before();
-    __syncthreads();
+    if constexpr (PAIR) tc::cluster_sync_all(); else __syncthreads();   // PAIR: the peer's barriers are initialised too
     tc::tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
 
@@ -201,16 +214,35 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         // ================= TMA producer =================
         if (lane == 0) {
             int stage = 0; uint32_t phase = 0;
-            for (int w = blockIdx.x; w < total; w += gridDim.x) {
+            for (int w = unit; w < total; w += n_units) {
                 const int split = w / tiles, t = w - split * tiles;
-                const int m0 = (t / p.n_tiles_n) * BM, n0 = (t % p.n_tiles_n) * BN;
+                const int m0 = (t / p.n_tiles_n) * TILE_M + (int)cta_rank * BM;       // this CTA's A rows
+                const int n0 = (t % p.n_tiles_n) * BN + (int)cta_rank * (BN - BNL);   // this CTA's share of the B rows
                 const int kbeg = split * p.k_per_split;
                 const int kend = min(p.K, kbeg + p.k_per_split);
                 for (int k0 = kbeg; k0 < kend; k0 += BK) {
                     tc::mbar_wait(&empty[stage], phase ^ 1);
-                    tc::mbar_expect_tx(&full[stage], STAGE_BYTES);
                     uint8_t* sA = smem + stage * STAGE_BYTES;
                     uint8_t* sB = sA + A_BYTES;
+                    if constexpr (PAIR) {
+                        // both CTAs load into their own smem; all completion bytes are signalled on the LEADER's barrier
+                        // (count 2: the leader's arrive + expect of both CTAs' bytes, the peer's plain remote arrive)
+                        const uint32_t fb = tc::mapa_u32(tc::smem_u32(&full[stage]), 0);
+                        if (cta_rank == 0) tc::mbar_expect_tx(&full[stage], 2 * STAGE_BYTES); else tc::mbar_arrive_cluster(fb);
+                        if (!A_MN) {
+                            tc::tma_load_2d_2sm(&tmA, fb, sA, k0, m0);
+                        } else {
+#pragma unroll
+                            for (int j = 0; j < BM / 64; ++j) tc::tma_load_2d_2sm(&tmA, fb, sA + j * 8192, m0 + 64 * j, k0);
+                        }
+                        if (!B_MN) {
+                            tc::tma_load_2d_2sm(&tmB, fb, sB, k0, n0);                     // box 64(k) x BN/2(n)
+                        } else {
+#pragma unroll
+                            for (int j = 0; j < BNL / 64; ++j) tc::tma_load_2d_2sm(&tmB, fb, sB + j * 8192, n0 + 64 * j, k0);
+                        }
+                    } else {
+                    tc::mbar_expect_tx(&full[stage], STAGE_BYTES);
                     if (!A_MN) {
                         tc::tma_load_2d(&tmA, &full[stage], sA, k0, m0);          // box 64(k) x 128(m)
                     } else {
@@ -225,16 +257,17 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                         for (int j = 0; j < BN / 64; ++j)                          // box 64(n) x 64(k)
                             tc::tma_load_2d(&tmB, &full[stage], sB + j * 8192, n0 + 64 * j, k0);
                     }
+                    }
                     if (++stage == STAGES) { stage = 0; phase ^= 1; }
                 }
             }
         }
     } else if (warp == 1) {
         // ================= MMA issuer =================
-        if (lane == 0) {
+        if (lane == 0 && cta_rank == 0) {   // PAIR: the leader issues for both CTAs
             int stage = 0; uint32_t phase = 0;
             int acc = 0; uint32_t acc_phase = 0;
-            for (int w = blockIdx.x; w < total; w += gridDim.x) {
+            for (int w = unit; w < total; w += n_units) {
                 const int split = w / tiles;
                 const int kbeg = split * p.k_per_split;
                 const int kend = min(p.K, kbeg + p.k_per_split);
@@ -257,13 +290,16 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                                                  : tc::smem_desc_sw128(aaddr + k * 32, 0, 1024);
                         const uint64_t bd = B_MN ? tc::smem_desc_sw128(baddr + k * 2048, 8192, 1024)
                                                  : tc::smem_desc_sw128(baddr + k * 32, 0, 1024);
-                        tc::umma_bf16(d_tmem, ad, bd, IDESC, accumulate);
+                        if constexpr (PAIR) tc::umma_bf16_2cta(d_tmem, ad, bd, IDESC, accumulate);
+                        else tc::umma_bf16(d_tmem, ad, bd, IDESC, accumulate);
                         accumulate = 1;
                     }
-                    tc::umma_commit(&empty[stage]);  // smem slot reusable once these MMAs retire
+                    // smem slot reusable once these MMAs retire (PAIR: in both CTAs)
+                    if constexpr (PAIR) tc::umma_commit_2cta(&empty[stage]); else tc::umma_commit(&empty[stage]);
                     if (++stage == STAGES) { stage = 0; phase ^= 1; }
                 }
-                tc::umma_commit(&tfull[acc]);        // accumulator complete -> epilogue
+                // accumulator complete -> epilogue
+                if constexpr (PAIR) tc::umma_commit_2cta(&tfull[acc]); else tc::umma_commit(&tfull[acc]);
                 if (p.dbg && blockIdx.x == 0) { p.dbg[0] += m_b - m_a; p.dbg[1] += m_wait_full; p.dbg[2] += clock64() - m_b; p.dbg[3] += 1; }
                 if (++acc == 2) { acc = 0; acc_phase ^= 1; }
             }
@@ -277,7 +313,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         const int bj = te >> 6, pch = te & 7, rcl = (te >> 3) & 7;
         float* scr = reinterpret_cast<float*>(smem + STAGES * STAGE_BYTES + 256);   // [128][8] (epilogue staging is unused by TE_PARTIAL)
         int stage = 0; uint32_t phase = 0;
-        for (int w = blockIdx.x; w < total; w += gridDim.x) {
+        for (int w = unit; w < total; w += n_units) {
             const int split = w / tiles, t = w - split * tiles;
             const int m0 = (t / p.n_tiles_n) * BM;
             const bool mine = (t % p.n_tiles_n) == 0;
@@ -321,9 +357,9 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         const int q = warp & 3;                 // TMEM lane quadrant this warp may access
         const int half = (warp - 2) >> 2;       // which interleaved 32-column chunks it owns (0..EPI_WARPS/4-1)
         int acc = 0; uint32_t acc_phase = 0;
-        for (int w = blockIdx.x; w < total; w += gridDim.x) {
+        for (int w = unit; w < total; w += n_units) {
             const int split = w / tiles, t = w - split * tiles;
-            const int m0 = (t / p.n_tiles_n) * BM, n0 = (t % p.n_tiles_n) * BN;
+            const int m0 = (t / p.n_tiles_n) * TILE_M + (int)cta_rank * BM, n0 = (t % p.n_tiles_n) * BN;
             long long e_a = clock64(), dbg_ld = 0, dbg_math = 0, dbg_st = 0;
             tc::mbar_wait(&tfull[acc], acc_phase);
             tc::tc_fence_after();
@@ -438,17 +474,23 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             }
             tc::tc_fence_before();
             __syncwarp();
-            if (lane == 0) tc::mbar_arrive(&tempty[acc]);
+            if (lane == 0) {
+                if constexpr (PAIR) tc::mbar_arrive_cluster(tc::mapa_u32(tc::smem_u32(&tempty[acc]), 0));   // the leader's barrier
+                else tc::mbar_arrive(&tempty[acc]);
+            }
             if (p.dbg && blockIdx.x == 0 && threadIdx.x == 64) { p.dbg[4] += e_b - e_a; p.dbg[5] += clock64() - e_b; p.dbg[6] += 1; p.dbg[8] += dbg_ld; p.dbg[9] += dbg_math; p.dbg[10] += dbg_st; }
             if (++acc == 2) { acc = 0; acc_phase ^= 1; }
         }
     }
 
+    // Reconverge the producer / MMA warps first: their lanes 1..31 must not sit in the (warp-aligned, blocking) cluster barrier
+    // while lane 0 is still working -- that would starve lane 0 of issue slots.
+    __syncwarp();
     tc::tc_fence_before();
-    __syncthreads();
+    if constexpr (PAIR) tc::cluster_sync_all(); else __syncthreads();   // PAIR: no CTA leaves while its peer may still signal it
     if (warp == 1) {
         tc::tc_fence_after();
-        tc::tmem_dealloc(tmem_base, TMEM_COLS);
+        if constexpr (PAIR) tc::tmem_dealloc_2cta(tmem_base, TMEM_COLS); else tc::tmem_dealloc(tmem_base, TMEM_COLS);
     }
 }
 
@@ -485,24 +527,25 @@ long long* gemm_dbg_buffer(int bn, bool amn, bool bmn, const TcParams& p) {
     static char last[128] = {0};
     if (!init) {
         init = true;
-        if (getenv("VSW_GEMM_DEBUG")) { cudaMalloc(&dbg, 128); cudaMemset(dbg, 0, 128); }
+        if (getenv("VSW_GEMM_DEBUG")) { cudaMalloc(&dbg, 1024); cudaMemset(dbg, 0, 1024); }
     }
     if (!dbg) return nullptr;
-    long long h[16];
-    cudaMemcpy(h, dbg, 128, cudaMemcpyDeviceToHost);
+    long long h[128];
+    cudaMemcpy(h, dbg, 1024, cudaMemcpyDeviceToHost);
     if (h[3]) fprintf(stderr, "[vsw gemm %s] tiles/cta=%lld  MMA thread: wait_tmem_empty=%lld wait_tma=%lld issue+rest=%lld | epilogue warp: wait_acc=%lld work=%lld (cycles per tile)\n",
                       last, h[3], h[0] / h[3], h[1] / h[3], (h[2] - h[1]) / h[3], h[4] / (h[6] + 1), h[5] / (h[6] + 1));
     if (h[3]) fprintf(stderr, "      epilogue split per tile: tmem_ld=%lld math=%lld stores=%lld\n", h[8] / (h[6] + 1), h[9] / (h[6] + 1), h[10] / (h[6] + 1));
-    cudaMemset(dbg, 0, 128);
+    cudaMemset(dbg, 0, 1024);
     snprintf(last, sizeof(last), "BN=%d A_MN=%d B_MN=%d M=%d N=%d K=%d epi=%d", bn, (int)amn, (int)bmn, p.M, p.N, p.K, p.epi);
     return dbg;
 }
 
-template <int BN, bool A_MN, bool B_MN, int EPI, bool COLSUM = false>
+template <int BN, bool A_MN, bool B_MN, int EPI, bool COLSUM = false, bool PAIR = false>
 int launch_tc_epi(const CUtensorMap& tmA, const CUtensorMap& tmB, const TcParams& p, cudaStream_t st) {
-    constexpr int STAGES = BN <= 128 ? 5 : 4;
-    constexpr size_t SMEM = (size_t)STAGES * (A_BYTES + BN * BK * 2) + 1024 + 256 + NUM_EPI_WARPS * 32 * 64;
-    auto kern = tc_gemm_kernel<BN, A_MN, B_MN, STAGES, EPI, COLSUM>;
+    constexpr int STAGE = A_BYTES + (PAIR ? BN / 2 : BN) * BK * 2;
+    constexpr int STAGES = PAIR ? 6 : (BN <= 128 ? 5 : 4);
+    constexpr size_t SMEM = (size_t)STAGES * STAGE + 1024 + 256 + NUM_EPI_WARPS * 32 * 64;
+    auto kern = tc_gemm_kernel<BN, A_MN, B_MN, STAGES, EPI, COLSUM, PAIR>;
     static bool configured = false;  // benign race: the attribute is idempotent
     if (!configured) {
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM);
@@ -510,26 +553,51 @@ int launch_tc_epi(const CUtensorMap& tmA, const CUtensorMap& tmB, const TcParams
         configured = true;
     }
     const int total = p.n_tiles_m * p.n_tiles_n * p.splits;
-    const int grid = total < kNumSMs ? total : kNumSMs;
     TcParams q = p;
     q.dbg = gemm_dbg_buffer(BN, A_MN, B_MN, p);
-    kern<<<grid, NUM_THREADS, SMEM, st>>>(tmA, tmB, q);
-    return check_launch("tc_gemm");
+    if constexpr (PAIR) {
+        // one CTA pair (cluster of 2 = one TPC) per work item slot
+        cudaLaunchConfig_t cfg = {};
+        cfg.blockDim = dim3(NUM_THREADS); cfg.dynamicSmemBytes = SMEM; cfg.stream = st;
+        cudaLaunchAttribute attr[1];
+        attr[0].id = cudaLaunchAttributeClusterDimension;
+        attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+        cfg.attrs = attr; cfg.numAttrs = 1;
+        // a persistent grid must be fully resident: not every TPC has both SMs enabled, so ask how many pairs fit
+        static int max_pairs = 0;
+        if (!max_pairs) {
+            cfg.gridDim = dim3(kNumSMs);
+            int n = 0;
+            if (cudaOccupancyMaxActiveClusters(&n, kern, &cfg) != cudaSuccess || n < 1) n = kNumSMs / 4;
+            max_pairs = n < kNumSMs / 2 ? n : kNumSMs / 2;
+            if (getenv("VSW_GEMM_DEBUG")) fprintf(stderr, "[vsw gemm] resident CTA pairs: %d\n", max_pairs);
+        }
+        const int pairs = total < max_pairs ? total : max_pairs;
+        cfg.gridDim = dim3(2 * pairs);
+        cudaError_t e = cudaLaunchKernelEx(&cfg, kern, tmA, tmB, q);
+        if (e != cudaSuccess) { set_error("tc gemm (pair): launch: %s", cudaGetErrorString(e)); return VSW_ERR_CUDA; }
+        return check_launch("tc_gemm_pair");
+    } else {
+        const int grid = total < kNumSMs ? total : kNumSMs;
+        kern<<<grid, NUM_THREADS, SMEM, st>>>(tmA, tmB, q);
+        return check_launch("tc_gemm");
+    }
 }
 
-template <int BN, bool A_MN, bool B_MN>
+// PAIR = CTA-pair (cta_group::2) 256 x 256 tiles; wgrad keeps single-CTA tiles (its column-sum warps need a local barrier)
+template <int BN, bool A_MN, bool B_MN, bool PAIR = false>
 int launch_tc(const CUtensorMap& tmA, const CUtensorMap& tmB, const TcParams& p, cudaStream_t st) {
     if constexpr (A_MN && B_MN) {
         return p.colsum ? launch_tc_epi<BN, true, true, TE_PARTIAL, true>(tmA, tmB, p, st)
                         : launch_tc_epi<BN, true, true, TE_PARTIAL>(tmA, tmB, p, st);
     } else if constexpr (B_MN) {
-        return p.gelu_pre ? launch_tc_epi<BN, false, true, TE_DGRAD_GELU>(tmA, tmB, p, st)
-                          : launch_tc_epi<BN, false, true, TE_DGRAD>(tmA, tmB, p, st);
+        return p.gelu_pre ? launch_tc_epi<BN, false, true, TE_DGRAD_GELU, false, PAIR>(tmA, tmB, p, st)
+                          : launch_tc_epi<BN, false, true, TE_DGRAD, false, PAIR>(tmA, tmB, p, st);
     } else {
         switch (p.epi) {
-            case TE_GELU: return launch_tc_epi<BN, false, false, TE_GELU>(tmA, tmB, p, st);
-            case TE_RESIDUAL: return launch_tc_epi<BN, false, false, TE_RESIDUAL>(tmA, tmB, p, st);
-            default: return launch_tc_epi<BN, false, false, TE_BIAS>(tmA, tmB, p, st);
+            case TE_GELU: return launch_tc_epi<BN, false, false, TE_GELU, false, PAIR>(tmA, tmB, p, st);
+            case TE_RESIDUAL: return launch_tc_epi<BN, false, false, TE_RESIDUAL, false, PAIR>(tmA, tmB, p, st);
+            default: return launch_tc_epi<BN, false, false, TE_BIAS, false, PAIR>(tmA, tmB, p, st);
         }
     }
 }
@@ -547,6 +615,15 @@ static int pick_bn(int M, int N) {
     return tiles256 >= kNumSMs ? 256 : 128;
 }
 
+// CTA-pair tiles when the 256-wide tile is in use, the reduction is long enough for the main loop to matter and there
+// are enough 256 x 256 tiles for the 74 pairs  (VSW_GEMM_PAIR=0 / 1 forces it off / on for experiments)
+static bool use_pair(int M, int N, int K, int BN) {
+    if (BN != 256) return false;
+    static const char* env = getenv("VSW_GEMM_PAIR");
+    if (env) return env[0] == '1';
+    return K >= 256 && (long long)ceil_div(M, 2 * BM) * (N / 256) >= kNumSMs / 2;
+}
+
 // ---------------------------------------------------------------------------------------------
 // forward
 // ---------------------------------------------------------------------------------------------
@@ -559,15 +636,17 @@ int tc_linear(const TcLinearArgs& a, cudaStream_t st) {
     }
     CUtensorMap tmA, tmB;
     const int BN = pick_bn(a.M, a.N);
+    const bool pair = use_pair(a.M, a.N, a.K, BN);
     if (!make_tmap_2d_bf16(&tmA, a.x, a.M, a.K, a.K, BM, BK)) return VSW_ERR_CUDA;
-    if (!make_tmap_2d_bf16(&tmB, a.w, a.N, a.K, a.K, BN, BK)) return VSW_ERR_CUDA;
+    if (!make_tmap_2d_bf16(&tmB, a.w, a.N, a.K, a.K, pair ? BN / 2 : BN, BK)) return VSW_ERR_CUDA;
     TcParams p{};
     p.M = a.M; p.N = a.N; p.K = a.K;
-    p.n_tiles_m = ceil_div(a.M, BM); p.n_tiles_n = ceil_div(a.N, BN); p.splits = 1; p.k_per_split = ceil_div(a.K, BK) * BK;
+    p.n_tiles_m = ceil_div(a.M, pair ? 2 * BM : BM); p.n_tiles_n = ceil_div(a.N, BN); p.splits = 1; p.k_per_split = ceil_div(a.K, BK) * BK;
     p.epi = a.epi == VSW_EPI_BIAS ? TE_BIAS : (a.epi == VSW_EPI_GELU ? TE_GELU : TE_RESIDUAL);
     p.bias = (const __nv_bfloat16*)a.bias; p.out = (__nv_bfloat16*)a.y; p.aux_out = (__nv_bfloat16*)a.aux_out;
     p.res = (const __nv_bfloat16*)a.res; p.rowmap = a.rowmap; p.rowscale = a.rowscale;
     p.rows_per_batch = a.rows_per_batch; p.dst_rows_per_batch = a.dst_rows_per_batch; p.ldc = a.N;
+    if (pair) return launch_tc<256, false, false, true>(tmA, tmB, p, st);
     return BN == 256 ? launch_tc<256, false, false>(tmA, tmB, p, st) : launch_tc<128, false, false>(tmA, tmB, p, st);
 }
 
@@ -597,8 +676,10 @@ int tc_dgrad(const TcDgradArgs& a, cudaStream_t st) {
     TcParams p{};
     p.M = a.M; p.N = a.K; p.K = a.N;
     const int BN = pick_bn(a.M, a.K);
-    p.n_tiles_m = ceil_div(a.M, BM); p.n_tiles_n = ceil_div(a.K, BN); p.splits = 1; p.k_per_split = ceil_div(a.N, BK) * BK;
+    const bool pair = use_pair(a.M, a.K, a.N, BN);
+    p.n_tiles_m = ceil_div(a.M, pair ? 2 * BM : BM); p.n_tiles_n = ceil_div(a.K, BN); p.splits = 1; p.k_per_split = ceil_div(a.N, BK) * BK;
     p.epi = TE_DGRAD; p.out = (__nv_bfloat16*)a.dx; p.gelu_pre = (const __nv_bfloat16*)a.gelu_pre; p.ldc = a.K;
+    if (pair) return launch_tc<256, false, true, true>(tmA, tmB, p, st);
     return BN == 256 ? launch_tc<256, false, true>(tmA, tmB, p, st) : launch_tc<128, false, true>(tmA, tmB, p, st);
 }
 
