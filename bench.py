@@ -129,7 +129,8 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     args = ap.parse_args()
-    assert args.warmup >= 3 or args.impl == "reference", "timing rules: at least 3 warm-up steps"
+    if args.impl != "reference" and args.warmup < 3:
+        args.warmup = 3   # timing rules: at least 3 warm-up steps (the JSON line reports the value actually used)
 
     rank = int(os.environ.get("RANK", 0))
     world = int(os.environ.get("WORLD_SIZE", 1))
@@ -242,7 +243,8 @@ def main():
         e2e_step()
         ms_e2e = timed(e2e_step, args.steps) / args.steps
         e2e = {"value": world * B / (ms_e2e / 1e3), "unit": "clips/s", "ms_per_step": ms_e2e,
-               "h2d_bytes_per_step": x_host.numel() * x_host.element_size(), "d2h_bytes_per_step": 4}
+               "h2d_bytes_per_step": world * x_host.numel() * x_host.element_size(), "d2h_bytes_per_step": 4 * world,
+               "h2d_bytes_per_step_per_gpu": x_host.numel() * x_host.element_size()}
 
     # ---- roofline of the dominant kernel family: per-launch CUDA events on the launching stream
     roofline, families = None, None
@@ -297,7 +299,7 @@ def main():
             "metric": "Video-Swin-B fwd+bwd clips/sec", "value": value, "unit": "clips/s", "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
-            "config": {"workload": workload, "model": args.model, "clips_per_gpu": B, "global_batch": world * B,
+            "config": {"workload": workload, "variant": args.model, "clips_per_gpu": B, "global_batch": world * B,
                        "parallelism": f"dp{world}", "gemm_backend": args.backend, "l2": l2_note,
                        "optimizer": "excluded (metric is encoder fwd+bwd, SURVEY 8d)"},
             "clocks": sampler.result(), "e2e": e2e, "gpu_launches": int(launches),

@@ -695,13 +695,26 @@ static void tc_wgrad_split(int M, int N, int K, int* splits, int* m_per_split) {
     const long long cap = (4LL * kNumSMs + tiles - 1) / tiles;
     if (smax > cap) smax = cap;
     if (smax < 1) smax = 1;
-    long long best = 1; double best_eff = -1.0;
-    for (long long s = 1; s <= smax; ++s) {
+    // efficiency of the persistent grid = items / (waves x SMs).  Among the split counts within 1.5 % of the best efficiency
+    // take the SMALLEST one that still gives every CTA two items (so one epilogue overlaps a main loop): the fp32 partials
+    // written by the epilogue and re-read by the reduce kernel grow linearly with the split count.
+    auto eff = [&](long long s) {
         const long long items = tiles * s;
         const long long waves = (items + kNumSMs - 1) / kNumSMs;
-        // efficiency of the last wave, slightly favouring more (shorter) items for balance
-        const double eff = (double)items / (double)(waves * kNumSMs) + 1e-3 * (double)s / (double)smax;
-        if (eff > best_eff) { best_eff = eff; best = s; }
+        return (double)items / (double)(waves * kNumSMs);
+    };
+    double best_eff = -1.0;
+    for (long long s = 1; s <= smax; ++s) best_eff = eff(s) > best_eff ? eff(s) : best_eff;
+    long long best = smax;
+    for (long long s = 1; s <= smax; ++s) {
+        if (eff(s) < best_eff - 0.015) continue;
+        if (tiles * s < 2LL * kNumSMs - kNumSMs / 8 && s < smax) continue;   // fewer than ~2 waves
+        best = s;
+        break;
+    }
+    if (getenv("VSW_WGRAD_MAXSPLIT")) {   // experiment: previous heuristic (largest split count among the best)
+        best = 1; double be = -1.0;
+        for (long long s = 1; s <= smax; ++s) { const double e = eff(s) + 1e-3 * (double)s / (double)smax; if (e > be) { be = e; best = s; } }
     }
     int mps = (int)((M + best - 1) / best);
     mps = (mps + BK - 1) / BK * BK;

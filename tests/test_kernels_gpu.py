@@ -209,6 +209,45 @@ def test_window_attention_fwd_bwd(vsw, oracle, dtype, geom, backend):
     assert rel_l2(dtab, tr.grad) < TOL[dtype] * (1 if dtype == torch.float32 else 1.5)
 
 
+@pytest.mark.parametrize("dtype", DTYPES)
+@pytest.mark.parametrize("backend", [0, 1])
+def test_window_attention_swin_l_384_window(vsw, oracle, dtype, backend):
+    """Window 8x12x12 (N = 1152, Swin-L 384, BASELINE configs 3/4): beyond the tcgen05 kernels' N <= 448, so AUTO must fall
+    back to the CUDA-core kernels (and a forced tcgen05 back end must refuse loudly)."""
+    VF, L = vsw.functional, vsw._lib
+    grid, window, shift, nH, hd, B = (8, 24, 24), (8, 12, 12), (0, 6, 6), 2, 32, 1
+    plan = VF.window_plan(grid, window, shift, "cuda")
+    nW, N = plan.nW, plan.N
+    assert N == 1152 and plan.shifted
+    B_ = B * nW
+    torch.manual_seed(5)
+    qkv = rnd(B_, N, 3, nH, hd, dtype=dtype)
+    Lt = 15 * 23 * 23
+    table = rnd(Lt, nH, dtype=dtype, scale=0.5)
+    rel_index = torch.from_numpy(oracle.relative_position_index(window)).cuda()
+    rowcode, colcode = VF.bias_codes(rel_index, N)
+    mask = vsw.compute_mask(*plan.pgrid, plan.ws, plan.ss, "cuda")
+    qr = qkv.double().requires_grad_(True)
+    tr = table.double().requires_grad_(True)
+    oref, lref = attn_reference(qr, tr, rel_index, mask, nW, nH, hd ** -0.5)
+    L.set_gemm_backend(backend)
+    try:
+        out, lse = VF.attn_fwd(qkv.view(B_ * N, -1), table, rowcode, colcode, plan.region, None, B_, nW, N, nH, hd, hd ** -0.5)
+        assert rel_l2(out.view(B_, N, -1), oref) < TOL[dtype]
+        dout = rnd(B_, N, nH * hd, dtype=dtype)
+        oref.backward(dout.double())
+        dqkv, dtab = VF.attn_bwd(qkv.view(B_ * N, -1), out, dout.view(B_ * N, -1), lse, table, rowcode, colcode, plan.region,
+                                 None, B_, nW, N, nH, hd, hd ** -0.5)
+        assert rel_l2(dqkv.view(B_, N, 3, nH, hd), qr.grad) < TOL[dtype] * (1 if dtype == torch.float32 else 1.5)
+        assert rel_l2(dtab, tr.grad) < TOL[dtype] * (1 if dtype == torch.float32 else 1.5)
+        if dtype == torch.bfloat16:
+            L.set_gemm_backend(L.GEMM_TCGEN05)
+            with pytest.raises(L.VswError):
+                VF.attn_fwd(qkv.view(B_ * N, -1), table, rowcode, colcode, plan.region, None, B_, nW, N, nH, hd, hd ** -0.5)
+    finally:
+        L.set_gemm_backend(0)
+
+
 # ---------------------------------------------------------------------------------------------
 @pytest.mark.parametrize("dtype", DTYPES)
 @pytest.mark.parametrize("shape", [(2, 3, 8, 32, 32), (1, 3, 4, 30, 27), (2, 3, 3, 8, 8)])
