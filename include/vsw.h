@@ -52,9 +52,12 @@ typedef enum {
 typedef enum {
     VSW_EPI_BIAS = 0,       /* y = acc + bias                                        (qkv, fc-like)          */
     VSW_EPI_GELU = 1,       /* y = gelu_erf(acc + bias); optional pre-activation out  [video_swin.py:76-77]   */
-    VSW_EPI_RESIDUAL = 2    /* y[dst] = res[dst] + rowscale[b] * (acc + bias), dst via optional row map
+    VSW_EPI_RESIDUAL = 2,   /* y[dst] = res[dst] + rowscale[b] * (acc + bias), dst via optional row map
                                [proj + window_reverse + roll back + residual, video_swin.py:170,233-241,256;
                                 fc2 + residual, video_swin.py:261]                                            */
+    VSW_EPI_GELU_GRAD = 3   /* y = gelu_erf(acc + bias) and aux_out = gelu_erf'(acc + bias): the training form of the
+                               fc1 epilogue -- the backward then needs one multiply per element
+                               (vsw_linear_dgrad_mul) instead of re-evaluating the GELU derivative             */
 } vsw_epilogue;
 
 /* GEMM back ends (vsw_set_gemm_backend): the CUDA-core fp32 kernel is the only one for VSW_F32. */
@@ -134,6 +137,7 @@ int vsw_merge_ln_bwd(const void* dy, const void* x, const void* gamma, const flo
 
 /* y = epilogue(x[M,K] w[N,K]^T + bias[N]).
  *   VSW_EPI_GELU:     aux_out (M,N) receives the pre-activation when non-NULL.
+ *   VSW_EPI_GELU_GRAD: aux_out (M,N), required, receives gelu'(pre-activation).
  *   VSW_EPI_RESIDUAL: rows are grouped in batches of rows_per_batch; source row m = b*rows_per_batch + r
  *                     is written to destination row b*dst_rows_per_batch + (rowmap ? rowmap[r] : r),
  *                     skipped when rowmap[r] < 0;  y[dst] = res[dst] + (rowscale ? rowscale[b] : 1) * (acc+bias).
@@ -156,6 +160,14 @@ int vsw_linear_dgrad(const void* dy, const void* w, void* dx,
                      const int32_t* a_rowmap, const float* a_rowscale, int rows_per_batch, int src_rows_per_batch,
                      void* a_out, const void* gelu_pre,
                      int dtype, void* stream);
+
+/* Same as vsw_linear_dgrad with a plain elementwise factor:  dx = (A w) (*) mul[M,K]   (mul = the gelu' tensor written by
+ * VSW_EPI_GELU_GRAD; autograd of fc2 followed by the GELU, video_swin.py:76-79). */
+int vsw_linear_dgrad_mul(const void* dy, const void* w, void* dx,
+                         int M, int N, int K,
+                         const int32_t* a_rowmap, const float* a_rowscale, int rows_per_batch, int src_rows_per_batch,
+                         void* a_out, const void* mul,
+                         int dtype, void* stream);
 
 /* dw[N,K] = dy[M,N]^T x[M,K]; db[N] = sum_m dy[m,:] (db may be NULL).  Split over M with an fp32
  * workspace (vsw_linear_wgrad_workspace bytes) and a fixed-order second pass.  dw/db are written in

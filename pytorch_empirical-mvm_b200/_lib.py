@@ -15,7 +15,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libvsw_b200.so")
 
 VSW_F32, VSW_BF16, VSW_F16 = 0, 1, 2
-EPI_BIAS, EPI_GELU, EPI_RESIDUAL = 0, 1, 2
+EPI_BIAS, EPI_GELU, EPI_RESIDUAL, EPI_GELU_GRAD = 0, 1, 2, 3
 GEMM_AUTO, GEMM_SIMT, GEMM_TCGEN05 = 0, 1, 2
 
 _DTYPES = {torch.float32: VSW_F32, torch.bfloat16: VSW_BF16, torch.float16: VSW_F16}
@@ -40,6 +40,7 @@ SIGNATURES = {
     "vsw_merge_ln_bwd": (_i, [_vp] * 9 + [_i] * 5 + [_vp, _sz, _vp]),
     "vsw_linear_fwd": (_i, [_vp] * 4 + [_i] * 4 + [_vp] * 4 + [_i, _i, _i, _vp]),
     "vsw_linear_dgrad": (_i, [_vp] * 3 + [_i] * 3 + [_vp, _vp, _i, _i, _vp, _vp, _i, _vp]),
+    "vsw_linear_dgrad_mul": (_i, [_vp] * 3 + [_i] * 3 + [_vp, _vp, _i, _i, _vp, _vp, _i, _vp]),
     "vsw_linear_wgrad_workspace": (_sz, [_i, _i, _i]),
     "vsw_linear_wgrad": (_i, [_vp] * 4 + [_i] * 5 + [_vp, _sz, _vp]),
     "vsw_window_attn_fwd": (_i, [_vp] * 8 + [_i] * 6 + [_f, _i, _vp]),

@@ -107,12 +107,15 @@ __global__ void __launch_bounds__(256) simt_gemm_kernel(SimtGemmParams p) {
             if (p.bias) v += to_f<T>(((const T*)p.bias)[n]);
             const long long o = drow * p.ldc + n;
             if (p.epi == SE_GELU) {
-                if (p.aux_out) ((T*)p.aux_out)[o] = from_f<T>(v);
+                if (p.aux_out) ((T*)p.aux_out)[o] = from_f<T>(p.aux_is_grad ? gelu_grad_f(v) : v);
                 v = gelu_f(v);
             } else if (p.epi == SE_RESIDUAL) {
                 v = to_f<T>(((const T*)p.res)[o]) + rsc * v;
             } else if (p.epi == SE_DGRAD) {
-                if (p.gelu_pre) v *= gelu_grad_f(to_f<T>(((const T*)p.gelu_pre)[o]));
+                if (p.gelu_pre) {
+                    const float u = to_f<T>(((const T*)p.gelu_pre)[o]);
+                    v *= p.aux_is_grad ? u : gelu_grad_f(u);
+                }
             }
             ((T*)p.C)[o] = from_f<T>(v);
         }

@@ -18,6 +18,7 @@ struct SimtGemmParams {
     // epilogue
     int epi; const void* bias; void* aux_out; const void* res; const int32_t* rowmap; const float* rowscale;
     int dst_rows_per_batch; const void* gelu_pre;
+    int aux_is_grad;   // SE_GELU: aux_out receives gelu'(pre); SE_DGRAD: gelu_pre already holds gelu'(pre)
     // split-K (wgrad)
     int ksplit; int k_per_split; float* partial;
 };

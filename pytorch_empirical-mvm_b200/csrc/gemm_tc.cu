@@ -103,7 +103,7 @@ constexpr int A_BYTES = BM * BK * 2;  // 16 KB
 constexpr int NUM_EPI_WARPS = 16;   // 4 per TMEM lane quadrant: the fused epilogues are latency/MUFU bound, not issue bound
 constexpr int NUM_THREADS = 64 + NUM_EPI_WARPS * 32;
 
-enum TcEpi { TE_BIAS = 0, TE_GELU = 1, TE_RESIDUAL = 2, TE_DGRAD = 3, TE_PARTIAL = 4, TE_DGRAD_GELU = 5 };
+enum TcEpi { TE_BIAS = 0, TE_GELU = 1, TE_RESIDUAL = 2, TE_DGRAD = 3, TE_PARTIAL = 4, TE_DGRAD_GELU = 5, TE_GELU_GRAD = 6, TE_DGRAD_MUL = 7 };
 
 struct TcParams {
     int M, N, K;                 // output M x N, reduction length K
@@ -141,8 +141,23 @@ __device__ __forceinline__ float gelu_grad_fast(float x) {
     return fmaf(w, du, fmaf(0.5f, t, 0.5f));
 }
 
+// y = GELU(x) and g = GELU'(x) from one tanh (training-form fc1 epilogue)
+__device__ __forceinline__ void gelu_both_fast(float x, float& y, float& g) {
+    const float s = fminf(x * x, 64.0f);
+    const float t = tanh_approx(x * fmaf(fmaf(GELU_C, s, GELU_B), s, GELU_A));
+    const float du = fmaf(fmaf(5.0f * GELU_C, s, 3.0f * GELU_B), s, GELU_A);
+    const float phi = fmaf(0.5f, t, 0.5f);
+    const float w = fmaf(-t, t, 1.0f) * (0.5f * x);
+    y = x * phi;
+    g = fmaf(w, du, phi);
+}
+
 __device__ __forceinline__ void ld8(const __nv_bfloat16* p, float (&o)[8]) {
     const uint4 u = __ldg(reinterpret_cast<const uint4*>(p));
+    float2 a = tc::unpack_bf16(u.x), b = tc::unpack_bf16(u.y), c = tc::unpack_bf16(u.z), d = tc::unpack_bf16(u.w);
+    o[0] = a.x; o[1] = a.y; o[2] = b.x; o[3] = b.y; o[4] = c.x; o[5] = c.y; o[6] = d.x; o[7] = d.y;
+}
+__device__ __forceinline__ void unpack8(const uint4& u, float (&o)[8]) {
     float2 a = tc::unpack_bf16(u.x), b = tc::unpack_bf16(u.y), c = tc::unpack_bf16(u.z), d = tc::unpack_bf16(u.w);
     o[0] = a.x; o[1] = a.y; o[2] = b.x; o[3] = b.y; o[4] = c.x; o[5] = c.y; o[6] = d.x; o[7] = d.y;
 }
@@ -387,9 +402,35 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 __syncwarp();
                 long long c_a = clock64();
                 tc::tmem_ld_32x32(tmem_base + acc * BN + c * 32 + ((uint32_t)(q * 32) << 16), r32);
+                const int col0 = n0 + c * 32;
+                // Side tensor of the epilogue (residual / GELU' / pre-activation), same (row, column) footprint as the output:
+                // loaded COALESCED (4 lanes per 64-byte row segment, rows via the owning lanes' registers) into the warp's
+                // staging buffer while the TMEM load is in flight, then re-read in the thread-per-row layout.
+                constexpr bool HAS_SIDE = (EPI == TE_RESIDUAL || EPI == TE_DGRAD_MUL || EPI == TE_DGRAD_GELU);
+                uint4 side[HAS_SIDE ? 4 : 1];
+                if constexpr (HAS_SIDE) {
+                    const __nv_bfloat16* sp = (EPI == TE_RESIDUAL) ? p.res : p.gelu_pre;
+                    const int unit = lane & 3;
+                    const int colu = col0 + unit * 8;
+                    uint4 ld[4];
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) {
+                        const int rl = k * 8 + (lane >> 2);
+                        const long long dr = __shfl_sync(0xffffffffu, drow, rl);
+                        const int okr = __shfl_sync(0xffffffffu, (int)row_ok, rl);
+                        ld[k] = (okr && colu < p.N) ? __ldg(reinterpret_cast<const uint4*>(sp + dr * p.ldc + colu)) : make_uint4(0, 0, 0, 0);
+                    }
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) {
+                        const int rl = k * 8 + (lane >> 2);
+                        tc::sts_u4(stg + rl * 64 + ((unit ^ ((rl >> 1) & 3)) << 4), ld[k]);
+                    }
+                    __syncwarp();
+#pragma unroll
+                    for (int g = 0; g < 4; ++g) side[g] = tc::lds_u4(stg + lane * 64 + ((g ^ ((lane >> 1) & 3)) << 4));
+                }
                 tc::tmem_ld_wait();
                 long long c_b = clock64();
-                const int col0 = n0 + c * 32;
                 if constexpr (EPI == TE_PARTIAL) {
                     if (row_ok) {
 #pragma unroll
@@ -427,17 +468,22 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                             }
 #pragma unroll
                             for (int e = 0; e < 8; ++e) v[e] = gelu_fast(v[e]);
-                        } else if constexpr (EPI == TE_RESIDUAL) {
-                            if (row_ok) {
-                                float rr[8];
-                                ld8(p.res + drow * p.ldc + col, rr);
+                        } else if constexpr (EPI == TE_GELU_GRAD) {
+                            float gd[8];
 #pragma unroll
-                                for (int e = 0; e < 8; ++e) v[e] = fmaf(rsc, v[e], rr[e]);
-                            }
-                        } else if constexpr (EPI == TE_DGRAD_GELU) {
-                            if (row_ok) {
-                                float u[8];
-                                ld8(p.gelu_pre + drow * p.ldc + col, u);
+                            for (int e = 0; e < 8; ++e) gelu_both_fast(v[e], v[e], gd[e]);
+#pragma unroll
+                            for (int e = 0; e < 4; ++e) packed_aux[g * 4 + e] = tc::pack_bf16(gd[2 * e], gd[2 * e + 1]);
+                        } else if constexpr (HAS_SIDE) {
+                            float u[8];
+                            unpack8(side[g], u);
+                            if constexpr (EPI == TE_DGRAD_MUL) {
+#pragma unroll
+                                for (int e = 0; e < 8; ++e) v[e] *= u[e];
+                            } else if constexpr (EPI == TE_RESIDUAL) {
+#pragma unroll
+                                for (int e = 0; e < 8; ++e) v[e] = fmaf(rsc, v[e], u[e]);
+                            } else {
 #pragma unroll
                                 for (int e = 0; e < 8; ++e) v[e] *= gelu_grad_fast(u[e]);
                             }
@@ -448,7 +494,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 }
                 long long c_c = clock64();
                 // ---- transposed, coalesced stores (one or two outputs)
-                const int npass = (EPI == TE_GELU && p.aux_out) ? 2 : 1;
+                const int npass = ((EPI == TE_GELU && p.aux_out) || EPI == TE_GELU_GRAD) ? 2 : 1;
                 for (int pass = 0; pass < npass; ++pass) {
                     const uint32_t* src = (npass == 2 && pass == 0) ? packed_aux : packed;
                     __nv_bfloat16* outp = (npass == 2 && pass == 0) ? p.aux_out : p.out;
@@ -591,11 +637,13 @@ int launch_tc(const CUtensorMap& tmA, const CUtensorMap& tmB, const TcParams& p,
         return p.colsum ? launch_tc_epi<BN, true, true, TE_PARTIAL, true>(tmA, tmB, p, st)
                         : launch_tc_epi<BN, true, true, TE_PARTIAL>(tmA, tmB, p, st);
     } else if constexpr (B_MN) {
+        if (p.gelu_pre && p.epi == TE_DGRAD_MUL) return launch_tc_epi<BN, false, true, TE_DGRAD_MUL, false, PAIR>(tmA, tmB, p, st);
         return p.gelu_pre ? launch_tc_epi<BN, false, true, TE_DGRAD_GELU, false, PAIR>(tmA, tmB, p, st)
                           : launch_tc_epi<BN, false, true, TE_DGRAD, false, PAIR>(tmA, tmB, p, st);
     } else {
         switch (p.epi) {
             case TE_GELU: return launch_tc_epi<BN, false, false, TE_GELU, false, PAIR>(tmA, tmB, p, st);
+            case TE_GELU_GRAD: return launch_tc_epi<BN, false, false, TE_GELU_GRAD, false, PAIR>(tmA, tmB, p, st);
             case TE_RESIDUAL: return launch_tc_epi<BN, false, false, TE_RESIDUAL, false, PAIR>(tmA, tmB, p, st);
             default: return launch_tc_epi<BN, false, false, TE_BIAS, false, PAIR>(tmA, tmB, p, st);
         }
@@ -642,7 +690,7 @@ int tc_linear(const TcLinearArgs& a, cudaStream_t st) {
     TcParams p{};
     p.M = a.M; p.N = a.N; p.K = a.K;
     p.n_tiles_m = ceil_div(a.M, pair ? 2 * BM : BM); p.n_tiles_n = ceil_div(a.N, BN); p.splits = 1; p.k_per_split = ceil_div(a.K, BK) * BK;
-    p.epi = a.epi == VSW_EPI_BIAS ? TE_BIAS : (a.epi == VSW_EPI_GELU ? TE_GELU : TE_RESIDUAL);
+    p.epi = a.epi == VSW_EPI_BIAS ? TE_BIAS : (a.epi == VSW_EPI_GELU ? TE_GELU : (a.epi == VSW_EPI_GELU_GRAD ? TE_GELU_GRAD : TE_RESIDUAL));
     p.bias = (const __nv_bfloat16*)a.bias; p.out = (__nv_bfloat16*)a.y; p.aux_out = (__nv_bfloat16*)a.aux_out;
     p.res = (const __nv_bfloat16*)a.res; p.rowmap = a.rowmap; p.rowscale = a.rowscale;
     p.rows_per_batch = a.rows_per_batch; p.dst_rows_per_batch = a.dst_rows_per_batch; p.ldc = a.N;
@@ -678,7 +726,8 @@ int tc_dgrad(const TcDgradArgs& a, cudaStream_t st) {
     const int BN = pick_bn(a.M, a.K);
     const bool pair = use_pair(a.M, a.K, a.N, BN);
     p.n_tiles_m = ceil_div(a.M, pair ? 2 * BM : BM); p.n_tiles_n = ceil_div(a.K, BN); p.splits = 1; p.k_per_split = ceil_div(a.N, BK) * BK;
-    p.epi = TE_DGRAD; p.out = (__nv_bfloat16*)a.dx; p.gelu_pre = (const __nv_bfloat16*)a.gelu_pre; p.ldc = a.K;
+    p.epi = (a.gelu_pre && a.pre_is_grad) ? TE_DGRAD_MUL : TE_DGRAD;
+    p.out = (__nv_bfloat16*)a.dx; p.gelu_pre = (const __nv_bfloat16*)a.gelu_pre; p.ldc = a.K;
     if (pair) return launch_tc<256, false, true, true>(tmA, tmB, p, st);
     return BN == 256 ? launch_tc<256, false, true>(tmA, tmB, p, st) : launch_tc<128, false, true>(tmA, tmB, p, st);
 }

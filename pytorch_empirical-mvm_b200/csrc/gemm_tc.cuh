@@ -17,6 +17,7 @@ struct TcDgradArgs {
     int M, N, K;
     const int32_t* a_rowmap; const float* a_rowscale; int rows_per_batch, src_rows_per_batch;
     void* a_out; const void* gelu_pre;
+    bool pre_is_grad;   // gelu_pre already holds gelu'(pre-activation): the epilogue is a plain multiply
 };
 
 // All return VSW_ERR_UNSUPPORTED (without launching anything) for shapes outside the tiling.

@@ -22,7 +22,8 @@ extern "C" int vsw_linear_fwd(const void* x, const void* w, const void* bias, vo
                               const float* rowscale, int rows_per_batch, int dst_rows_per_batch, int dtype,
                               void* stream) {
     VSW_REQUIRE(x && w && y && M > 0 && N > 0 && K > 0, VSW_ERR_ARG, "vsw_linear_fwd: bad args");
-    VSW_REQUIRE(epilogue >= VSW_EPI_BIAS && epilogue <= VSW_EPI_RESIDUAL, VSW_ERR_ARG, "vsw_linear_fwd: bad epilogue");
+    VSW_REQUIRE(epilogue >= VSW_EPI_BIAS && epilogue <= VSW_EPI_GELU_GRAD, VSW_ERR_ARG, "vsw_linear_fwd: bad epilogue");
+    VSW_REQUIRE(epilogue != VSW_EPI_GELU_GRAD || aux_out, VSW_ERR_ARG, "vsw_linear_fwd: VSW_EPI_GELU_GRAD needs aux_out");
     if (epilogue == VSW_EPI_RESIDUAL) {
         VSW_REQUIRE(res, VSW_ERR_ARG, "vsw_linear_fwd: residual epilogue needs res");
         if (rows_per_batch <= 0) { rows_per_batch = M; dst_rows_per_batch = M; }
@@ -42,15 +43,16 @@ extern "C" int vsw_linear_fwd(const void* x, const void* w, const void* bias, vo
     SimtGemmParams p{};
     p.A = x; p.B = w; p.C = y; p.M = M; p.N = N; p.K = K;
     p.sam = K; p.sak = 1; p.sbn = K; p.sbk = 1; p.ldc = N;
-    p.epi = epilogue == VSW_EPI_BIAS ? SE_BIAS : (epilogue == VSW_EPI_GELU ? SE_GELU : SE_RESIDUAL);
+    p.epi = epilogue == VSW_EPI_BIAS ? SE_BIAS : (epilogue == VSW_EPI_RESIDUAL ? SE_RESIDUAL : SE_GELU);
+    p.aux_is_grad = epilogue == VSW_EPI_GELU_GRAD;
     p.bias = bias; p.aux_out = aux_out; p.res = res; p.rowmap = rowmap; p.rowscale = rowscale;
     p.rows_per_batch = rows_per_batch; p.dst_rows_per_batch = dst_rows_per_batch;
     return launch_simt_gemm(p, true, true, dtype, st);
 }
 
-extern "C" int vsw_linear_dgrad(const void* dy, const void* w, void* dx, int M, int N, int K, const int32_t* a_rowmap,
-                                const float* a_rowscale, int rows_per_batch, int src_rows_per_batch, void* a_out,
-                                const void* gelu_pre, int dtype, void* stream) {
+static int linear_dgrad_impl(const void* dy, const void* w, void* dx, int M, int N, int K, const int32_t* a_rowmap,
+                             const float* a_rowscale, int rows_per_batch, int src_rows_per_batch, void* a_out,
+                             const void* gelu_pre, bool pre_is_grad, int dtype, void* stream) {
     VSW_REQUIRE(dy && w && dx && M > 0 && N > 0 && K > 0, VSW_ERR_ARG, "vsw_linear_dgrad: bad args");
     if (a_rowmap || a_rowscale) {
         VSW_REQUIRE(rows_per_batch > 0 && M % rows_per_batch == 0 && src_rows_per_batch > 0, VSW_ERR_ARG,
@@ -61,7 +63,7 @@ extern "C" int vsw_linear_dgrad(const void* dy, const void* w, void* dx, int M, 
         TcDgradArgs a{};
         a.dy = dy; a.w = w; a.dx = dx; a.M = M; a.N = N; a.K = K; a.a_rowmap = a_rowmap; a.a_rowscale = a_rowscale;
         a.rows_per_batch = rows_per_batch; a.src_rows_per_batch = src_rows_per_batch; a.a_out = a_out;
-        a.gelu_pre = gelu_pre;
+        a.gelu_pre = gelu_pre; a.pre_is_grad = pre_is_grad;
         int rc = tc_dgrad(a, st);
         if (rc != VSW_ERR_UNSUPPORTED || backend() == VSW_GEMM_TCGEN05) return rc;
     }
@@ -71,8 +73,23 @@ extern "C" int vsw_linear_dgrad(const void* dy, const void* w, void* dx, int M, 
     p.sam = N; p.sak = 1; p.sbn = 1; p.sbk = K; p.ldc = K;
     p.a_rowmap = a_rowmap; p.a_rowscale = a_rowscale; p.rows_per_batch = rows_per_batch;
     p.src_rows_per_batch = src_rows_per_batch; p.a_out = a_out;
-    p.epi = SE_DGRAD; p.gelu_pre = gelu_pre;
+    p.epi = SE_DGRAD; p.gelu_pre = gelu_pre; p.aux_is_grad = pre_is_grad ? 1 : 0;
     return launch_simt_gemm(p, true, false, dtype, st);
+}
+
+extern "C" int vsw_linear_dgrad(const void* dy, const void* w, void* dx, int M, int N, int K, const int32_t* a_rowmap,
+                                const float* a_rowscale, int rows_per_batch, int src_rows_per_batch, void* a_out,
+                                const void* gelu_pre, int dtype, void* stream) {
+    return linear_dgrad_impl(dy, w, dx, M, N, K, a_rowmap, a_rowscale, rows_per_batch, src_rows_per_batch, a_out, gelu_pre,
+                             false, dtype, stream);
+}
+
+extern "C" int vsw_linear_dgrad_mul(const void* dy, const void* w, void* dx, int M, int N, int K, const int32_t* a_rowmap,
+                                    const float* a_rowscale, int rows_per_batch, int src_rows_per_batch, void* a_out,
+                                    const void* mul, int dtype, void* stream) {
+    VSW_REQUIRE(mul, VSW_ERR_ARG, "vsw_linear_dgrad_mul: mul is required");
+    return linear_dgrad_impl(dy, w, dx, M, N, K, a_rowmap, a_rowscale, rows_per_batch, src_rows_per_batch, a_out, mul, true,
+                             dtype, stream);
 }
 
 static void wgrad_split(int M, int N, int K, int* splits, int* m_per_split) {

@@ -195,15 +195,21 @@ def linear_fwd(x2d, w, bias, M, N, K, epi=L.EPI_BIAS, out=None, aux_out=None, re
 
 
 def linear_dgrad(dy, w, M, N, K, a_rowmap=None, a_rowscale=None, rows_per_batch=0, src_rows_per_batch=0, a_out=None,
-                 gelu_pre=None):
+                 gelu_pre=None, mul=None):
+    """dx = (A w) [* gelu'(gelu_pre) | * mul];  `mul` is the gelu' tensor written by the EPI_GELU_GRAD forward epilogue."""
     dx = _empty((M, K), dy.dtype, dy.device)
     t0 = PROFILER.begin() if PROFILER is not None else None
-    L.check(L.lib().vsw_linear_dgrad(L.ptr(dy), L.ptr(w), L.ptr(dx), M, N, K, L.ptr(a_rowmap), L.ptr(a_rowscale),
-                                     rows_per_batch, src_rows_per_batch, L.ptr(a_out), L.ptr(gelu_pre), L.dt(dy),
-                                     L.stream()), "vsw_linear_dgrad")
+    if mul is not None:
+        L.check(L.lib().vsw_linear_dgrad_mul(L.ptr(dy), L.ptr(w), L.ptr(dx), M, N, K, L.ptr(a_rowmap), L.ptr(a_rowscale),
+                                             rows_per_batch, src_rows_per_batch, L.ptr(a_out), L.ptr(mul), L.dt(dy),
+                                             L.stream()), "vsw_linear_dgrad_mul")
+    else:
+        L.check(L.lib().vsw_linear_dgrad(L.ptr(dy), L.ptr(w), L.ptr(dx), M, N, K, L.ptr(a_rowmap), L.ptr(a_rowscale),
+                                         rows_per_batch, src_rows_per_batch, L.ptr(a_out), L.ptr(gelu_pre), L.dt(dy),
+                                         L.stream()), "vsw_linear_dgrad")
     if t0 is not None:
         e = _esz(dy)
-        nb = (M * N * (1 + (a_out is not None)) + N * K + M * K * (1 + (gelu_pre is not None))) * e
+        nb = (M * N * (1 + (a_out is not None)) + N * K + M * K * (1 + (gelu_pre is not None or mul is not None))) * e
         PROFILER.end("linear_dgrad", t0, 2.0 * M * N * K, nb)
     return dx
 
@@ -325,8 +331,8 @@ class _MlpBranch(torch.autograd.Function):
         x = _c(x)
         n2, mean, rstd = ln_fwd(x, g2, b2, None, B, T, T, C)
         need_grad = any(ctx.needs_input_grad)
-        u = _empty((M, Hd), x.dtype, x.device) if need_grad else None
-        g = linear_fwd(n2.view(M, C), w1, bb1, M, Hd, C, epi=L.EPI_GELU, aux_out=u)
+        u = _empty((M, Hd), x.dtype, x.device) if need_grad else None   # gelu'(fc1 pre-activation), consumed by the backward
+        g = linear_fwd(n2.view(M, C), w1, bb1, M, Hd, C, epi=L.EPI_GELU_GRAD if need_grad else L.EPI_GELU, aux_out=u)
         out = linear_fwd(g, w2, bb2, M, C, Hd, epi=L.EPI_RESIDUAL, res=x, rowscale=rowscale, rows_per_batch=T,
                          dst_rows_per_batch=T).view(B, T, C)
         if need_grad:
@@ -342,7 +348,7 @@ class _MlpBranch(torch.autograd.Function):
         dout = _c(dout)
         a_buf = _empty((M, C), x.dtype, x.device) if rowscale is not None else None
         du = linear_dgrad(dout.view(M, C), w2, M, C, Hd, a_rowscale=rowscale, rows_per_batch=T, src_rows_per_batch=T,
-                          a_out=a_buf, gelu_pre=u)
+                          a_out=a_buf, mul=u)
         dw2, db2 = linear_wgrad(a_buf if a_buf is not None else dout.view(M, C), g, M, C, Hd)
         del a_buf
         dn2 = linear_dgrad(du, w1, M, Hd, C)
@@ -394,8 +400,8 @@ class _Mlp(torch.autograd.Function):
         M, C = x2d.shape
         Hd, Co = w1.shape[0], w2.shape[0]
         x2d = _c(x2d)
-        u = _empty((M, Hd), x2d.dtype, x2d.device)
-        g = linear_fwd(x2d, w1, b1, M, Hd, C, epi=L.EPI_GELU, aux_out=u)
+        u = _empty((M, Hd), x2d.dtype, x2d.device)   # gelu'(fc1 pre-activation)
+        g = linear_fwd(x2d, w1, b1, M, Hd, C, epi=L.EPI_GELU_GRAD, aux_out=u)
         y = linear_fwd(g, w2, b2, M, Co, Hd)
         ctx.save_for_backward(x2d, w1, w2, u, g)
         ctx.has_bias = (b1 is not None, b2 is not None)
@@ -407,7 +413,7 @@ class _Mlp(torch.autograd.Function):
         M, C = x2d.shape
         Hd, Co = w1.shape[0], w2.shape[0]
         dy = _c(dy)
-        du = linear_dgrad(dy, w2, M, Co, Hd, gelu_pre=u)
+        du = linear_dgrad(dy, w2, M, Co, Hd, mul=u)
         dw2, db2 = linear_wgrad(dy, g, M, Co, Hd, need_bias=ctx.has_bias[1])
         dx = linear_dgrad(du, w1, M, Hd, C)
         dw1, db1 = linear_wgrad(du, x2d, M, Hd, C, need_bias=ctx.has_bias[0])

@@ -73,12 +73,17 @@ def linear_case(M, N, K, iters):
     u = torch.empty(M, N, device="cuda", dtype=torch.bfloat16)
     t_f = timeit(lambda: VF.linear_fwd(x, w, b, M, N, K), iters)
     t_g = timeit(lambda: VF.linear_fwd(x, w, b, M, N, K, epi=L.EPI_GELU, aux_out=u), iters)
+    t_gg = timeit(lambda: VF.linear_fwd(x, w, b, M, N, K, epi=L.EPI_GELU_GRAD, aux_out=u), iters)
+    pre = torch.randn(M, K, device="cuda").bfloat16()
+    t_dg = timeit(lambda: VF.linear_dgrad(dy, w, M, N, K, gelu_pre=pre), iters)
+    t_dm = timeit(lambda: VF.linear_dgrad(dy, w, M, N, K, mul=pre), iters)
     t_d = timeit(lambda: VF.linear_dgrad(dy, w, M, N, K), iters)
     t_w = timeit(lambda: VF.linear_wgrad(dy, x, M, N, K), iters)
     t_ref = timeit(lambda: torch.matmul(x, w.t()), iters)
     fl = 2.0 * M * N * K
     by = 2.0 * (M * K + N * K + M * N)
-    return dict(kernel="linear", M=M, N=N, K=K, fwd_ms=t_f, gelu_ms=t_g, dgrad_ms=t_d, wgrad_ms=t_w, cublas_ms=t_ref,
+    return dict(kernel="linear", M=M, N=N, K=K, fwd_ms=t_f, gelu_ms=t_g, gelu_grad_ms=t_gg, dgrad_ms=t_d, dgrad_gelu_ms=t_dg,
+                dgrad_mul_ms=t_dm, wgrad_ms=t_w, cublas_ms=t_ref,
                 fwd_tflops=fl / t_f / 1e9, gelu_tflops=fl / t_g / 1e9, dgrad_tflops=fl / t_d / 1e9,
                 wgrad_tflops=fl / t_w / 1e9, cublas_tflops=fl / t_ref / 1e9, fwd_gbs=by / t_f / 1e6,
                 t_flop_ms=fl / 1373.6e9, t_byte_ms=by / 6545.6e6)

@@ -96,6 +96,12 @@ def test_linear_fwd_epilogues(vsw, dtype, M, N, K, backend):
     u = torch.empty(M, N, dtype=dtype, device="cuda")
     y = VF.linear_fwd(x, w, b, M, N, K, epi=L.EPI_GELU, aux_out=u)
     assert rel_l2(u, ref) < TOL[dtype] and rel_l2(y, F.gelu(ref)) < TOL[dtype]
+    # training form: the second output is gelu'(pre-activation)
+    gd = torch.empty_like(u)
+    y2 = VF.linear_fwd(x, w, b, M, N, K, epi=L.EPI_GELU_GRAD, aux_out=gd)
+    rd = ref.clone().requires_grad_(True)
+    F.gelu(rd).sum().backward()
+    assert rel_l2(y2, F.gelu(ref)) < TOL[dtype] and rel_l2(gd, rd.grad) < TOL[dtype]
     res = rnd(M, N, dtype=dtype)
     y = VF.linear_fwd(x, w, b, M, N, K, epi=L.EPI_RESIDUAL, res=res, rows_per_batch=M, dst_rows_per_batch=M)
     assert rel_l2(y, res.double() + ref) < TOL[dtype]
@@ -147,6 +153,8 @@ def test_linear_dgrad_wgrad(vsw, dtype, M, N, K, backend):
     ud = u.double().requires_grad_(True)
     F.gelu(ud).backward(dy.double() @ w.double())
     assert rel_l2(dxg, ud.grad) < TOL[dtype]
+    dxm = VF.linear_dgrad(dy, w, M, N, K, mul=u)
+    assert rel_l2(dxm, (dy.double() @ w.double()) * u.double()) < TOL[dtype]
     dw, db = VF.linear_wgrad(dy, x, M, N, K)
     assert rel_l2(dw, dy.double().t() @ x.double()) < TOL[dtype]
     assert rel_l2(db, dy.double().sum(0)) < TOL[dtype]
