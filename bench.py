@@ -180,9 +180,11 @@ def main():
     model.init_weights()
     model = model.to(dev).bfloat16().train()
     net = model
-    if world > 1:
+    dp_mode = os.environ.get("VSW_DP_MODE", "coalesced") if world > 1 else "none"
+    if world > 1 and dp_mode == "ddp":
         from torch.nn.parallel import DistributedDataParallel as DDP
-        net = DDP(model, device_ids=[local_rank], gradient_as_bucket_view=True, bucket_cap_mb=50)
+        net = DDP(model, device_ids=[local_rank], gradient_as_bucket_view=True,
+                  bucket_cap_mb=int(os.environ.get("VSW_DDP_BUCKET_MB", "50")))
     B = args.batch
     torch.manual_seed(1 + rank)  # per-rank clips
     x_host = torch.randn(B, 3, 8, side, side).pin_memory()  # fp32 frames as the data loader yields them
@@ -199,6 +201,8 @@ def main():
         y = (module or net)(x)
         loss = (y * Rm).sum(dtype=torch.float32)
         loss.backward()
+        if dp_mode == "coalesced" and module is None:
+            vsw.dp.all_reduce_gradients_coalesced(model.parameters())   # the one exchange step (NCCL, in place, averaged)
         return loss
 
     def barrier():

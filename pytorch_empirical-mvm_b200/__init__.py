@@ -4,9 +4,9 @@ Drop-in for the reference's ``visbackbone/video_swin.py`` (see ``video_swin.py``
 ``csrc/`` behind the C ABI of ``include/vsw.h`` and are loaded through ctypes (``_lib``).
 The directory name contains a '-', so import it with ``importlib.import_module("pytorch_empirical-mvm_b200")``.
 """
-from . import _lib, functional  # noqa: F401
+from . import _lib, dp, functional  # noqa: F401
 from .video_swin import *  # noqa: F401,F403
 from .video_swin import __all__ as _vs_all
 
-__all__ = list(_vs_all) + ["functional", "_lib"]
+__all__ = list(_vs_all) + ["functional", "_lib", "dp"]
 __version__ = "0.1.0"

@@ -56,3 +56,25 @@ def all_reduce_gradients(params: Iterable[torch.Tensor], world_size: int | None 
             p.grad.copy_(flat[off:off + n].view_as(p.grad))
             off += n
     return len(work)
+
+
+def all_reduce_gradients_coalesced(params: Iterable[torch.Tensor]) -> int:
+    """Copy-free form of the exchange step: every ``.grad`` tensor is averaged IN PLACE by one coalesced NCCL group call
+    (``ReduceOp.AVG``; no flat buffer, no per-parameter copy or divide kernels).  Our autograd Functions hand each weight
+    gradient to autograd as a fresh tensor, so DDP's bucket views would cost one copy kernel per parameter per step.
+    Returns the number of tensors reduced.  (gloo has no AVG: it takes the SUM + divide route.)"""
+    if not dist.is_initialized() or dist.get_world_size() == 1:
+        return 0
+    grads = [p.grad for p in params if p.grad is not None]
+    if not grads:
+        return 0
+    if dist.get_backend() != "nccl":
+        for g in grads:
+            dist.all_reduce(g, op=dist.ReduceOp.SUM)
+            g.div_(dist.get_world_size())
+        return len(grads)
+    with dist._coalescing_manager(device=grads[0].device, async_ops=True) as cm:
+        for g in grads:
+            dist.all_reduce(g, op=dist.ReduceOp.AVG)
+    cm.wait()
+    return len(grads)

@@ -37,8 +37,16 @@ def _worker(rank, world, port, tmpdir):
         y = O.swin_forward(full, x[sl], cfg)
         loss = (y * R[sl]).sum() / n_clips * world
         loss.backward()
+        local = {k: p.grad.clone() for k, p in params.items()}
         ncoll = dp.all_reduce_gradients(params.values(), bucket_bytes=64 << 10)
         assert ncoll >= 2  # several buckets at this bucket size
+        # the copy-free, in-place form of the same exchange step (what bench.py uses) must give the same averages
+        twins = {k: torch.nn.Parameter(torch.zeros_like(v)) for k, v in params.items()}
+        for k, t in twins.items():
+            t.grad = local[k].clone()
+        assert dp.all_reduce_gradients_coalesced(twins.values()) == len(twins)
+        for k in twins:
+            assert torch.allclose(twins[k].grad, params[k].grad, rtol=1e-6, atol=1e-7), k
         if rank == 0:
             ref = {k: torch.nn.Parameter(v.clone()) for k, v in sd.items() if v.is_floating_point()}
             fr = dict(sd)
