@@ -50,7 +50,7 @@ struct Smem {
     int* rc; int* cc;
     float* xmax; float* xsum;   // xmax [4][128]; xsum [2 tile parities][4][128]
     float* maxbias; int* masked;  // [2]
-    float* k2max;                 // [2] max_j |k_j|^2 of the staged item
+    float* k2max;                 // [2] max_j |k_j|^2 of the staged item; [2..3] = min of the bias column (x log2e)
     float* q2[2];                 // [2][512] |q_i|^2 of the staged item
     uint64_t* qkv_full; uint64_t* qkv_empty; uint64_t* aux_full; uint64_t* aux_empty;  // [2] each
     uint64_t* s_full; uint64_t* p_full; uint64_t* o_full;
@@ -131,37 +131,21 @@ __device__ __forceinline__ float row_norm2(const __nv_bfloat16* rowp) {
 // TMEM lane quadrant each); all boundaries are multiples of 16.  part_off = offset of part `part` inside a half.
 __device__ __forceinline__ int part_off(int len, int part) { return ((((len >> 4) * part) / NPARTS) << 4); }
 
-// ---- forward softmax over the full chunks [cbeg, cfull) of one row, software-pipelined TMEM loads --------
-// pass 1: row max (raw accumulator when !MASKED: the caller scales afterwards; scaled + mask when MASKED)
-template <bool MASKED>
-__device__ __forceinline__ float fwd_rowmax(uint32_t srow, int cbeg, int cfull, uint32_t reg_a, uint32_t regi4,
-                                            float scale_log2) {
+// ---- forward softmax over the full chunks [cbeg, cfull) of one row ---------------------------------------------
+// exact-path pass 1 (rare): true row max of  acc*scale_log2 + bias (+mask)  -- a compact un-pipelined loop
+__device__ __forceinline__ float fwd_rowmax_exact(bool masked, uint32_t srow, int cbeg, int cfull, uint32_t tabrow, uint32_t cc_a,
+                                                  uint32_t reg_a, uint32_t regi4, float scale_log2) {
     float mx = -INFINITY;
-    if (cbeg >= cfull) return mx;
-    uint32_t a[16], b[16];
-    auto body = [&](const uint32_t (&r)[16], int c) {
-        if (MASKED) {
-            uint32_t nq4[4];
-            neq16(reg_a + c, regi4, nq4);
+#pragma unroll 1
+    for (int c = cbeg; c < cfull; c += 16) {
+        uint32_t r[16], cj[16], nq4[4] = {0, 0, 0, 0};
+        tc::tmem_ld_32x16(srow + c, r);
+        lds16i(cc_a + c * 4, cj);
+        if (masked) neq16(reg_a + c, regi4, nq4);
+        tc::tmem_ld_wait();
 #pragma unroll
-            for (int e = 0; e < 16; ++e) mx = fmaxf(mx, mask_add(__uint_as_float(r[e]) * scale_log2, nq4, e));
-        } else {
-#pragma unroll
-            for (int e = 0; e < 16; ++e) mx = fmaxf(mx, __uint_as_float(r[e]));
-        }
-    };
-    tc::tmem_ld_32x16(srow + cbeg, a);
-    tc::tmem_ld_wait();
-    for (int c = cbeg; c < cfull; c += 32) {
-        const bool hb = c + 16 < cfull, ha = c + 32 < cfull;
-        if (hb) tc::tmem_ld_32x16(srow + c + 16, b);
-        body(a, c);
-        if (hb) {
-            tc::tmem_ld_wait();
-            if (ha) tc::tmem_ld_32x16(srow + c + 32, a);
-            body(b, c + 16);
-            if (ha) tc::tmem_ld_wait();
-        }
+        for (int e = 0; e < 16; ++e)
+            mx = fmaxf(mx, mask_add(fmaf(__uint_as_float(r[e]), scale_log2, tc::lds_f32(tabrow + cj[e])), nq4, e));
     }
     return mx;
 }
@@ -169,7 +153,7 @@ __device__ __forceinline__ float fwd_rowmax(uint32_t srow, int cbeg, int cfull, 
 // pass 2: p = exp2(acc*scale_log2 + bias[rowcode+colcode] (+mask) - max) -> packed bf16 back into TMEM, returns row sum
 template <bool MASKED>
 __device__ __forceinline__ float fwd_exp(uint32_t srow, uint32_t prow, int cbase, int cbeg, int cfull, uint32_t tabrow,
-                                         uint32_t cc_a, uint32_t reg_a, uint32_t regi4, float scale_log2, float nm) {
+                                         uint32_t cc_a, uint32_t reg_a, uint32_t regi4, float scale_log2) {
     float sum = 0.f;
     if (cbeg >= cfull) return sum;
     uint32_t a[16], b[16];
@@ -183,8 +167,8 @@ __device__ __forceinline__ float fwd_exp(uint32_t srow, uint32_t prow, int cbase
         uint32_t pw[8];
 #pragma unroll
         for (int e = 0; e < 16; e += 2) {
-            float v0 = fmaf(__uint_as_float(r[e]), scale_log2, tb[e]) + nm;
-            float v1 = fmaf(__uint_as_float(r[e + 1]), scale_log2, tb[e + 1]) + nm;
+            float v0 = fmaf(__uint_as_float(r[e]), scale_log2, tb[e]);
+            float v1 = fmaf(__uint_as_float(r[e + 1]), scale_log2, tb[e + 1]);
             if (MASKED) { v0 = mask_add(v0, nq4, e); v1 = mask_add(v1, nq4, e + 1); }
             const float p0 = tc::ex2_approx(v0), p1 = tc::ex2_approx(v1);
             sum += p0 + p1;
@@ -204,6 +188,31 @@ __device__ __forceinline__ float fwd_exp(uint32_t srow, uint32_t prow, int cbase
             body(b, c + 16);
             if (ha) tc::tmem_ld_wait();
         }
+    }
+    return sum;
+}
+
+// exact-path variant (row max subtracted): rare, so a compact un-pipelined loop that does not weigh on the hot loop's registers
+__device__ __forceinline__ float fwd_exp_sub(bool masked, uint32_t srow, uint32_t prow, int cbase, int cbeg, int cfull,
+                                             uint32_t tabrow, uint32_t cc_a, uint32_t reg_a, uint32_t regi4, float scale_log2,
+                                             float nm) {
+    float sum = 0.f;
+#pragma unroll 1
+    for (int c = cbeg; c < cfull; c += 16) {
+        uint32_t r[16], cj[16], nq4[4] = {0, 0, 0, 0}, pw[8];
+        tc::tmem_ld_32x16(srow + c, r);
+        lds16i(cc_a + c * 4, cj);
+        if (masked) neq16(reg_a + c, regi4, nq4);
+        tc::tmem_ld_wait();
+#pragma unroll
+        for (int e = 0; e < 16; e += 2) {
+            const float v0 = mask_add(fmaf(__uint_as_float(r[e]), scale_log2, tc::lds_f32(tabrow + cj[e])) + nm, nq4, e);
+            const float v1 = mask_add(fmaf(__uint_as_float(r[e + 1]), scale_log2, tc::lds_f32(tabrow + cj[e + 1])) + nm, nq4, e + 1);
+            const float p0 = tc::ex2_approx(v0), p1 = tc::ex2_approx(v1);
+            sum += p0 + p1;
+            pw[e / 2] = tc::pack_bf16(p0, p1);
+        }
+        tc::tmem_st_32x8(prow + (c - cbase) / 2, pw);
     }
     return sum;
 }
@@ -308,13 +317,15 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const FwdParams p)
             const int st = it & 1; const uint32_t ph = (it >> 1) & 1;
             const int b_ = w / p.nH, h = w - b_ * p.nH, win = b_ % p.nW;
             tc::mbar_wait(&s.aux_empty[st], ph ^ 1);
-            float mb = -INFINITY;
+            float mb = -INFINITY, nb = -INFINITY;   // max and -min of the bias column
             for (int l = lane; l < p.L; l += 32) {
                 const float v = __bfloat162float(p.table[(long long)l * p.nH + h]) * LOG2E;
                 s.tab[st][l] = v;
                 mb = fmaxf(mb, v);
+                nb = fmaxf(nb, -v);
             }
             mb = warp_max(mb);
+            nb = warp_max(nb);
             int diff = 0;
             if (p.region) {
                 const uint8_t* rg = p.region + (long long)win * p.N;
@@ -333,7 +344,7 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const FwdParams p)
                 s.q2[st][n] = row_norm2(rowp);
             }
             k2 = warp_max(k2);
-            if (lane == 0) { s.maxbias[st] = mb; s.masked[st] = diff; s.k2max[st] = k2; }
+            if (lane == 0) { s.maxbias[st] = mb; s.masked[st] = diff; s.k2max[st] = k2; s.k2max[2 + st] = -nb; }
             __syncwarp();
             if (lane == 0) tc::mbar_arrive(&s.aux_full[st]);
         }
@@ -361,6 +372,7 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const FwdParams p)
             const bool masked = s.masked[st] != 0;
             const float mb = s.maxbias[st];
             const float k2max = s.k2max[st];
+            const bool bias_ok = mb <= 50.0f && s.k2max[2 + st] >= -50.0f;   // |bias| <= 50 in log2 units
             const float* tab = s.tab[st];
             const uint8_t* reg = s.reg[st];
             const uint32_t reg_a = tc::smem_u32(reg), cc_a = tc::smem_u32(s.cc);
@@ -413,11 +425,13 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const FwdParams p)
                 const uint8_t regi = masked ? reg[ic] : 0;
                 const uint32_t regi4 = (uint32_t)regi * 0x01010101u;
                 const bool warp_rows = t * QT + q * 32 < p.N;   // warp-uniform: any valid row in this warp?
-                // Single-pass softmax when it is provably safe: |s_ij| <= |q_i| max_j|k_j| scale =: bound, so with
-                // m = bound every exponent lies in [-2 bound - bias range, 0]; for bound <= 50 (log2 units) nothing
-                // can underflow fp32/bf16.  Otherwise (huge logits) fall back to the exact two-pass row max.
+                // Single-pass softmax when it is provably safe: |s_ij| <= |q_i| max_j|k_j| scale =: bound.  For bound <= 50 and
+                // |bias| <= 50 (log2 units) every exponent lies in [-100, 100] (masked entries lower still, they flush to
+                // 0 like the reference's e^-100), far inside the fp32 AND bf16 exponent range, so the exponentials need
+                // no max subtraction at all (softmax = p / sum p is invariant to it; lse = log sum).  Otherwise (huge
+                // logits or bias values) fall back to the exact two-pass row max.
                 const float bound = sqrtf(s.q2[st][ic] * k2max) * p.scale_log2;
-                const bool fast = __all_sync(0xffffffffu, bound <= 50.0f);
+                const bool fast = __all_sync(0xffffffffu, bound <= 50.0f) && bias_ok;
                 long long t_a = clock64();
                 tc::mbar_wait(&s.s_full[0], sph);
                 if (!fast) tc::mbar_wait(&s.s_full[1], sph);
@@ -425,17 +439,16 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const FwdParams p)
                 long long t_b = clock64();
                 float mx;
                 if (fast) {
-                    mx = bound + mb;
+                    mx = 0.f;   // no subtraction at all: every exponent is within +-100, far inside the fp32 / bf16 range
                 } else {
-                    // ---- pass 1: row max of the raw scores (+ exact mask term in masked windows) over both halves;
-                    //      the bias is bounded by its per-head maximum `mb`, so mx is an upper bound of the true max
+                    // ---- pass 1: exact row max of score*scale + bias (+ mask) over both halves
                     mx = -INFINITY;
                     if (warp_rows) {
-#pragma unroll
+                        const uint32_t tabrow1 = tc::smem_u32(tab + rci);
+#pragma unroll 1
                         for (int hh = 0; hh < NHALF; ++hh) {
                             const int cfull = min(ce[hh], nfull);
-                            mx = fmaxf(mx, masked ? fwd_rowmax<true>(srow, cb[hh], cfull, reg_a, regi4, p.scale_log2)
-                                                  : fwd_rowmax<false>(srow, cb[hh], cfull, reg_a, regi4, p.scale_log2) * p.scale_log2);
+                            mx = fmaxf(mx, fwd_rowmax_exact(masked, srow, cb[hh], cfull, tabrow1, cc_a, reg_a, regi4, p.scale_log2));
                             for (int c = max(cb[hh], cfull); c < ce[hh]; c += 16) {   // chunk with columns >= N
                                 uint32_t r[16];
                                 tc::tmem_ld_32x16(srow + c, r);
@@ -443,7 +456,7 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const FwdParams p)
 #pragma unroll
                                 for (int e = 0; e < 16; ++e) {
                                     if (c + e < p.N) {
-                                        float v = __uint_as_float(r[e]) * p.scale_log2;
+                                        float v = fmaf(__uint_as_float(r[e]), p.scale_log2, tc::lds_f32(tabrow1 + s.cc[c + e]));
                                         if (masked && reg[c + e] != regi) v += MASKV;
                                         mx = fmaxf(mx, v);
                                     }
@@ -456,7 +469,7 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const FwdParams p)
 #pragma unroll
                     for (int k = 0; k < NPARTS; ++k) mx = fmaxf(mx, s.xmax[k * QT + row]);
                     tc::named_bar_sync(1 + q, 32 * NPARTS);   // xmax may be rewritten by the next tile
-                    mx += mb;
+                    if (!(mx > -INFINITY)) mx = 0.f;          // rows beyond the window
                 }
                 long long t_c = clock64();
                 // ---- pass 2: p = exp2(s - max) -> packed bf16 into TMEM (aliasing S), row sum in fp32, half by half;
@@ -471,8 +484,11 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const FwdParams p)
                     const uint32_t prow = srow + qb;   // P (packed bf16) aliases the part's own S columns
                     if (warp_rows) {
                         const int qf = min(qe, nfull);
-                        sum += masked ? fwd_exp<true>(srow, prow, qb, qb, qf, tabrow, cc_a, reg_a, regi4, p.scale_log2, nm)
-                                      : fwd_exp<false>(srow, prow, qb, qb, qf, tabrow, cc_a, reg_a, regi4, p.scale_log2, nm);
+                        if (fast)
+                            sum += masked ? fwd_exp<true>(srow, prow, qb, qb, qf, tabrow, cc_a, reg_a, regi4, p.scale_log2)
+                                          : fwd_exp<false>(srow, prow, qb, qb, qf, tabrow, cc_a, reg_a, regi4, p.scale_log2);
+                        else
+                            sum += fwd_exp_sub(masked, srow, prow, qb, qb, qf, tabrow, cc_a, reg_a, regi4, p.scale_log2, nm);
                         for (int c = max(qb, qf); c < qe; c += 16) {   // chunk with columns >= N
                             uint32_t r[16];
                             tc::tmem_ld_32x16(srow + c, r);

@@ -217,6 +217,44 @@ def test_window_attention_fwd_bwd(vsw, oracle, dtype, geom, backend):
     assert rel_l2(dtab, tr.grad) < TOL[dtype] * (1 if dtype == torch.float32 else 1.5)
 
 
+@pytest.mark.parametrize("case", ["huge_logits", "huge_bias"])
+def test_window_attention_exact_softmax_path(vsw, oracle, case):
+    """The tcgen05 forward skips the row-max subtraction only when |scores| and |bias| are provably small; huge logits or bias
+    values must take the exact two-pass path and still match (and the recompute backward must accept its log-sum-exp)."""
+    VF, L = vsw.functional, vsw._lib
+    L.set_gemm_backend(L.GEMM_TCGEN05)
+    try:
+        grid, window, shift, nH, hd, B = (8, 14, 14), (8, 7, 7), (0, 3, 3), 2, 32, 1
+        plan = VF.window_plan(grid, window, shift, "cuda")
+        nW, N = plan.nW, plan.N
+        B_ = B * nW
+        torch.manual_seed(11)
+        qkv = rnd(B_, N, 3, nH, hd, dtype=torch.bfloat16)
+        table = rnd(15 * 13 * 13, nH, dtype=torch.bfloat16, scale=0.5)
+        if case == "huge_logits":
+            qkv[:, :, :2] *= 6.0        # |q||k| scale log2e ~ 400 >> 50
+        else:
+            table = table * 150.0       # bias range far beyond +-50 log2 units
+        rel_index = torch.from_numpy(oracle.relative_position_index(window)).cuda()
+        rowcode, colcode = VF.bias_codes(rel_index, N)
+        mask = vsw.compute_mask(*plan.pgrid, plan.ws, plan.ss, "cuda")
+        qr = qkv.double().requires_grad_(True)
+        tr = table.double().requires_grad_(True)
+        oref, lref = attn_reference(qr, tr, rel_index, mask, nW, nH, hd ** -0.5)
+        out, lse = VF.attn_fwd(qkv.view(B_ * N, -1), table, rowcode, colcode, plan.region, None, B_, nW, N, nH, hd, hd ** -0.5)
+        assert torch.isfinite(out.float()).all() and torch.isfinite(lse).all()
+        assert rel_l2(out.view(B_, N, -1), oref) < 3e-2
+        assert rel_l2(lse, lref) < 1e-2
+        dout = rnd(B_, N, nH * hd, dtype=torch.bfloat16)
+        oref.backward(dout.double())
+        dqkv, dtab = VF.attn_bwd(qkv.view(B_ * N, -1), out, dout.view(B_ * N, -1), lse, table, rowcode, colcode, plan.region,
+                                 None, B_, nW, N, nH, hd, hd ** -0.5)
+        assert torch.isfinite(dqkv.float()).all() and torch.isfinite(dtab.float()).all()
+        assert rel_l2(dqkv.view(B_, N, 3, nH, hd)[:, :, 2], qr.grad[:, :, 2]) < 6e-2   # dV (softmax is nearly one-hot here)
+    finally:
+        L.set_gemm_backend(0)
+
+
 @pytest.mark.parametrize("dtype", DTYPES)
 @pytest.mark.parametrize("backend", [0, 1])
 def test_window_attention_swin_l_384_window(vsw, oracle, dtype, backend):
