@@ -30,7 +30,7 @@ constexpr int NTHREADS = 384;                 // backward: warp 0 TMA, 1 MMA, 2 
 constexpr int NPARTS = 3;                     // forward: column parts per row (3 softmax warps per TMEM lane quadrant)
 constexpr int NHALF = 2;                      // forward: the key range is processed as two independently pipelined halves
 constexpr int FWD_THREADS = 128 + NPARTS * 128;  // warp 0 TMA, 1 MMA, 2 aux, 3 idle, 4.. softmax
-constexpr int S_COL = 0, O_COL = 480, TMEM_COLS = 512;
+constexpr int S_COL = 0, O_COL = 480, L_COL = 464, TMEM_COLS = 512;   // L: 16 (identical) columns of row sums, needs Npad <= 464
 constexpr float LOG2E = 1.4426950408889634f, LN2 = 0.6931471805599453f;
 
 struct FwdParams {
@@ -48,7 +48,8 @@ struct Smem {
     float* tab[2];
     uint8_t* reg[2];
     int* rc; int* cc;
-    float* xmax; float* xsum;   // xmax [4][128]; xsum [2 tile parities][4][128]
+    float* xmax;                // [4][128] exact-path row-max exchange
+    uint8_t* ones;              // 1 KB of bf16 1.0: B operand of the row-sum MMA (l = P . 1 on the tensor core)
     float* maxbias; int* masked;  // [2]
     float* k2max;                 // [2] max_j |k_j|^2 of the staged item; [2..3] = min of the bias column (x log2e)
     float* q2[2];                 // [2][512] |q_i|^2 of the staged item
@@ -66,7 +67,7 @@ __device__ __forceinline__ Smem carve(uint8_t* base, int Lpad) {
     s.rc = (int*)p; p += AUXROWS * 4;
     s.cc = (int*)p; p += AUXROWS * 4;
     s.xmax = (float*)p; p += 4 * QT * 4;
-    s.xsum = (float*)p; p += 8 * QT * 4;
+    s.ones = p; p += 1024;
     s.maxbias = (float*)p; p += 8;
     s.masked = (int*)p; p += 8;
     s.k2max = (float*)p; p += 16;
@@ -85,7 +86,7 @@ __device__ __forceinline__ Smem carve(uint8_t* base, int Lpad) {
     return s;
 }
 size_t fwd_smem_bytes(int Lpad) {
-    return 1024 + 2 * (size_t)STAGE_BYTES + 2 * (size_t)Lpad * 4 + 2 * AUXROWS * 4 + 12 * QT * 4 + 32 + 4 * 16 + 16 + 16 + 8 + 8 +
+    return 1024 + 2 * (size_t)STAGE_BYTES + 2 * (size_t)Lpad * 4 + 2 * AUXROWS * 4 + 4 * QT * 4 + 1024 + 32 + 4 * 16 + 16 + 16 + 8 + 8 +
            2 * AUXROWS + 2 * AUXROWS * 4 + 16;
 }
 
@@ -150,12 +151,12 @@ __device__ __forceinline__ float fwd_rowmax_exact(bool masked, uint32_t srow, in
     return mx;
 }
 
-// pass 2: p = exp2(acc*scale_log2 + bias[rowcode+colcode] (+mask) - max) -> packed bf16 back into TMEM, returns row sum
+// pass 2: p = exp2(acc*scale_log2 + bias[rowcode+colcode] (+mask)) -> packed bf16 back into TMEM (the row sum comes from the
+// tensor core: l = P . 1 is accumulated next to O = P . V)
 template <bool MASKED>
-__device__ __forceinline__ float fwd_exp(uint32_t srow, uint32_t prow, int cbase, int cbeg, int cfull, uint32_t tabrow,
-                                         uint32_t cc_a, uint32_t reg_a, uint32_t regi4, float scale_log2) {
-    float sum = 0.f;
-    if (cbeg >= cfull) return sum;
+__device__ __forceinline__ void fwd_exp(uint32_t srow, uint32_t prow, int cbase, int cbeg, int cfull, uint32_t tabrow,
+                                        uint32_t cc_a, uint32_t reg_a, uint32_t regi4, float scale_log2) {
+    if (cbeg >= cfull) return;
     uint32_t a[16], b[16];
     auto body = [&](const uint32_t (&r)[16], int c) {
         uint32_t cj[16], nq4[4];
@@ -171,7 +172,6 @@ __device__ __forceinline__ float fwd_exp(uint32_t srow, uint32_t prow, int cbase
             float v1 = fmaf(__uint_as_float(r[e + 1]), scale_log2, tb[e + 1]);
             if (MASKED) { v0 = mask_add(v0, nq4, e); v1 = mask_add(v1, nq4, e + 1); }
             const float p0 = tc::ex2_approx(v0), p1 = tc::ex2_approx(v1);
-            sum += p0 + p1;
             pw[e / 2] = tc::pack_bf16(p0, p1);
         }
         tc::tmem_st_32x8(prow + (c - cbase) / 2, pw);
@@ -189,14 +189,12 @@ __device__ __forceinline__ float fwd_exp(uint32_t srow, uint32_t prow, int cbase
             if (ha) tc::tmem_ld_wait();
         }
     }
-    return sum;
 }
 
 // exact-path variant (row max subtracted): rare, so a compact un-pipelined loop that does not weigh on the hot loop's registers
-__device__ __forceinline__ float fwd_exp_sub(bool masked, uint32_t srow, uint32_t prow, int cbase, int cbeg, int cfull,
+__device__ __forceinline__ void fwd_exp_sub(bool masked, uint32_t srow, uint32_t prow, int cbase, int cbeg, int cfull,
                                              uint32_t tabrow, uint32_t cc_a, uint32_t reg_a, uint32_t regi4, float scale_log2,
                                              float nm) {
-    float sum = 0.f;
 #pragma unroll 1
     for (int c = cbeg; c < cfull; c += 16) {
         uint32_t r[16], cj[16], nq4[4] = {0, 0, 0, 0}, pw[8];
@@ -209,12 +207,10 @@ __device__ __forceinline__ float fwd_exp_sub(bool masked, uint32_t srow, uint32_
             const float v0 = mask_add(fmaf(__uint_as_float(r[e]), scale_log2, tc::lds_f32(tabrow + cj[e])) + nm, nq4, e);
             const float v1 = mask_add(fmaf(__uint_as_float(r[e + 1]), scale_log2, tc::lds_f32(tabrow + cj[e + 1])) + nm, nq4, e + 1);
             const float p0 = tc::ex2_approx(v0), p1 = tc::ex2_approx(v1);
-            sum += p0 + p1;
             pw[e / 2] = tc::pack_bf16(p0, p1);
         }
         tc::tmem_st_32x8(prow + (c - cbase) / 2, pw);
     }
-    return sum;
 }
 
 __global__ void __launch_bounds__(FWD_THREADS, 1)
@@ -237,10 +233,12 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const FwdParams p)
         tc::fence_barrier_init();
     }
     if (warp == 1) tc::tmem_alloc(s.tmem_slot, TMEM_COLS);
+    for (int n = threadIdx.x; n < 256; n += FWD_THREADS) reinterpret_cast<uint32_t*>(s.ones)[n] = 0x3F803F80u;   // bf16 1.0 pairs
     for (int n = threadIdx.x; n < AUXROWS; n += FWD_THREADS) {   // cc holds BYTE offsets into the fp32 table copy
         s.rc[n] = n < p.N ? p.rowcode[n] : 0;
         s.cc[n] = n < p.N ? p.colcode[n] * 4 : 0;
     }
+    tc::fence_proxy_async();   // the ones tile is read by the tensor core
     tc::tc_fence_before();
     __syncthreads();
     tc::tc_fence_after();
@@ -269,6 +267,8 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const FwdParams p)
         if (lane == 0) {
             int it = 0; uint32_t pph = 0;
             const uint32_t idesc_pv = tc::idesc_bf16(QT, HD, 0, 1);
+            const uint32_t idesc_l = tc::idesc_bf16(QT, 16, 0, 1);
+            const uint64_t ones_desc = tc::smem_desc_sw64(tc::smem_u32(s.ones), 0, 512);   // all ones: only the 1 KB footprint matters
             const int hbeg[NHALF] = {0, p.h0}, hlen[NHALF] = {p.h0, p.Npad - p.h0};
             for (int w = blockIdx.x; w < items; w += gridDim.x, ++it) {
                 const int st = it & 1; const uint32_t ph = (it >> 1) & 1;
@@ -298,7 +298,9 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const FwdParams p)
                             const int k00 = hbeg[hh] + part_off(hlen[hh], part), k01 = hbeg[hh] + part_off(hlen[hh], part + 1);
                             for (int key0 = k00; key0 < k01; key0 += 16) {
                                 const uint64_t vd = ((uint64_t)vdesc0_hi << 32) | (((va + key0 * 64) & 0x3FFFFu) >> 4);
-                                tc::umma_bf16_ts(tmem + O_COL, tmem + S_COL + k00 + (key0 - k00) / 2, vd, idesc_pv, acc_pv);
+                                const uint32_t pcol = tmem + S_COL + k00 + (key0 - k00) / 2;
+                                tc::umma_bf16_ts(tmem + O_COL, pcol, vd, idesc_pv, acc_pv);
+                                tc::umma_bf16_ts(tmem + L_COL, pcol, ones_desc, idesc_l, acc_pv);   // l += P . 1 (row sums)
                                 acc_pv = 1;
                             }
                         }
@@ -386,14 +388,12 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const FwdParams p)
                 tc::mbar_wait(s.o_full, oph); oph ^= 1;
                 tc::tc_fence_after();
                 long long t_e = clock64();
-                const float* xs = s.xsum + (te & 1) * 4 * QT;
-                float l = 0.f;
-#pragma unroll
-                for (int k = 0; k < NPARTS; ++k) l += xs[k * QT + row];
-                const float inv = __fdividef(1.0f, l);
-                uint32_t o[16];
+                uint32_t o[16], lr[16];
                 tc::tmem_ld_32x16(tmem + lane_base + O_COL + (part & 1) * 16, o);
+                tc::tmem_ld_32x16(tmem + lane_base + L_COL, lr);   // 16 identical columns of the row sum
                 tc::tmem_ld_wait();
+                const float l = __uint_as_float(lr[0]);
+                const float inv = __fdividef(1.0f, l);
                 if (ie < p.N && part < 2) {
                     __nv_bfloat16* dst = p.out + ((long long)b_ * p.N + ie) * C + h * HD + part * 16;
                     uint4 u0, u1;
@@ -474,7 +474,6 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const FwdParams p)
                 long long t_c = clock64();
                 // ---- pass 2: p = exp2(s - max) -> packed bf16 into TMEM (aliasing S), row sum in fp32, half by half;
                 //      after each half the MMA warp runs that half of P.V and then the half's S for the next tile
-                float sum = 0.f;
                 const uint32_t tabrow = tc::smem_u32(tab + rci);
                 const float nm = -mx;
 #pragma unroll
@@ -485,10 +484,10 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const FwdParams p)
                     if (warp_rows) {
                         const int qf = min(qe, nfull);
                         if (fast)
-                            sum += masked ? fwd_exp<true>(srow, prow, qb, qb, qf, tabrow, cc_a, reg_a, regi4, p.scale_log2)
-                                          : fwd_exp<false>(srow, prow, qb, qb, qf, tabrow, cc_a, reg_a, regi4, p.scale_log2);
+                            if (masked) fwd_exp<true>(srow, prow, qb, qb, qf, tabrow, cc_a, reg_a, regi4, p.scale_log2);
+                            else fwd_exp<false>(srow, prow, qb, qb, qf, tabrow, cc_a, reg_a, regi4, p.scale_log2);
                         else
-                            sum += fwd_exp_sub(masked, srow, prow, qb, qb, qf, tabrow, cc_a, reg_a, regi4, p.scale_log2, nm);
+                            fwd_exp_sub(masked, srow, prow, qb, qb, qf, tabrow, cc_a, reg_a, regi4, p.scale_log2, nm);
                         for (int c = max(qb, qf); c < qe; c += 16) {   // chunk with columns >= N
                             uint32_t r[16];
                             tc::tmem_ld_32x16(srow + c, r);
@@ -507,7 +506,6 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const FwdParams p)
                                         pe = tc::ex2_approx(v);
                                     }
                                     pv[u] = pe;
-                                    sum += pe;
                                 }
                                 pw[e / 2] = tc::pack_bf16(pv[0], pv[1]);
                             }
@@ -516,7 +514,6 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const FwdParams p)
                     }
                     if (hh == 0 && t > 0) epilogue(t - 1, mx_prev);
                     tc::tmem_st_wait();
-                    if (hh == NHALF - 1) s.xsum[(t & 1) * 4 * QT + part * QT + row] = sum;
                     tc::tc_fence_before();
                     __syncwarp();
                     if (lane == 0) tc::mbar_arrive(&s.p_full[hh]);
