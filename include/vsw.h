@@ -192,19 +192,21 @@ int vsw_linear_wgrad(const void* dy, const void* x, void* dw, void* db,
 int vsw_window_attn_fwd(const void* qkv, const void* bias_table, const int32_t* rowcode, const int32_t* colcode,
                         const uint8_t* region, const void* dense_mask,
                         void* out, float* lse,
-                        int B_, int nW, int N, int nH, int hd, int L, float scale,
+                        int B_, int nW, int N, int nH, int hd, int L, float scale, int window_dims,
                         int dtype, void* stream);
 
 /* Recompute-based backward.  dqkv (B_,N,3,nH,hd); dbias_table (L,nH) fp32, OVERWRITTEN
  * with the reduction over batch and windows, via workspace partials (fixed order).
- * window_planes: depth wd of the effective window (N = wd*wh*ww) or 0 if unknown -- a layout hint only
- * (lets the tensor-core kernel order keys plane-minor; the kernel validates it against the codes). */
+ * window_dims (both directions) = wd_eff | wh << 8 | ww << 16, any field 0 if unknown -- layout hints only, validated
+ * against the codes inside the kernels:  wd_eff = depth of the EFFECTIVE window (N = wd_eff * tokens per plane; lets the
+ * backward order keys plane-minor);  wh, ww = height / width of the CONFIGURED window whose relative_position_index
+ * produced rowcode/colcode (lets the kernels pad the on-chip bias table against shared-memory bank conflicts). */
 size_t vsw_window_attn_bwd_workspace(int B_, int N, int nH, int hd, int L);
 int vsw_window_attn_bwd(const void* qkv, const void* out, const void* dout, const float* lse,
                         const void* bias_table, const int32_t* rowcode, const int32_t* colcode,
                         const uint8_t* region, const void* dense_mask,
                         void* dqkv, float* dbias_table,
-                        int B_, int nW, int N, int nH, int hd, int L, float scale, int window_planes,
+                        int B_, int nW, int N, int nH, int hd, int L, float scale, int window_dims,
                         int dtype, void* ws, size_t ws_bytes, void* stream);
 
 /* ------------------------------------------------------------------------------------------------

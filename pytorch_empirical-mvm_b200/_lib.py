@@ -43,7 +43,7 @@ SIGNATURES = {
     "vsw_linear_dgrad_mul": (_i, [_vp] * 3 + [_i] * 3 + [_vp, _vp, _i, _i, _vp, _vp, _i, _vp]),
     "vsw_linear_wgrad_workspace": (_sz, [_i, _i, _i]),
     "vsw_linear_wgrad": (_i, [_vp] * 4 + [_i] * 5 + [_vp, _sz, _vp]),
-    "vsw_window_attn_fwd": (_i, [_vp] * 8 + [_i] * 6 + [_f, _i, _vp]),
+    "vsw_window_attn_fwd": (_i, [_vp] * 8 + [_i] * 6 + [_f, _i, _i, _vp]),
     "vsw_window_attn_bwd_workspace": (_sz, [_i] * 5),
     "vsw_window_attn_bwd": (_i, [_vp] * 11 + [_i] * 6 + [_f, _i, _i, _vp, _sz, _vp]),
     "vsw_patch_im2col": (_i, [_vp, _vp] + [_i] * 10 + [_vp]),

@@ -19,13 +19,13 @@ using namespace vsw;
 
 extern "C" int vsw_window_attn_fwd(const void* qkv, const void* bias_table, const int32_t* rowcode,
                                    const int32_t* colcode, const uint8_t* region, const void* dense_mask, void* out,
-                                   float* lse, int B_, int nW, int N, int nH, int hd, int L, float scale, int dtype,
-                                   void* stream) {
+                                   float* lse, int B_, int nW, int N, int nH, int hd, int L, float scale,
+                                   int window_dims, int dtype, void* stream) {
     VSW_ATTN_CHECK("vsw_window_attn_fwd");
     VSW_REQUIRE(out && lse, VSW_ERR_ARG, "vsw_window_attn_fwd: out/lse NULL");
     cudaStream_t st = (cudaStream_t)stream;
     if (attn_want_tc(dtype, hd, dense_mask)) {
-        int rc = tc_attn_fwd(qkv, bias_table, rowcode, colcode, region, out, lse, B_, nW, N, nH, hd, L, scale, st);
+        int rc = tc_attn_fwd(qkv, bias_table, rowcode, colcode, region, out, lse, B_, nW, N, nH, hd, L, scale, window_dims, st);
         if (rc != VSW_ERR_UNSUPPORTED || backend() == VSW_GEMM_TCGEN05) return rc;
     }
     return simt_attn_fwd(qkv, bias_table, rowcode, colcode, region, dense_mask, out, lse, B_, nW, N, nH, hd, L, scale,
@@ -40,7 +40,7 @@ extern "C" size_t vsw_window_attn_bwd_workspace(int B_, int N, int nH, int hd, i
 extern "C" int vsw_window_attn_bwd(const void* qkv, const void* out, const void* dout, const float* lse,
                                    const void* bias_table, const int32_t* rowcode, const int32_t* colcode,
                                    const uint8_t* region, const void* dense_mask, void* dqkv, float* dbias_table,
-                                   int B_, int nW, int N, int nH, int hd, int L, float scale, int window_planes,
+                                   int B_, int nW, int N, int nH, int hd, int L, float scale, int window_dims,
                                    int dtype, void* ws, size_t ws_bytes, void* stream) {
     VSW_ATTN_CHECK("vsw_window_attn_bwd");
     VSW_REQUIRE(out && dout && lse && dqkv && dbias_table && ws, VSW_ERR_ARG, "vsw_window_attn_bwd: NULL pointer");
@@ -49,7 +49,7 @@ extern "C" int vsw_window_attn_bwd(const void* qkv, const void* out, const void*
     cudaStream_t st = (cudaStream_t)stream;
     if (attn_want_tc(dtype, hd, dense_mask)) {
         int rc = tc_attn_bwd(qkv, out, dout, lse, bias_table, rowcode, colcode, region, dqkv, dbias_table, B_, nW, N,
-                             nH, hd, L, scale, window_planes, ws, ws_bytes, st);
+                             nH, hd, L, scale, window_dims, ws, ws_bytes, st);
         if (rc != VSW_ERR_UNSUPPORTED || backend() == VSW_GEMM_TCGEN05) return rc;
     }
     return simt_attn_bwd(qkv, out, dout, lse, bias_table, rowcode, colcode, region, dense_mask, dqkv, dbias_table, B_,

@@ -17,11 +17,11 @@ int simt_attn_bwd(const void* qkv, const void* out, const void* dout, const floa
 // tcgen05 family (attn_tc.cu): bf16, head_dim 32, region-id masks.  UNSUPPORTED otherwise.
 int tc_attn_fwd(const void* qkv, const void* table, const int32_t* rowcode, const int32_t* colcode,
                 const uint8_t* region, void* out, float* lse, int B_, int nW, int N, int nH, int hd, int L,
-                float scale, cudaStream_t st);
+                float scale, int window_dims, cudaStream_t st);
 size_t tc_attn_bwd_workspace(int B_, int N, int nH, int hd, int L);
 int tc_attn_bwd(const void* qkv, const void* out, const void* dout, const float* lse, const void* table,
                 const int32_t* rowcode, const int32_t* colcode, const uint8_t* region, void* dqkv, float* dbias,
-                int B_, int nW, int N, int nH, int hd, int L, float scale, int planes, void* ws, size_t ws_bytes,
+                int B_, int nW, int N, int nH, int hd, int L, float scale, int window_dims, void* ws, size_t ws_bytes,
                 cudaStream_t st);
 
 }  // namespace vsw

@@ -13,6 +13,7 @@
 //   O = P V          tcgen05.mma (TS: A = P from TMEM, B = V MN-major from smem), 128 x 32 fp32 in TMEM
 //   epilogue         O / rowsum -> bf16 -> global, log-sum-exp -> global (for the recompute backward)
 #include <stdlib.h>
+#include <vector>
 #include "attn.cuh"
 #include "tc_common.cuh"
 
@@ -33,6 +34,41 @@ constexpr int FWD_THREADS = 128 + NPARTS * 128;  // warp 0 TMA, 1 MMA, 2 aux, 3 
 constexpr int S_COL = 0, O_COL = 480, L_COL = 464, TMEM_COLS = 512;   // L: 16 (identical) columns of row sums, needs Npad <= 464
 constexpr float LOG2E = 1.4426950408889634f, LN2 = 0.6931471805599453f;
 
+// On-chip layout of the bias column (and of the backward's histograms).  The reference's table index is
+// (dd)(2wh-1)(2ww-1) + (dh)(2ww-1) + dw  (video_swin.py:127-141); with the window's h-stride 2ww-1 = 13, rows h and h+2..3 of a
+// 7x7 plane alias the same shared-memory banks inside every 32-token group, so each bias gather / histogram update is a 2-way
+// bank conflict.  Padding the h-stride to R2 + pad with (R2 + pad) % 32 == ww makes a plane's 49 tokens hit consecutive banks;
+// pad is accepted only if the padded index is still injective (planes interleave into the gaps: 169 = 4*39 + 13) -- the table
+// grows by 12 %, the conflict replays drop from 1.92 to 1.54 wavefronts per access.
+struct BiasLayout { int wh, ww, R1, R2, pad, Lphys, M1, M2; };   // pad == 0: dense layout; M1/M2: 2^20-scaled reciprocals of R1/R2
+__host__ __device__ inline int bias_dh(int l, int R1, int R2, int M1, int M2) {   // (l % R1) / R2 without a division
+    const int l1 = l - (int)(((unsigned)l * (unsigned)M1) >> 20) * R1;
+    return (int)(((unsigned)l1 * (unsigned)M2) >> 20);
+}
+inline BiasLayout bias_layout(int window_dims, int L) {
+    BiasLayout b{0, 0, 0, 0, 0, L, 0, 0};
+    const int wh = (window_dims >> 8) & 0xFF, ww = (window_dims >> 16) & 0xFF;
+    if (wh < 1 || ww < 1 || getenv("VSW_ATTN_DENSE_TABLE")) return b;
+    const int R2 = 2 * ww - 1, R1 = (2 * wh - 1) * R2;
+    if (L % R1 != 0) return b;                       // not this window's table
+    const int nd = L / R1;                            // 2wd-1
+    const int pad = ((ww - R2) % 32 + 32) % 32;
+    if (pad == 0) return b;
+    const int Lphys = L + pad * (2 * wh - 2);
+    if (Lphys > 3 * L / 2) return b;                  // keep the growth modest
+    const int M1 = ((1 << 20) + R1 - 1) / R1, M2 = ((1 << 20) + R2 - 1) / R2;
+    std::vector<char> seen((size_t)Lphys, 0);         // injectivity of l -> l + pad * ((l % R1) / R2), and the reciprocals
+    for (int l = 0; l < L; ++l) {
+        if (L >= 4096 || bias_dh(l, R1, R2, M1, M2) != (l % R1) / R2) return b;
+        const int lp = l + pad * ((l % R1) / R2);
+        if (seen[lp]) return b;
+        seen[lp] = 1;
+    }
+    (void)nd;
+    b.wh = wh; b.ww = ww; b.R1 = R1; b.R2 = R2; b.pad = pad; b.Lphys = Lphys; b.M1 = M1; b.M2 = M2;
+    return b;
+}
+
 struct FwdParams {
     const __nv_bfloat16* qkv; const __nv_bfloat16* table; const int32_t* rowcode; const int32_t* colcode; const uint8_t* region;
     __nv_bfloat16* out; float* lse;
@@ -40,6 +76,7 @@ struct FwdParams {
     float scale_log2;
     int Npad, nq;
     int h0;           // keys [0, h0) form half 0, [h0, Npad) half 1 (both multiples of 16)
+    int wh, ww, R1, R2, pad, M1, M2;   // padded on-chip bias layout (pad == 0: dense); see bias_layout()
     long long* dbg;   // optional per-phase cycle counters (profiling builds only)
 };
 
@@ -234,9 +271,20 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const FwdParams p)
     }
     if (warp == 1) tc::tmem_alloc(s.tmem_slot, TMEM_COLS);
     for (int n = threadIdx.x; n < 256; n += FWD_THREADS) reinterpret_cast<uint32_t*>(s.ones)[n] = 0x3F803F80u;   // bf16 1.0 pairs
+    // padded bias layout: only if the codes really are this window's dense (dd, dh, dw) codes (checked here, every CTA)
+    int pad = p.pad;
+    if (pad) {
+        bool ok = p.rowcode[0] + p.colcode[0] == (p.L - 1) / 2;
+        for (int n = threadIdx.x; n < p.N && ok; n += FWD_THREADS) {
+            const int e = (n / (p.wh * p.ww)) * p.R1 + ((n / p.ww) % p.wh) * p.R2 + n % p.ww;
+            ok = p.rowcode[n] - p.rowcode[0] == e && p.colcode[0] - p.colcode[n] == e;
+        }
+        if (!__syncthreads_and(ok)) pad = 0;
+    }
     for (int n = threadIdx.x; n < AUXROWS; n += FWD_THREADS) {   // cc holds BYTE offsets into the fp32 table copy
-        s.rc[n] = n < p.N ? p.rowcode[n] : 0;
-        s.cc[n] = n < p.N ? p.colcode[n] * 4 : 0;
+        const int hn = pad ? (n / p.ww) % p.wh : 0;
+        s.rc[n] = n < p.N ? p.rowcode[n] + pad * hn : 0;
+        s.cc[n] = n < p.N ? (p.colcode[n] + pad * (p.wh - 1 - hn)) * 4 : 0;
     }
     tc::fence_proxy_async();   // the ones tile is read by the tensor core
     tc::tc_fence_before();
@@ -322,7 +370,7 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const FwdParams p)
             float mb = -INFINITY, nb = -INFINITY;   // max and -min of the bias column
             for (int l = lane; l < p.L; l += 32) {
                 const float v = __bfloat162float(p.table[(long long)l * p.nH + h]) * LOG2E;
-                s.tab[st][l] = v;
+                s.tab[st][pad ? l + pad * bias_dh(l, p.R1, p.R2, p.M1, p.M2) : l] = v;   // padded layout (bias_layout())
                 mb = fmaxf(mb, v);
                 nb = fmaxf(nb, -v);
             }
@@ -545,8 +593,10 @@ bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 
 
 int tc_attn_fwd(const void* qkv, const void* table, const int32_t* rowcode, const int32_t* colcode,
                 const uint8_t* region, void* out, float* lse, int B_, int nW, int N, int nH, int hd, int L,
-                float scale, cudaStream_t st) {
-    const int Lpad = (L + 3) / 4 * 4;
+                float scale, int window_dims, cudaStream_t st) {
+    BiasLayout bl = bias_layout(window_dims, L);
+    if (fwd_smem_bytes((bl.Lphys + 3) / 4 * 4) > 227 * 1024) bl = bias_layout(0, L);   // no room for the padded table
+    const int Lpad = (bl.Lphys + 3) / 4 * 4;
     const size_t smem = fwd_smem_bytes(Lpad);
     if (hd != HD || N > 448 || N < 1 || smem > 227 * 1024 || !aligned16(qkv) || !aligned16(out)) {
         set_error("tcgen05 window attention: needs head_dim 32, N <= 448 and a bias table that fits shared memory "
@@ -560,6 +610,7 @@ int tc_attn_fwd(const void* qkv, const void* table, const int32_t* rowcode, cons
     p.qkv = (const __nv_bfloat16*)qkv; p.table = (const __nv_bfloat16*)table; p.rowcode = rowcode; p.colcode = colcode; p.region = region;
     p.out = (__nv_bfloat16*)out; p.lse = lse;
     p.B_ = B_; p.nW = nW; p.N = N; p.nH = nH; p.L = L; p.Lpad = Lpad;
+    p.wh = bl.wh; p.ww = bl.ww; p.R1 = bl.R1; p.R2 = bl.R2; p.pad = bl.pad; p.M1 = bl.M1; p.M2 = bl.M2;
     p.scale_log2 = scale * LOG2E;
     p.Npad = (N + 15) / 16 * 16;
     p.nq = (N + QT - 1) / QT;

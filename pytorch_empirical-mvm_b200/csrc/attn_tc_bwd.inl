@@ -36,11 +36,12 @@ struct BwdParams {
     int ntail;        // > 0: the last query tile holds only ntail (<= 8) rows and is processed transposed (see below)
     long long* dbg;
     int wd, hw, boxhw;   // key permutation: column c' = hw_index * wd + plane (plane = temporal slab of the window)
+    int wh, ww, R1, R2, pad;   // padded on-chip bias / histogram layout (pad == 0: dense); see bias_layout()
 };
 
 struct BwdSmem {
     float* tab; float* hist;          // [Lpad], [8][Lpad]
-    float* delta; float* lse2;        // [2][512] each (one copy per column half)
+    float* delta; float* lse2;        // [512] each (the two column-half warps of a row write identical values)
     int* rc; int* cc;                 // [512]
     uint8_t* reg[2]; int* masked;     // region ids per item in COLUMN order (double-buffered)
     uint8_t* regq[2];                 // region ids per item in QUERY (natural) order
@@ -53,8 +54,8 @@ __device__ __forceinline__ BwdSmem bwd_carve(uint8_t* base, int Lpad) {
     uint8_t* p = base + BW_MISC_OFF;
     s.tab = (float*)p; p += (size_t)Lpad * 4;
     s.hist = (float*)p; p += (size_t)8 * Lpad * 4;
-    s.delta = (float*)p; p += 2 * 512 * 4;
-    s.lse2 = (float*)p; p += 2 * 512 * 4;
+    s.delta = (float*)p; p += 512 * 4;
+    s.lse2 = (float*)p; p += 512 * 4;
     s.rc = (int*)p; p += 512 * 4;
     s.cc = (int*)p; p += 512 * 4;
     s.kv_full = (uint64_t*)p; p += 8;
@@ -77,7 +78,7 @@ __device__ __forceinline__ BwdSmem bwd_carve(uint8_t* base, int Lpad) {
     return s;
 }
 size_t bwd_smem_bytes(int Lpad) {
-    return 1024 + BW_MISC_OFF + (size_t)9 * Lpad * 4 + 4 * 512 * 4 + 2 * 512 * 4 + 15 * 8 + 16 + 2048 + 16 + 64;
+    return 1024 + BW_MISC_OFF + (size_t)9 * Lpad * 4 + 2 * 512 * 4 + 2 * 512 * 4 + 15 * 8 + 16 + 2048 + 16 + 64;
 }
 
 // byte offset of the 16-byte unit holding keys [8u, 8u+8) of query row i inside a 128B-swizzled chunk
@@ -163,14 +164,25 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_const
     if (warp == 1) tc::tmem_alloc(s.tmem_slot, TMEM_COLS);
     // one-time shared-memory state: codes, bias column (x log2e), zeroed histograms and P/dS tiles
     if (threadIdx.x == 0) *s.batched = 1;
+    // padded bias / histogram layout: only if the codes really are this window's dense (dd, dh, dw) codes
+    int pad = p.pad;
+    if (pad) {
+        bool ok = p.rowcode[0] + p.colcode[0] == (p.L - 1) / 2;
+        for (int n = threadIdx.x; n < p.N && ok; n += NTHREADS) {
+            const int e = (n / (p.wh * p.ww)) * p.R1 + ((n / p.ww) % p.wh) * p.R2 + n % p.ww;
+            ok = p.rowcode[n] - p.rowcode[0] == e && p.colcode[0] - p.colcode[n] == e;
+        }
+        if (!__syncthreads_and(ok)) pad = 0;
+    }
     for (int n = threadIdx.x; n < 512; n += NTHREADS) {
-        s.rc[n] = n < p.N ? p.rowcode[n] : 0;
+        s.rc[n] = n < p.N ? p.rowcode[n] + (pad ? pad * ((n / p.ww) % p.wh) : 0) : 0;
         // column c' of the permuted key order holds key j = plane * hw + spatial index
         const int sp = n / p.wd, pl = n - sp * p.wd;
-        s.cc[n] = sp < p.hw ? p.colcode[pl * p.hw + sp] * 4 : 0;   // BYTE offsets into the fp32 table / histogram rows
+        const int j = pl * p.hw + sp;
+        s.cc[n] = sp < p.hw ? (p.colcode[j] + (pad ? pad * (p.wh - 1 - (j / p.ww) % p.wh) : 0)) * 4 : 0;   // BYTE offsets
     }
     for (int l = threadIdx.x; l < p.L; l += NTHREADS)
-        s.tab[l] = __bfloat162float(p.table[(long long)l * p.nH + h]) * LOG2E;
+        s.tab[pad ? l + pad * ((l % p.R1) / p.R2) : l] = __bfloat162float(p.table[(long long)l * p.nH + h]) * LOG2E;
     for (int l = threadIdx.x; l < 8 * p.Lpad; l += NTHREADS) s.hist[l] = 0.f;
     for (int i = threadIdx.x; i < 65536 / 16; i += NTHREADS)
         reinterpret_cast<uint4*>(base + BW_P_OFF)[i] = make_uint4(0, 0, 0, 0);
@@ -326,8 +338,8 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_const
         const int row = q * 32 + lane;
         const uint32_t lane_base = (uint32_t)(q * 32) << 16;
         float* hist = s.hist + (size_t)(warp - 4) * p.Lpad;
-        float* my_delta = s.delta + half * 512;
-        float* my_lse2 = s.lse2 + half * 512;
+        float* my_delta = s.delta;
+        float* my_lse2 = s.lse2;
         uint8_t* ptile = base + BW_P_OFF + half * 16384;    // this warp's 64-key chunk
         uint8_t* dstile = base + BW_DS_OFF + half * 16384;
         int it = 0; uint32_t sph = 0, dkvph = 0, dqph = 0;
@@ -604,7 +616,8 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_const
         for (int l = threadIdx.x; l < p.L; l += NTHREADS) {
             float t = 0.f;
 #pragma unroll
-            for (int w8 = 0; w8 < 8; ++w8) t += s.hist[(size_t)w8 * p.Lpad + l];
+            const int lp = pad ? l + pad * ((l % p.R1) / p.R2) : l;
+            for (int w8 = 0; w8 < 8; ++w8) t += s.hist[(size_t)w8 * p.Lpad + lp];
             part[l] = t;
         }
     }
@@ -640,10 +653,13 @@ size_t tc_attn_bwd_workspace(int B_, int N, int nH, int hd, int L) {
 
 int tc_attn_bwd(const void* qkv, const void* out, const void* dout, const float* lse, const void* table,
                 const int32_t* rowcode, const int32_t* colcode, const uint8_t* region, void* dqkv, float* dbias,
-                int B_, int nW, int N, int nH, int hd, int L, float scale, int planes, void* ws, size_t ws_bytes,
+                int B_, int nW, int N, int nH, int hd, int L, float scale, int window_dims, void* ws, size_t ws_bytes,
                 cudaStream_t st) {
-    const int Lpad = (L + 3) / 4 * 4;
+    BiasLayout bl = bias_layout(window_dims, L);
+    if (bwd_smem_bytes((bl.Lphys + 3) / 4 * 4) > 227 * 1024) bl = bias_layout(0, L);   // no room for the padded copies
+    const int Lpad = (bl.Lphys + 3) / 4 * 4;
     const size_t smem = bwd_smem_bytes(Lpad);
+    const int planes = window_dims & 0xFF;
     if (hd != HD || N > 448 || N < 1 || nH > kNumSMs || smem > 227 * 1024 || !aligned16(qkv) || !aligned16(out) ||
         !aligned16(dout) || !aligned16(dqkv)) {
         set_error("tcgen05 window attention bwd: needs head_dim 32, N <= 448, bias table fitting shared memory "
@@ -671,6 +687,7 @@ int tc_attn_bwd(const void* qkv, const void* out, const void* dout, const float*
     p.dqkv = (__nv_bfloat16*)dqkv; p.dbias_part = (float*)ws;
     p.B_ = B_; p.nW = nW; p.N = N; p.nH = nH; p.L = L; p.Lpad = Lpad; p.groups = groups;
     p.scale = scale; p.scale_log2 = scale * LOG2E;
+    p.wh = bl.wh; p.ww = bl.ww; p.R1 = bl.R1; p.R2 = bl.R2; p.pad = bl.pad;
     p.Npad = (N + 15) / 16 * 16; p.nq = (N + QT - 1) / QT;
     p.ntail = (N % QT != 0 && N % QT <= 8 && !getenv("VSW_ATTN_NO_TAIL")) ? N % QT : 0;
     p.wd = wd; p.hw = hw; p.boxhw = boxhw; p.nkb = (hw + boxhw - 1) / boxhw;

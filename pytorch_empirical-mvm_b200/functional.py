@@ -228,20 +228,27 @@ def linear_wgrad(dy, x2d, M, N, K, need_bias=True, grad_dtype=None):
     return dw, db
 
 
-def attn_fwd(qkv, table, rowcode, colcode, region, dense_mask, B_, nW, N, nH, hd, scale):
+def window_dims(planes=0, window=None):
+    """packed layout hint of the attention ABI: effective window depth | configured window height << 8 | width << 16"""
+    wh, ww = (int(window[1]), int(window[2])) if window is not None else (0, 0)
+    return (int(planes) & 0xFF) | ((wh & 0xFF) << 8) | ((ww & 0xFF) << 16)
+
+
+def attn_fwd(qkv, table, rowcode, colcode, region, dense_mask, B_, nW, N, nH, hd, scale, window=None):
     C = nH * hd
     out = _empty((B_ * N, C), qkv.dtype, qkv.device)
     lse = _empty((B_, nH, N), torch.float32, qkv.device)
     t0 = PROFILER.begin() if PROFILER is not None else None
     L.check(L.lib().vsw_window_attn_fwd(L.ptr(qkv), L.ptr(table), L.ptr(rowcode), L.ptr(colcode), L.ptr(region),
                                         L.ptr(dense_mask), L.ptr(out), L.ptr(lse), B_, nW, N, nH, hd, table.shape[0],
-                                        float(scale), L.dt(qkv), L.stream()), "vsw_window_attn_fwd")
+                                        float(scale), window_dims(0, window), L.dt(qkv), L.stream()), "vsw_window_attn_fwd")
     if t0 is not None:  # QK^T + PV = 4*N*N*hd flops per (window, head); q,k,v read + o written once
         PROFILER.end("window_attn_fwd", t0, 4.0 * B_ * nH * N * N * hd, 4 * B_ * N * C * _esz(qkv))
     return out, lse
 
 
-def attn_bwd(qkv, out, dout, lse, table, rowcode, colcode, region, dense_mask, B_, nW, N, nH, hd, scale, planes=0):
+def attn_bwd(qkv, out, dout, lse, table, rowcode, colcode, region, dense_mask, B_, nW, N, nH, hd, scale, planes=0,
+             window=None):
     dqkv = torch.empty_like(qkv)
     Lt = table.shape[0]
     dtable = _empty((Lt, nH), torch.float32, qkv.device)
@@ -250,7 +257,7 @@ def attn_bwd(qkv, out, dout, lse, table, rowcode, colcode, region, dense_mask, B
     t0 = PROFILER.begin() if PROFILER is not None else None
     L.check(L.lib().vsw_window_attn_bwd(L.ptr(qkv), L.ptr(out), L.ptr(dout), L.ptr(lse), L.ptr(table), L.ptr(rowcode),
                                         L.ptr(colcode), L.ptr(region), L.ptr(dense_mask), L.ptr(dqkv), L.ptr(dtable),
-                                        B_, nW, N, nH, hd, Lt, float(scale), int(planes), L.dt(qkv), L.ptr(ws), wsb,
+                                        B_, nW, N, nH, hd, Lt, float(scale), window_dims(planes, window), L.dt(qkv), L.ptr(ws), wsb,
                                         L.stream()),
             "vsw_window_attn_bwd")
     if t0 is not None:  # dV, dP, dQ, dK = 8*N*N*hd useful flops (the S/P recompute is not counted)
@@ -273,7 +280,7 @@ def _grad_to(g, like):
 class _AttnBranch(torch.autograd.Function):
     @staticmethod
     def forward(ctx, x, g1, b1, wqkv, bqkv, table, wproj, bproj, rowscale, plan: WindowPlan, rowcode, colcode,
-                dense_mask, nH, scale):
+                dense_mask, nH, scale, cfg_window=None):
         B, T, C = x.shape
         nW, N = plan.nW, plan.N
         hd = C // nH
@@ -282,12 +289,12 @@ class _AttnBranch(torch.autograd.Function):
         xw, mean, rstd = ln_fwd(x, g1, b1, plan.gather, B, T, R, C)
         qkv = linear_fwd(xw.view(B * R, C), wqkv, bqkv, B * R, 3 * C, C)
         region = plan.region if (plan.shifted and dense_mask is None) else None
-        o, lse = attn_fwd(qkv, table, rowcode, colcode, region, dense_mask, B * nW, nW, N, nH, hd, scale)
+        o, lse = attn_fwd(qkv, table, rowcode, colcode, region, dense_mask, B * nW, nW, N, nH, hd, scale, window=cfg_window)
         x1 = linear_fwd(o, wproj, bproj, B * R, C, C, epi=L.EPI_RESIDUAL, res=x, rowmap=plan.gather,
                         rowscale=rowscale, rows_per_batch=R, dst_rows_per_batch=T, out_rows=B * T).view(B, T, C)
         ctx.save_for_backward(x, g1, wqkv, table, wproj, rowscale, xw, mean, rstd, qkv, o, lse, rowcode, colcode,
                               dense_mask)
-        ctx.plan, ctx.nH, ctx.scale = plan, nH, scale
+        ctx.plan, ctx.nH, ctx.scale, ctx.cfg_window = plan, nH, scale, cfg_window
         ctx.has_qkv_bias = bqkv is not None
         return x1
 
@@ -309,14 +316,14 @@ class _AttnBranch(torch.autograd.Function):
         del a_buf
         region = plan.region if (plan.shifted and dense_mask is None) else None
         dqkv, dtable = attn_bwd(qkv, o, dO, lse, table, rowcode, colcode, region, dense_mask, B * nW, nW, N, nH, hd, scale,
-                                planes=plan.ws[0])
+                                planes=plan.ws[0], window=ctx.cfg_window)
         del dO
         dxw = linear_dgrad(dqkv, wqkv, M, 3 * C, C)
         dwq, dbq = linear_wgrad(dqkv, xw.view(M, C), M, 3 * C, C, need_bias=ctx.has_qkv_bias)
         del dqkv
         dx, dg1, db1 = ln_bwd(dxw, x, g1, mean, rstd, plan.gather, dx1, B, T, R, C)
         return (dx, _grad_to(dg1, g1), _grad_to(db1, g1), dwq, dbq, _grad_to(dtable, table), dwp, dbp,
-                None, None, None, None, None, None, None)
+                None, None, None, None, None, None, None, None)
 
 
 # ----------------------------------------------------------------------------------------------
@@ -363,16 +370,16 @@ class _MlpBranch(torch.autograd.Function):
 # ----------------------------------------------------------------------------------------------
 class _WindowAttention(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, xw, wqkv, bqkv, table, wproj, bproj, rowcode, colcode, dense_mask, nW, nH, scale):
+    def forward(ctx, xw, wqkv, bqkv, table, wproj, bproj, rowcode, colcode, dense_mask, nW, nH, scale, cfg_window=None):
         B_, N, C = xw.shape
         hd = C // nH
         M = B_ * N
         xw = _c(xw)
         qkv = linear_fwd(xw.view(M, C), wqkv, bqkv, M, 3 * C, C)
-        o, lse = attn_fwd(qkv, table, rowcode, colcode, None, dense_mask, B_, nW, N, nH, hd, scale)
+        o, lse = attn_fwd(qkv, table, rowcode, colcode, None, dense_mask, B_, nW, N, nH, hd, scale, window=cfg_window)
         y = linear_fwd(o, wproj, bproj, M, C, C).view(B_, N, C)
         ctx.save_for_backward(xw, wqkv, table, wproj, qkv, o, lse, rowcode, colcode, dense_mask)
-        ctx.nW, ctx.nH, ctx.scale, ctx.has_qkv_bias = nW, nH, scale, bqkv is not None
+        ctx.nW, ctx.nH, ctx.scale, ctx.has_qkv_bias, ctx.cfg_window = nW, nH, scale, bqkv is not None, cfg_window
         return y
 
     @staticmethod
@@ -385,10 +392,11 @@ class _WindowAttention(torch.autograd.Function):
         dy = _c(dy).view(M, C)
         dO = linear_dgrad(dy, wproj, M, C, C)
         dwp, dbp = linear_wgrad(dy, o, M, C, C)
-        dqkv, dtable = attn_bwd(qkv, o, dO, lse, table, rowcode, colcode, None, dense_mask, B_, ctx.nW, N, nH, hd, ctx.scale)
+        dqkv, dtable = attn_bwd(qkv, o, dO, lse, table, rowcode, colcode, None, dense_mask, B_, ctx.nW, N, nH, hd, ctx.scale,
+                                window=ctx.cfg_window)
         dxw = linear_dgrad(dqkv, wqkv, M, 3 * C, C).view(B_, N, C)
         dwq, dbq = linear_wgrad(dqkv, xw.view(M, C), M, 3 * C, C, need_bias=ctx.has_qkv_bias)
-        return dxw, dwq, dbq, _grad_to(dtable, table), dwp, dbp, None, None, None, None, None, None
+        return dxw, dwq, dbq, _grad_to(dtable, table), dwp, dbp, None, None, None, None, None, None, None
 
 
 # ----------------------------------------------------------------------------------------------
@@ -559,17 +567,20 @@ class _PatchEmbed(torch.autograd.Function):
 
 
 # public functional entry points --------------------------------------------------------------
-def attn_branch(x, g1, b1, wqkv, bqkv, table, wproj, bproj, rowscale, plan, rowcode, colcode, dense_mask, nH, scale):
+def attn_branch(x, g1, b1, wqkv, bqkv, table, wproj, bproj, rowscale, plan, rowcode, colcode, dense_mask, nH, scale,
+                cfg_window=None):
+    """cfg_window: the module's CONFIGURED window (whose relative_position_index produced the codes) -- a layout hint"""
     return _AttnBranch.apply(x, g1, b1, wqkv, bqkv, table, wproj, bproj, rowscale, plan, rowcode, colcode, dense_mask,
-                             nH, scale)
+                             nH, scale, cfg_window)
 
 
 def mlp_branch(x, g2, b2, w1, bb1, w2, bb2, rowscale):
     return _MlpBranch.apply(x, g2, b2, w1, bb1, w2, bb2, rowscale)
 
 
-def window_attention(xw, wqkv, bqkv, table, wproj, bproj, rowcode, colcode, dense_mask, nW, nH, scale):
-    return _WindowAttention.apply(xw, wqkv, bqkv, table, wproj, bproj, rowcode, colcode, dense_mask, nW, nH, scale)
+def window_attention(xw, wqkv, bqkv, table, wproj, bproj, rowcode, colcode, dense_mask, nW, nH, scale, cfg_window=None):
+    return _WindowAttention.apply(xw, wqkv, bqkv, table, wproj, bproj, rowcode, colcode, dense_mask, nW, nH, scale,
+                                  cfg_window)
 
 
 def mlp(x2d, w1, b1, w2, b2):

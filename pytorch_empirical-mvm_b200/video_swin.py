@@ -217,7 +217,7 @@ class WindowAttention3D(nn.Module):
             mask = _cast(mask, cd).contiguous()
         wq, bq, tab, wp, bp = self.params(cd)
         return VF.window_attention(_cast(x, cd), wq, bq, tab, wp, bp, rowcode, colcode, mask, nW, self.num_heads,
-                                   self.scale)
+                                   self.scale, cfg_window=self.window_size)
 
 
 class SwinTransformerBlock3D(nn.Module):
@@ -259,7 +259,7 @@ class SwinTransformerBlock3D(nn.Module):
         wq, bq, tab, wp, bp = self.attn.params(cd)
         y = VF.attn_branch(x.view(B, D * H * W, C), _cast(self.norm1.weight, cd), _cast(self.norm1.bias, cd), wq, bq,
                            tab, wp, bp, self._dp_scale(x), plan, rowcode, colcode, dense, self.num_heads,
-                           self.attn.scale)
+                           self.attn.scale, cfg_window=self.attn.window_size)
         return y.view(B, D, H, W, C)
 
     def _part2(self, x, cd):

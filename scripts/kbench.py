@@ -55,10 +55,10 @@ def attn_case(B, grid, nH, shifted, iters):
     att = vsw.WindowAttention3D(C, window, nH).cuda()
     rc, cc = att.bias_codes(N)
     region = plan.region if plan.shifted else None
-    out, lse = VF.attn_fwd(qkv, table, rc, cc, region, None, B_, nW, N, nH, 32, 32 ** -0.5)
+    out, lse = VF.attn_fwd(qkv, table, rc, cc, region, None, B_, nW, N, nH, 32, 32 ** -0.5, window=window)
     dout = torch.randn_like(out)
-    tf = timeit(lambda: VF.attn_fwd(qkv, table, rc, cc, region, None, B_, nW, N, nH, 32, 32 ** -0.5), iters)
-    tb = timeit(lambda: VF.attn_bwd(qkv, out, dout, lse, table, rc, cc, region, None, B_, nW, N, nH, 32, 32 ** -0.5, planes=8), iters)
+    tf = timeit(lambda: VF.attn_fwd(qkv, table, rc, cc, region, None, B_, nW, N, nH, 32, 32 ** -0.5, window=window), iters)
+    tb = timeit(lambda: VF.attn_bwd(qkv, out, dout, lse, table, rc, cc, region, None, B_, nW, N, nH, 32, 32 ** -0.5, planes=8, window=window), iters)
     fl = 4.0 * B_ * nH * N * N * 32
     return dict(kernel="window_attn", B_=B_, N=N, nH=nH, shifted=shifted, fwd_ms=tf, bwd_ms=tb,
                 fwd_tflops=fl / tf / 1e9, bwd_tflops=2 * fl / tb / 1e9,

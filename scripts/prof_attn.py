@@ -16,8 +16,8 @@ table = (torch.randn(2535, nH, device="cuda") * 0.1).bfloat16()
 att = vsw.WindowAttention3D(C, window, nH).cuda()
 rc, cc = att.bias_codes(N)
 for _ in range(2):
-    out, lse = VF.attn_fwd(qkv, table, rc, cc, plan.region, None, B_, nW, N, nH, 32, 32 ** -0.5)
+    out, lse = VF.attn_fwd(qkv, table, rc, cc, plan.region, None, B_, nW, N, nH, 32, 32 ** -0.5, window=window)
     dout = torch.randn_like(out)
-    VF.attn_bwd(qkv, out, dout, lse, table, rc, cc, plan.region, None, B_, nW, N, nH, 32, 32 ** -0.5, planes=8)
+    VF.attn_bwd(qkv, out, dout, lse, table, rc, cc, plan.region, None, B_, nW, N, nH, 32, 32 ** -0.5, planes=8, window=window)
 torch.cuda.synchronize()
 print("done")

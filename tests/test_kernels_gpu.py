@@ -202,6 +202,10 @@ def test_window_attention_fwd_bwd(vsw, oracle, dtype, geom, backend):
     out, lse = VF.attn_fwd(qkv.view(B_ * N, -1), table, rowcode, colcode, plan.region, None, B_, nW, N, nH, hd, hd ** -0.5)
     assert rel_l2(out.view(B_, N, -1), oref) < TOL[dtype]
     assert rel_l2(lse, lref) < (1e-5 if dtype == torch.float32 else 1e-2)
+    # with the configured window as layout hint (padded on-chip bias table in the tcgen05 kernels): same result
+    out_h, lse_h = VF.attn_fwd(qkv.view(B_ * N, -1), table, rowcode, colcode, plan.region, None, B_, nW, N, nH, hd, hd ** -0.5,
+                               window=window)
+    assert rel_l2(out_h.view(B_, N, -1), oref) < TOL[dtype] and rel_l2(lse_h, lref) < (1e-5 if dtype == torch.float32 else 1e-2)
     if plan.shifted:  # the dense-mask path must agree with the region-id path
         L.set_gemm_backend(L.GEMM_SIMT)
         out2, _ = VF.attn_fwd(qkv.view(B_ * N, -1), table, rowcode, colcode, None, mask.to(dtype), B_, nW, N, nH, hd, hd ** -0.5)
@@ -215,6 +219,9 @@ def test_window_attention_fwd_bwd(vsw, oracle, dtype, geom, backend):
     for i, nm in enumerate("qkv"):
         assert rel_l2(dq[:, :, i], qr.grad[:, :, i]) < TOL[dtype] * (1 if dtype == torch.float32 else 1.5), nm
     assert rel_l2(dtab, tr.grad) < TOL[dtype] * (1 if dtype == torch.float32 else 1.5)
+    dqkv_h, dtab_h = VF.attn_bwd(qkv.view(B_ * N, -1), out, dout.view(B_ * N, -1), lse, table, rowcode, colcode, plan.region,
+                                 None, B_, nW, N, nH, hd, hd ** -0.5, planes=plan.ws[0], window=window)
+    assert rel_l2(dqkv_h, dqkv) < 1e-3 and rel_l2(dtab_h, tr.grad) < TOL[dtype] * (1 if dtype == torch.float32 else 1.5)
 
 
 @pytest.mark.parametrize("case", ["huge_logits", "huge_bias"])
