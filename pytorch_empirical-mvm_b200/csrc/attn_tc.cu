@@ -146,13 +146,12 @@ __device__ __forceinline__ float mask_add(float v, const uint32_t (&w)[4], int e
     return (w[e >> 2] & (0xFFu << (8 * (e & 3)))) ? v + MASKV : v;
 }
 
-// squared L2 norm of one head row (32 bf16 = 64 B, 16-byte aligned) in global memory
-__device__ __forceinline__ float row_norm2(const __nv_bfloat16* rowp) {
-    const uint4* v4 = reinterpret_cast<const uint4*>(rowp);
+// squared L2 norm of one head row (64 B) already staged in shared memory (the 64-byte swizzle only permutes its 16-byte units)
+__device__ __forceinline__ float row_norm2_smem(uint32_t row_addr) {
     float acc = 0.f;
 #pragma unroll
     for (int v = 0; v < 4; ++v) {
-        const uint4 a = __ldg(v4 + v);
+        const uint4 a = tc::lds_u4(row_addr + v * 16);
         const uint32_t w[4] = {a.x, a.y, a.z, a.w};
 #pragma unroll
         for (int e = 0; e < 4; ++e) {
@@ -257,13 +256,17 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const FwdParams p)
     const Smem s = carve(base, p.Lpad);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int C = p.nH * HD;
+    // Work items = (head, window) pairs in HEAD-MAJOR order, one contiguous range per CTA: a CTA then stays on one head
+    // for (almost) all its items, so the bias column is loaded into shared memory once instead of once per item.
     const int items = p.B_ * p.nH;
+    const int w_begin = (int)blockIdx.x * (items / (int)gridDim.x) + min((int)blockIdx.x, items % (int)gridDim.x);
+    const int w_end = w_begin + items / (int)gridDim.x + ((int)blockIdx.x < items % (int)gridDim.x ? 1 : 0);
 
     if (warp == 0 && lane == 0) {
         tc::prefetch_tmap(&tmQKV);
         for (int i = 0; i < 2; ++i) {
             tc::mbar_init(&s.qkv_full[i], 1); tc::mbar_init(&s.qkv_empty[i], 1);
-            tc::mbar_init(&s.aux_full[i], 1); tc::mbar_init(&s.aux_empty[i], 4 * NPARTS);
+            tc::mbar_init(&s.aux_full[i], 2); tc::mbar_init(&s.aux_empty[i], 4 * NPARTS);
         }
         tc::mbar_init(s.o_full, 1);
         for (int i = 0; i < NHALF; ++i) { tc::mbar_init(&s.s_full[i], 1); tc::mbar_init(&s.p_full[i], 4 * NPARTS); }
@@ -296,9 +299,9 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const FwdParams p)
         // ===================== TMA producer =====================
         if (lane == 0) {
             int it = 0;
-            for (int w = blockIdx.x; w < items; w += gridDim.x, ++it) {
+            for (int w = w_begin; w < w_end; ++w, ++it) {
                 const int st = it & 1; const uint32_t ph = (it >> 1) & 1;
-                const int b_ = w / p.nH, h = w - b_ * p.nH;
+                const int h = w / p.B_, b_ = w - h * p.B_;
                 tc::mbar_wait(&s.qkv_empty[st], ph ^ 1);
                 tc::mbar_expect_tx(&s.qkv_full[st], 3 * p.nq * BOX_BYTES);
                 for (int which = 0; which < 3; ++which)
@@ -318,7 +321,7 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const FwdParams p)
             const uint32_t idesc_l = tc::idesc_bf16(QT, 16, 0, 1);
             const uint64_t ones_desc = tc::smem_desc_sw64(tc::smem_u32(s.ones), 0, 512);   // all ones: only the 1 KB footprint matters
             const int hbeg[NHALF] = {0, p.h0}, hlen[NHALF] = {p.h0, p.Npad - p.h0};
-            for (int w = blockIdx.x; w < items; w += gridDim.x, ++it) {
+            for (int w = w_begin; w < w_end; ++w, ++it) {
                 const int st = it & 1; const uint32_t ph = (it >> 1) & 1;
                 tc::mbar_wait(&s.qkv_full[st], ph);
                 tc::tc_fence_after();
@@ -360,43 +363,58 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const FwdParams p)
                 tc::umma_commit(&s.qkv_empty[st]);
             }
         }
-    } else if (warp == 2) {
-        // ===================== aux loader: bias-table column (x log2e), region ids =====================
+    } else if (warp == 2 || warp == 3) {
+        // ===================== aux warps: bias-table column (x log2e), region ids, |q|^2 and max |k|^2 =====================
+        // warp 2: bias column (only when the head differs from what the stage holds) and max_j |k_j|^2;
+        // warp 3: region ids of the window and |q_i|^2.  The norms are taken from the TMA-staged Q / K tiles in shared memory.
         int it = 0;
-        for (int w = blockIdx.x; w < items; w += gridDim.x, ++it) {
+        int tab_head[2] = {-1, -1};
+        for (int w = w_begin; w < w_end; ++w, ++it) {
             const int st = it & 1; const uint32_t ph = (it >> 1) & 1;
-            const int b_ = w / p.nH, h = w - b_ * p.nH, win = b_ % p.nW;
+            const int h = w / p.B_, b_ = w - h * p.B_, win = b_ % p.nW;
+            long long ax_a = clock64();
             tc::mbar_wait(&s.aux_empty[st], ph ^ 1);
-            float mb = -INFINITY, nb = -INFINITY;   // max and -min of the bias column
-            for (int l = lane; l < p.L; l += 32) {
-                const float v = __bfloat162float(p.table[(long long)l * p.nH + h]) * LOG2E;
-                s.tab[st][pad ? l + pad * bias_dh(l, p.R1, p.R2, p.M1, p.M2) : l] = v;   // padded layout (bias_layout())
-                mb = fmaxf(mb, v);
-                nb = fmaxf(nb, -v);
-            }
-            mb = warp_max(mb);
-            nb = warp_max(nb);
-            int diff = 0;
-            if (p.region) {
-                const uint8_t* rg = p.region + (long long)win * p.N;
-                const uint8_t r0 = rg[0];
-                for (int n = lane; n < p.N; n += 32) {
-                    const uint8_t r = rg[n];
-                    s.reg[st][n] = r;
-                    diff |= (r != r0);
+            long long ax_b = clock64();
+            if (warp == 2) {
+                if (tab_head[st] != h) {
+                    tab_head[st] = h;
+                    float mb = -INFINITY, nb = -INFINITY;   // max and -min of the bias column
+                    for (int l = lane; l < p.L; l += 32) {
+                        const float v = __bfloat162float(p.table[(long long)l * p.nH + h]) * LOG2E;
+                        s.tab[st][pad ? l + pad * bias_dh(l, p.R1, p.R2, p.M1, p.M2) : l] = v;   // padded layout (bias_layout())
+                        mb = fmaxf(mb, v);
+                        nb = fmaxf(nb, -v);
+                    }
+                    mb = warp_max(mb);
+                    nb = warp_max(nb);
+                    if (lane == 0) { s.maxbias[st] = mb; s.k2max[2 + st] = -nb; }
                 }
+                tc::mbar_wait(&s.qkv_full[st], ph);
+                const uint32_t ka = tc::smem_u32(s.stage[st]) + OPER_BYTES;
+                float k2 = 0.f;   // max_j |k_j|^2: with |q_i| it bounds the scores of row i (Cauchy-Schwarz)
+                for (int n = lane; n < p.N; n += 32) k2 = fmaxf(k2, row_norm2_smem(ka + n * 64));
+                k2 = warp_max(k2);
+                if (lane == 0) s.k2max[st] = k2;
+            } else {
+                int diff = 0;
+                if (p.region) {
+                    const uint8_t* rg = p.region + (long long)win * p.N;
+                    const uint8_t r0 = rg[0];
+                    for (int n = lane; n < p.N; n += 32) {
+                        const uint8_t r = rg[n];
+                        s.reg[st][n] = r;
+                        diff |= (r != r0);
+                    }
+                }
+                diff = __any_sync(0xffffffffu, diff);
+                if (lane == 0) s.masked[st] = diff;
+                tc::mbar_wait(&s.qkv_full[st], ph);
+                const uint32_t qa = tc::smem_u32(s.stage[st]);
+                for (int n = lane; n < p.N; n += 32) s.q2[st][n] = row_norm2_smem(qa + n * 64);
             }
-            diff = __any_sync(0xffffffffu, diff);
-            float k2 = 0.f;   // max_j |k_j|^2: with |q_i| it bounds the scores of row i (Cauchy-Schwarz)
-            for (int n = lane; n < p.N; n += 32) {
-                const __nv_bfloat16* rowp = p.qkv + (((long long)b_ * p.N + n) * 3) * C + h * HD;
-                k2 = fmaxf(k2, row_norm2(rowp + C));
-                s.q2[st][n] = row_norm2(rowp);
-            }
-            k2 = warp_max(k2);
-            if (lane == 0) { s.maxbias[st] = mb; s.masked[st] = diff; s.k2max[st] = k2; s.k2max[2 + st] = -nb; }
             __syncwarp();
             if (lane == 0) tc::mbar_arrive(&s.aux_full[st]);
+            if (p.dbg && blockIdx.x == 0 && threadIdx.x == 64) { p.dbg[6] += ax_b - ax_a; p.dbg[7] += clock64() - ax_b; }
         }
     } else if (warp >= 4) {
         // ===================== softmax + epilogue warps =====================
@@ -415,9 +433,47 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const FwdParams p)
         }
         const int nfull = p.N & ~15;                      // chunks below nfull have no padded columns
         int it = 0; uint32_t sph = 0, oph = 0;
-        for (int w = blockIdx.x; w < items; w += gridDim.x, ++it) {
+        int pend_b = -1, pend_h = 0; float pend_mx = 0.f;   // item whose last tile still awaits its epilogue
+        // ---- epilogue of tile te: O / l -> bf16 -> global; lse.  Runs one tile late (after the first half of
+        //      the next tile's softmax) so the wait for the P.V MMAs is hidden; the next tile's P.V cannot
+        //      start before every warp has passed this point (it needs their p_full[0] arrival).
+        auto epilogue = [&](int eb, int eh, int te, float mxe) {   // (window, head) of the tile's item, tile, row max
+            const int ie = te * QT + row;
+            long long t_d = clock64();
+            tc::mbar_wait(s.o_full, oph); oph ^= 1;
+            tc::tc_fence_after();
+            long long t_e = clock64();
+            uint32_t o[16], lr[16];
+            tc::tmem_ld_32x16(tmem + lane_base + O_COL + (part & 1) * 16, o);
+            tc::tmem_ld_32x16(tmem + lane_base + L_COL, lr);   // 16 identical columns of the row sum
+            tc::tmem_ld_wait();
+            const float l = __uint_as_float(lr[0]);
+            const float inv = __fdividef(1.0f, l);
+            if (ie < p.N && part < 2) {
+                __nv_bfloat16* dst = p.out + ((long long)eb * p.N + ie) * C + eh * HD + part * 16;
+                uint4 u0, u1;
+                u0.x = tc::pack_bf16(__uint_as_float(o[0]) * inv, __uint_as_float(o[1]) * inv);
+                u0.y = tc::pack_bf16(__uint_as_float(o[2]) * inv, __uint_as_float(o[3]) * inv);
+                u0.z = tc::pack_bf16(__uint_as_float(o[4]) * inv, __uint_as_float(o[5]) * inv);
+                u0.w = tc::pack_bf16(__uint_as_float(o[6]) * inv, __uint_as_float(o[7]) * inv);
+                u1.x = tc::pack_bf16(__uint_as_float(o[8]) * inv, __uint_as_float(o[9]) * inv);
+                u1.y = tc::pack_bf16(__uint_as_float(o[10]) * inv, __uint_as_float(o[11]) * inv);
+                u1.z = tc::pack_bf16(__uint_as_float(o[12]) * inv, __uint_as_float(o[13]) * inv);
+                u1.w = tc::pack_bf16(__uint_as_float(o[14]) * inv, __uint_as_float(o[15]) * inv);
+                reinterpret_cast<uint4*>(dst)[0] = u0;
+                reinterpret_cast<uint4*>(dst)[1] = u1;
+                if (part == 0) p.lse[((long long)eb * p.nH + eh) * p.N + ie] = (mxe + __log2f(l)) * LN2;
+            }
+            tc::tc_fence_before();  // O reads complete before the next p_full arrive lets P.V overwrite O
+            if (p.dbg && blockIdx.x == 0 && threadIdx.x == 128) {
+                long long t_f = clock64();
+                p.dbg[3] += t_e - t_d; p.dbg[4] += t_f - t_e;
+            }
+        };
+
+        for (int w = w_begin; w < w_end; ++w, ++it) {
             const int st = it & 1; const uint32_t ph = (it >> 1) & 1;
-            const int b_ = w / p.nH, h = w - b_ * p.nH;
+            const int h = w / p.B_, b_ = w - h * p.B_;
             tc::mbar_wait(&s.aux_full[st], ph);
             const bool masked = s.masked[st] != 0;
             const float mb = s.maxbias[st];
@@ -426,43 +482,6 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const FwdParams p)
             const float* tab = s.tab[st];
             const uint8_t* reg = s.reg[st];
             const uint32_t reg_a = tc::smem_u32(reg), cc_a = tc::smem_u32(s.cc);
-
-            // ---- epilogue of tile te: O / l -> bf16 -> global; lse.  Runs one tile late (after the first half of
-            //      the next tile's softmax) so the wait for the P.V MMAs is hidden; the next tile's P.V cannot
-            //      start before every warp has passed this point (it needs their p_full[0] arrival).
-            auto epilogue = [&](int te, float mxe) {
-                const int ie = te * QT + row;
-                long long t_d = clock64();
-                tc::mbar_wait(s.o_full, oph); oph ^= 1;
-                tc::tc_fence_after();
-                long long t_e = clock64();
-                uint32_t o[16], lr[16];
-                tc::tmem_ld_32x16(tmem + lane_base + O_COL + (part & 1) * 16, o);
-                tc::tmem_ld_32x16(tmem + lane_base + L_COL, lr);   // 16 identical columns of the row sum
-                tc::tmem_ld_wait();
-                const float l = __uint_as_float(lr[0]);
-                const float inv = __fdividef(1.0f, l);
-                if (ie < p.N && part < 2) {
-                    __nv_bfloat16* dst = p.out + ((long long)b_ * p.N + ie) * C + h * HD + part * 16;
-                    uint4 u0, u1;
-                    u0.x = tc::pack_bf16(__uint_as_float(o[0]) * inv, __uint_as_float(o[1]) * inv);
-                    u0.y = tc::pack_bf16(__uint_as_float(o[2]) * inv, __uint_as_float(o[3]) * inv);
-                    u0.z = tc::pack_bf16(__uint_as_float(o[4]) * inv, __uint_as_float(o[5]) * inv);
-                    u0.w = tc::pack_bf16(__uint_as_float(o[6]) * inv, __uint_as_float(o[7]) * inv);
-                    u1.x = tc::pack_bf16(__uint_as_float(o[8]) * inv, __uint_as_float(o[9]) * inv);
-                    u1.y = tc::pack_bf16(__uint_as_float(o[10]) * inv, __uint_as_float(o[11]) * inv);
-                    u1.z = tc::pack_bf16(__uint_as_float(o[12]) * inv, __uint_as_float(o[13]) * inv);
-                    u1.w = tc::pack_bf16(__uint_as_float(o[14]) * inv, __uint_as_float(o[15]) * inv);
-                    reinterpret_cast<uint4*>(dst)[0] = u0;
-                    reinterpret_cast<uint4*>(dst)[1] = u1;
-                    if (part == 0) p.lse[((long long)b_ * p.nH + h) * p.N + ie] = (mxe + __log2f(l)) * LN2;
-                }
-                tc::tc_fence_before();  // O reads complete before the next p_full arrive lets P.V overwrite O
-                if (p.dbg && blockIdx.x == 0 && threadIdx.x == 128) {
-                    long long t_f = clock64();
-                    p.dbg[3] += t_e - t_d; p.dbg[4] += t_f - t_e;
-                }
-            };
 
             float mx_prev = 0.f;
             for (int t = 0; t < p.nq; ++t) {
@@ -560,7 +579,9 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const FwdParams p)
                             tc::tmem_st_32x8(prow + (c - qb) / 2, pw);
                         }
                     }
-                    if (hh == 0 && t > 0) epilogue(t - 1, mx_prev);
+                    // deferred epilogue of the previous tile -- which, for tile 0, is the LAST tile of the previous item
+                    if (hh == 0 && t > 0) epilogue(b_, h, t - 1, mx_prev);
+                    if (hh == 0 && t == 0 && pend_b >= 0) epilogue(pend_b, pend_h, p.nq - 1, pend_mx);
                     tc::tmem_st_wait();
                     tc::tc_fence_before();
                     __syncwarp();
@@ -573,10 +594,11 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const FwdParams p)
                     p.dbg[0] += t_b - t_a; p.dbg[1] += t_c - t_b; p.dbg[2] += t_d - t_c; p.dbg[5] += 1;
                 }
             }
-            epilogue(p.nq - 1, mx_prev);
+            pend_b = b_; pend_h = h; pend_mx = mx_prev;   // the last tile's epilogue runs inside the next item's first tile
             __syncwarp();
             if (lane == 0) tc::mbar_arrive(&s.aux_empty[st]);
         }
+        if (pend_b >= 0) epilogue(pend_b, pend_h, p.nq - 1, pend_mx);   // the CTA's very last tile
     }
 
     tc::tc_fence_before();
@@ -626,7 +648,7 @@ int tc_attn_fwd(const void* qkv, const void* table, const int32_t* rowcode, cons
         if (dbg && getenv("VSW_ATTN_DEBUG_DUMP")) {
             long long h[8];
             cudaMemcpy(h, dbg, 64, cudaMemcpyDeviceToHost);
-            if (h[5]) fprintf(stderr, "[vsw attn fwd] tiles=%lld avg cycles: wait_s=%lld pass1=%lld pass2=%lld wait_o=%lld epi=%lld\n", h[5], h[0]/h[5], h[1]/h[5], h[2]/h[5], h[3]/h[5], h[4]/h[5]);
+            if (h[5]) fprintf(stderr, "[vsw attn fwd] tiles=%lld avg cycles: wait_s=%lld pass1=%lld pass2=%lld wait_o=%lld epi=%lld | aux warp per item: wait %lld work %lld\n", h[5], h[0]/h[5], h[1]/h[5], h[2]/h[5], h[3]/h[5], h[4]/h[5], h[6] * 4 / h[5], h[7] * 4 / h[5]);
             cudaMemset(dbg, 0, 64);
         }
     }
