@@ -108,3 +108,31 @@ def test_init_weights_statistics(vsw):
     with pytest.raises(TypeError):
         m.pretrained = 3
         m.init_weights()
+
+
+def test_window_dims_hint_packing(vsw):
+    """layout hint of the attention ABI: effective depth | configured height << 8 | configured width << 16"""
+    VF = vsw.functional
+    assert VF.window_dims() == 0
+    assert VF.window_dims(8) == 8
+    assert VF.window_dims(8, (8, 7, 7)) == 8 | (7 << 8) | (7 << 16)
+    assert VF.window_dims(0, (8, 12, 12)) == (12 << 8) | (12 << 16)
+    # every attention module hands its configured window to the kernels
+    att = vsw.WindowAttention3D(64, (4, 6, 6), 2)
+    assert tuple(att.window_size) == (4, 6, 6)
+
+
+def test_bias_codes_are_dense_toeplitz(vsw, oracle):
+    """the codes the kernels validate in-kernel before padding their on-chip table: rowcode[n] - rowcode[0] ==
+    colcode[0] - colcode[n] == d R1 + h R2 + w and rowcode[0] + colcode[0] == (L - 1) / 2 (centre of the table)"""
+    VF = vsw.functional
+    for wd, wh, ww in [(8, 7, 7), (4, 6, 6), (2, 3, 5)]:
+        idx = torch.from_numpy(oracle.relative_position_index((wd, wh, ww)))
+        N = wd * wh * ww
+        rc, cc = VF.bias_codes(idx, N)
+        R2, R1 = 2 * ww - 1, (2 * wh - 1) * (2 * ww - 1)
+        L = (2 * wd - 1) * R1
+        n = torch.arange(N)
+        e = (n // (wh * ww)) * R1 + ((n // ww) % wh) * R2 + n % ww
+        assert torch.equal(rc.cpu().long() - int(rc[0]), e) and torch.equal(int(cc[0]) - cc.cpu().long(), e)
+        assert int(rc[0]) + int(cc[0]) == (L - 1) // 2
