@@ -181,6 +181,7 @@ def main():
     model = model.to(dev).bfloat16().train()
     net = model
     dp_mode = os.environ.get("VSW_DP_MODE", "coalesced") if world > 1 else "none"
+    reducer = vsw.dp.OverlappedGradReducer(model) if dp_mode == "overlap" else None
     if world > 1 and dp_mode == "ddp":
         from torch.nn.parallel import DistributedDataParallel as DDP
         net = DDP(model, device_ids=[local_rank], gradient_as_bucket_view=True,
@@ -203,6 +204,8 @@ def main():
         loss.backward()
         if dp_mode == "coalesced" and module is None:
             vsw.dp.all_reduce_gradients_coalesced(model.parameters())   # the one exchange step (NCCL, in place, averaged)
+        elif dp_mode == "overlap" and module is None:
+            reducer.finish()   # per-block coalesced all-reduces were launched from autograd hooks during backward
         return loss
 
     def barrier():
@@ -273,6 +276,8 @@ def main():
                "h2d_bytes_per_step_per_gpu": x_host.numel() * x_host.element_size(),
                "pipeline": "H2D of step i+1 on a copy stream overlaps the compute of step i (double-buffered)"}
 
+    if reducer is not None:
+        reducer.remove()   # the next leg runs on rank 0 alone: no collective may be issued from its backward
     # ---- roofline of the dominant kernel family: per-launch CUDA events on the launching stream
     roofline, families = None, None
     if rank == 0:

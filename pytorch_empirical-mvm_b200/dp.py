@@ -78,3 +78,73 @@ def all_reduce_gradients_coalesced(params: Iterable[torch.Tensor]) -> int:
             dist.all_reduce(g, op=dist.ReduceOp.AVG)
     cm.wait()
     return len(grads)
+
+
+class OverlappedGradReducer:
+    """The exchange step overlapped with backward, still copy-free: parameters are grouped (one group per direct child of
+    every ``nn.ModuleList`` / top-level sub-module, i.e. one per Swin block), and as soon as autograd has accumulated the
+    gradient of the last parameter of a group the group's ``.grad`` tensors are averaged in place by ONE coalesced, asynchronous
+    NCCL call.  ``finish()`` (after ``loss.backward()``) reduces whatever is left and waits for all outstanding calls."""
+
+    def __init__(self, module: torch.nn.Module):
+        self.groups: List[List[torch.nn.Parameter]] = []
+        seen = set()
+
+        def add(mod):
+            ps = [p for p in mod.parameters() if p.requires_grad and id(p) not in seen]
+            if ps:
+                seen.update(id(p) for p in ps)
+                self.groups.append(ps)
+
+        def walk(mod):
+            for child in mod.children():
+                if isinstance(child, torch.nn.ModuleList) or any(isinstance(c, torch.nn.ModuleList) for c in child.children()):
+                    walk(child)
+                else:
+                    add(child)
+            add(mod)   # parameters held directly by `mod`
+        walk(module)
+        self._left = [len(g) for g in self.groups]
+        self._launched = [False] * len(self.groups)
+        self._works = []
+        self._hooks = []
+        for gi, g in enumerate(self.groups):
+            for p in g:
+                self._hooks.append(p.register_post_accumulate_grad_hook(lambda _p, gi=gi: self._ready(gi)))
+
+    def _launch(self, gi: int) -> None:
+        grads = [p.grad for p in self.groups[gi] if p.grad is not None]
+        self._launched[gi] = True
+        if not grads or not dist.is_initialized() or dist.get_world_size() == 1:
+            return
+        if dist.get_backend() != "nccl":
+            for g in grads:
+                dist.all_reduce(g, op=dist.ReduceOp.SUM)
+                g.div_(dist.get_world_size())
+            return
+        with dist._coalescing_manager(device=grads[0].device, async_ops=True) as cm:
+            for g in grads:
+                dist.all_reduce(g, op=dist.ReduceOp.AVG)
+        self._works.append(cm)
+
+    def _ready(self, gi: int) -> None:
+        self._left[gi] -= 1
+        if self._left[gi] == 0 and not self._launched[gi]:
+            self._launch(gi)
+
+    def finish(self) -> int:
+        """call after backward: reduce groups whose parameters did not all receive a gradient, wait, re-arm; returns #groups"""
+        for gi in range(len(self.groups)):
+            if not self._launched[gi]:
+                self._launch(gi)
+        for cm in self._works:
+            cm.wait()
+        self._works.clear()
+        self._left = [len(g) for g in self.groups]
+        self._launched = [False] * len(self.groups)
+        return len(self.groups)
+
+    def remove(self) -> None:
+        for h in self._hooks:
+            h.remove()
+        self._hooks.clear()

@@ -65,6 +65,69 @@ def _worker(rank, world, port, tmpdir):
         dist.destroy_process_group()
 
 
+def _worker_overlap(rank, world, port, tmpdir):
+    """OverlappedGradReducer: hooks launch one reduction per block during backward; result == full-batch gradients"""
+    sys.path.insert(0, ROOT)
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        dp = importlib.import_module("pytorch_empirical-mvm_b200.dp")
+
+        class Block(torch.nn.Module):
+            def __init__(self):
+                super().__init__()
+                self.a, self.b = torch.nn.Linear(8, 8), torch.nn.Linear(8, 8)
+
+            def forward(self, x):
+                return x + self.b(torch.tanh(self.a(x)))
+
+        class Net(torch.nn.Module):
+            def __init__(self):
+                super().__init__()
+                self.embed = torch.nn.Linear(4, 8)
+                self.layers = torch.nn.ModuleList([torch.nn.ModuleList([Block(), Block()]), torch.nn.ModuleList([Block()])])
+                self.unused = torch.nn.Linear(3, 3)   # never receives a gradient: finish() must cope
+                self.head = torch.nn.Linear(8, 2)
+
+            def forward(self, x):
+                x = self.embed(x)
+                for stage in self.layers:
+                    for blk in stage:
+                        x = blk(x)
+                return self.head(x)
+
+        torch.manual_seed(0)
+        net, ref = Net().double(), Net().double()
+        ref.load_state_dict(net.state_dict())
+        red = dp.OverlappedGradReducer(net)
+        assert len(red.groups) == 6   # embed, 3 blocks, unused, head
+        g = torch.Generator().manual_seed(3)
+        x, t = torch.randn(6, 4, generator=g).double(), torch.randn(6, 2, generator=g).double()
+        sl = dp.clip_shard(6, rank, world)
+        for _ in range(2):   # two steps: the reducer re-arms itself
+            net.zero_grad(set_to_none=True)
+            ((net(x[sl]) - t[sl]) ** 2).sum().mul(world / 6).backward()
+            red.finish()
+        ref.zero_grad(set_to_none=True)
+        ((ref(x) - t) ** 2).sum().div(6).backward()
+        for (n, p), (_, q) in zip(net.named_parameters(), ref.named_parameters()):
+            if q.grad is None:
+                assert p.grad is None, n
+            else:
+                assert torch.allclose(p.grad, q.grad, rtol=1e-9, atol=1e-12), n
+        with open(os.path.join(tmpdir, f"ok{rank}"), "w") as f:
+            f.write("ok")
+    finally:
+        dist.destroy_process_group()
+
+
+def test_overlapped_grad_reducer_gloo(tmp_path):
+    world, port = 2, 29000 + os.getpid() % 1000 + 1
+    mp.spawn(_worker_overlap, args=(world, port, str(tmp_path)), nprocs=world, join=True)
+    assert all(os.path.exists(os.path.join(str(tmp_path), f"ok{r}")) for r in range(world))
+
+
 def test_clip_shard_covers_batch():
     dp = importlib.import_module("pytorch_empirical-mvm_b200.dp")
     for n in (1, 5, 32, 33):
