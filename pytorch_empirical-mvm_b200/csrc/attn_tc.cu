@@ -1,17 +1,20 @@
 // tcgen05 / TMEM fused window attention for sm_100a (bf16, head_dim 32, N <= 448 tokens per window).
 // Reference op: WindowAttention3D.forward, visbackbone/video_swin.py:149-169.
 //
-// One persistent CTA per SM walks (window, head) work items.  Per item the whole Q, K, V of the head
-// (N x 32 bf16 each) is TMA-loaded into 64-byte-swizzled shared memory (double-buffered across items,
-// 3-D tensor map so rows >= N read as zero), then for each 128-query tile:
-//   S = Q K^T        tcgen05.mma (SS), fp32 accumulator 128 x Npad in TMEM (whole key range: no online rescale)
-//   softmax          8 warps, one thread per (row, column half): pass 1 row max over TMEM, pass 2
-//                    exp2(S*scale*log2e + bias*log2e [+ mask] - max) with the relative-position bias looked up
-//                    from a shared-memory copy of the table column (index = rowcode[i] + colcode[j]) and the
-//                    shift mask derived from uint8 region ids -- nothing N x N ever exists in HBM;
+// One persistent CTA per SM walks a contiguous range of (head, window) work items (head-major, so the bias column stays
+// in shared memory).  Per item the whole Q, K, V of the head (N x 32 bf16 each) is TMA-loaded into 64-byte-swizzled shared
+// memory (double-buffered across items, 3-D tensor map so rows >= N read as zero), then for each 128-query tile:
+//   S = Q K^T        tcgen05.mma (SS), fp32 accumulators in TMEM over the whole key range (no online rescale), issued as two
+//                    key halves so that S of one half / the next tile is computed while the softmax warps work on the other
+//   softmax          12 warps (3 column parts x 4 TMEM lane quadrants), one thread per row and part:
+//                    p = exp2(S*scale*log2e + bias*log2e [+ mask]) with the relative-position bias gathered from a padded
+//                    shared-memory copy of the table column (index = rowcode[i] + colcode[j]) and the shift mask derived from
+//                    uint8 region ids -- nothing N x N ever exists in HBM.  No max is subtracted when |score| and |bias| are
+//                    provably <= 50 log2 units (Cauchy-Schwarz bound from |q_i|, max|k_j|); otherwise an exact two-pass path.
 //                    P is written back to TMEM as packed bf16, aliasing S
-//   O = P V          tcgen05.mma (TS: A = P from TMEM, B = V MN-major from smem), 128 x 32 fp32 in TMEM
-//   epilogue         O / rowsum -> bf16 -> global, log-sum-exp -> global (for the recompute backward)
+//   O = P V, l = P 1 tcgen05.mma (TS: A = P from TMEM, B = V MN-major from smem / a tile of ones): 128 x 32 (+16) fp32 in TMEM
+//   epilogue         O / l -> bf16 -> global, log-sum-exp -> global (for the recompute backward); deferred by one tile
+// Two aux warps stage the per-item side data (bias column when the head changes, region ids, |q|^2, max|k|^2).
 #include <stdlib.h>
 #include <vector>
 #include "attn.cuh"

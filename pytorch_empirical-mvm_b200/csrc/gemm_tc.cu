@@ -5,12 +5,14 @@
 //   dgrad    dx = dy w          A = dy (K-major),  B = w  (MN-major: w is (N,K) row-major, reduced over N)
 //   wgrad    dw = dy^T x        A = dy (MN-major), B = x  (MN-major), reduced over the M rows, split across
 //                               CTAs into fp32 partials + fixed-order second pass (deterministic)
-// Roles (10 warps, 1 CTA/SM): warp 0 = TMA producer, warp 1 = MMA issuer (one elected lane) + TMEM owner,
-// warps 2..9 = epilogue (TMEM -> registers -> fused epilogue -> global).  The accumulator is double-buffered
+// Roles (18 warps, 1 CTA/SM): warp 0 = TMA producer, warp 1 = MMA issuer (one elected lane) + TMEM owner,
+// warps 2..17 = epilogue (TMEM -> registers -> fused epilogue -> smem transposition -> coalesced global stores; in the wgrad
+// variant four of them add up the dy tiles for the bias gradient instead).  The accumulator is double-buffered
 // in TMEM (2 x BN fp32 columns) so the epilogue of tile i overlaps the MMAs of tile i+1; operands flow
 // through a STAGES-deep TMA ring with 128-byte swizzle (no bank conflicts, no padding).
-// Fused epilogues: bias | bias+GELU(+pre-activation) | bias+drop-path scale+row scatter+residual |
-//                  dgrad (* GELU') | fp32 partial.
+// Fused epilogues (compile-time): bias | bias+GELU(+pre-activation | +GELU') | bias+drop-path scale+row scatter+residual |
+//                  dgrad (* GELU'(pre) | * saved GELU') | fp32 split partial.
+// CTA-pair mode (cta_group::2, 256 x 256 tiles, each CTA loads half of B) for the fwd / dgrad GEMMs with 256-wide tiles.
 #include <cudaTypedefs.h>
 #include <stdlib.h>
 #include <mutex>
