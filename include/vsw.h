@@ -224,6 +224,35 @@ int vsw_patch_im2col(const void* x, void* col, int B, int Cin, int D, int H, int
 int vsw_patch_col2im(const void* dcol, void* dx, int B, int Cin, int D, int H, int W, int pd, int ph, int pw,
                      int x_dtype, int dtype, void* stream);
 
+/* ------------------------------------------------------------------------------------------------
+ * EncVideo tail (model.py:57-76) -- the consumer of the Swin output in every VIOLET step.
+ * After `fc` (a vsw_linear_fwd, model.py:42) each frame's h*w tokens get a class row in front, the position and
+ * frame-length (or frame-order) embeddings are added and the rows are LayerNorm-ed (eps 1e-5):
+ *   pre[b,t,p,:]      = (p == 0 ? emb_cls : f[b,t,p-1,:]) + emb_pos[p,:] + (odr && odr[b,t] != t ? emb_odr : emb_len[t,:])
+ *   out[b, t*P+p, :]  = LN(pre[b,t,p,:]) * gamma + beta          P = 1 + hw          (model.py:57-70)
+ *   m_img[b, t*P+p]   = vt_mask ? vt_mask[b,t,p] : 1             int64                (model.py:72-76)
+ *   f (B*Tn*hw, C) in dtype; out (B*Tn*P, C) in out_dtype (dtype, or fp32 as under autocast);
+ *   emb_cls (C), emb_pos (pos_rows >= P, C), emb_len (len_rows >= Tn, C), emb_odr (C), gamma, beta (C): fp32;
+ *   odr (B*Tn) int32 or NULL; vt_mask (B*Tn*P) int64 or NULL; m_img (B*Tn*P) int64 or NULL;
+ *   mean / rstd (B*Tn*P) fp32 or both NULL (saved for the backward).
+ * ---------------------------------------------------------------------------------------------- */
+int vsw_enc_video_tail_fwd(const void* f, const float* emb_cls, const float* emb_pos, const float* emb_len,
+                           const float* emb_odr, const int32_t* odr, const float* gamma, const float* beta,
+                           const int64_t* vt_mask, void* out, int64_t* m_img, float* mean, float* rstd,
+                           int B, int Tn, int hw, int C, int pos_rows, int len_rows, float eps,
+                           int dtype, int out_dtype, void* stream);
+
+/* Backward of the above (pre is recomputed from the inputs).  df (B*Tn*hw, C) in dtype or NULL; the parameter gradients
+ * are fp32 and OVERWRITTEN: demb_cls (C), demb_pos (pos_rows, C; rows >= P get 0), demb_len (len_rows, C; rows >= Tn
+ * get 0), demb_odr (C; 0 when odr == NULL), dgamma, dbeta (C).  Fixed reduction orders through the fp32 workspace. */
+size_t vsw_enc_video_tail_bwd_workspace(int B, int Tn, int hw, int C);
+int vsw_enc_video_tail_bwd(const void* dy, const void* f, const float* emb_cls, const float* emb_pos,
+                           const float* emb_len, const float* emb_odr, const int32_t* odr, const float* gamma,
+                           const float* mean, const float* rstd, void* df, float* demb_cls, float* demb_pos,
+                           float* demb_len, float* demb_odr, float* dgamma, float* dbeta,
+                           int B, int Tn, int hw, int C, int pos_rows, int len_rows, int dtype, int dy_dtype,
+                           void* ws, size_t ws_bytes, void* stream);
+
 #if defined(__GNUC__)
 #pragma GCC visibility pop
 #endif

@@ -7,6 +7,7 @@ The directory name contains a '-', so import it with ``importlib.import_module("
 from . import _lib, dp, functional  # noqa: F401
 from .video_swin import *  # noqa: F401,F403
 from .video_swin import __all__ as _vs_all
+from .enc_video import EncVideo  # noqa: F401  (reference model.py:7-78)
 
-__all__ = list(_vs_all) + ["functional", "_lib", "dp"]
+__all__ = list(_vs_all) + ["EncVideo", "functional", "_lib", "dp"]
 __version__ = "0.1.0"

@@ -48,6 +48,9 @@ SIGNATURES = {
     "vsw_window_attn_bwd": (_i, [_vp] * 11 + [_i] * 6 + [_f, _i, _i, _vp, _sz, _vp]),
     "vsw_patch_im2col": (_i, [_vp, _vp] + [_i] * 10 + [_vp]),
     "vsw_patch_col2im": (_i, [_vp, _vp] + [_i] * 10 + [_vp]),
+    "vsw_enc_video_tail_fwd": (_i, [_vp] * 13 + [_i] * 6 + [_f, _i, _i, _vp]),
+    "vsw_enc_video_tail_bwd_workspace": (_sz, [_i] * 4),
+    "vsw_enc_video_tail_bwd": (_i, [_vp] * 17 + [_i] * 8 + [_vp, _sz, _vp]),
 }
 
 _lock = threading.Lock()

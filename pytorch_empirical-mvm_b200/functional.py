@@ -566,6 +566,64 @@ class _PatchEmbed(torch.autograd.Function):
                 _grad_to(dbeta, gamma) if gamma is not None else None, None)
 
 
+# ----------------------------------------------------------------------------------------------
+# autograd: EncVideo tail -- class row + position / frame-length|order embeddings + LayerNorm + mask
+# (model.py:57-76)
+# ----------------------------------------------------------------------------------------------
+class _EncVideoTail(torch.autograd.Function):
+    """f (B,Tn,hw,C) -> (out (B, Tn*(1+hw), C), m_img (B, Tn*(1+hw)) int64).  The six small parameter tensors go to the
+    kernels as fp32 (their gradients come back in the parameters' own dtype)."""
+
+    @staticmethod
+    def forward(ctx, f, emb_cls, emb_pos, emb_len, emb_odr, gamma, beta, odr, vt_mask, out_dtype):
+        B, Tn, hw, C = f.shape
+        P = hw + 1
+        f = _c(f)
+        params = [t.detach().reshape(-1, C).float().contiguous() for t in (emb_cls, emb_pos, emb_len, emb_odr, gamma, beta)]
+        cls32, pos32, len32, odr32, g32, b32 = params
+        pos_rows, len_rows = pos32.shape[0], len32.shape[0]
+        out_dtype = out_dtype or f.dtype
+        out = _empty((B, Tn * P, C), out_dtype, f.device)
+        m_img = _empty((B, Tn * P), torch.int64, f.device)
+        mean = _empty((B * Tn * P,), torch.float32, f.device)
+        rstd = _empty((B * Tn * P,), torch.float32, f.device)
+        t0 = PROFILER.begin() if PROFILER is not None else None
+        L.check(L.lib().vsw_enc_video_tail_fwd(L.ptr(f), L.ptr(cls32), L.ptr(pos32), L.ptr(len32), L.ptr(odr32), L.ptr(odr),
+                                               L.ptr(g32), L.ptr(b32), L.ptr(vt_mask), L.ptr(out), L.ptr(m_img), L.ptr(mean),
+                                               L.ptr(rstd), B, Tn, hw, C, pos_rows, len_rows, LN_EPS, L.dt(f),
+                                               L.dt(out_dtype), L.stream()), "vsw_enc_video_tail_fwd")
+        if t0 is not None:
+            PROFILER.end("enc_video_tail_fwd", t0, 0.0, B * Tn * C * (hw * _esz(f) + P * out.element_size()))
+        ctx.save_for_backward(f, cls32, pos32, len32, odr32, g32, odr, mean, rstd)
+        ctx.param_meta = [(t.shape, t.dtype) for t in (emb_cls, emb_pos, emb_len, emb_odr, gamma, beta)]
+        ctx.mark_non_differentiable(m_img)
+        return out, m_img
+
+    @staticmethod
+    def backward(ctx, dout, _dm):
+        f, cls32, pos32, len32, odr32, g32, odr, mean, rstd = ctx.saved_tensors
+        B, Tn, hw, C = f.shape
+        P = hw + 1
+        pos_rows, len_rows = pos32.shape[0], len32.shape[0]
+        dout = _c(dout)
+        if dout.dtype not in (f.dtype, torch.float32):
+            dout = dout.to(f.dtype)
+        df = torch.empty_like(f) if ctx.needs_input_grad[0] else None
+        dev = f.device
+        grads = [_empty(s, torch.float32, dev) for s in ((C,), (pos_rows, C), (len_rows, C), (C,), (C,), (C,))]
+        wsb = int(L.lib().vsw_enc_video_tail_bwd_workspace(B, Tn, hw, C))
+        ws = _empty((max(wsb, 4),), torch.uint8, dev)
+        t0 = PROFILER.begin() if PROFILER is not None else None
+        L.check(L.lib().vsw_enc_video_tail_bwd(L.ptr(dout), L.ptr(f), L.ptr(cls32), L.ptr(pos32), L.ptr(len32), L.ptr(odr32),
+                                               L.ptr(odr), L.ptr(g32), L.ptr(mean), L.ptr(rstd), L.ptr(df),
+                                               *[L.ptr(g) for g in grads], B, Tn, hw, C, pos_rows, len_rows, L.dt(f),
+                                               L.dt(dout), L.ptr(ws), wsb, L.stream()), "vsw_enc_video_tail_bwd")
+        if t0 is not None:
+            PROFILER.end("enc_video_tail_bwd", t0, 0.0, B * Tn * C * (P * dout.element_size() + 2 * hw * _esz(f)))
+        pg = [g.view(shape).to(dtype) for g, (shape, dtype) in zip(grads, ctx.param_meta)]
+        return (df, *pg, None, None, None)
+
+
 # public functional entry points --------------------------------------------------------------
 def attn_branch(x, g1, b1, wqkv, bqkv, table, wproj, bproj, rowscale, plan, rowcode, colcode, dense_mask, nH, scale,
                 cfg_window=None):
@@ -601,3 +659,8 @@ def patch_merge(x, gamma, beta, wred, grid):
 
 def patch_embed(x, w, b, gamma, beta, patch):
     return _PatchEmbed.apply(x, w, b, gamma, beta, patch)
+
+
+def enc_video_tail(f, emb_cls, emb_pos, emb_len, emb_odr, gamma, beta, odr=None, vt_mask=None, out_dtype=None):
+    """odr: (B,Tn) int32 device tensor or None; vt_mask: (B,Tn,1+hw) int64 device tensor or None"""
+    return _EncVideoTail.apply(f, emb_cls, emb_pos, emb_len, emb_odr, gamma, beta, odr, vt_mask, out_dtype)

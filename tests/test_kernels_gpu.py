@@ -350,3 +350,100 @@ def test_patch_merge(vsw, dtype, grid):
     y.backward(dy.view(y.shape))
     for got, ref, nm in zip(xs, (xr, gr, ber, wr), ("x", "gamma", "beta", "w")):
         assert rel_l2(got.grad, ref.grad) < TOL[dtype], nm
+
+
+# ---------------------------------------------------------------------------------------------
+# EncVideo tail (model.py:57-76): class row + position / frame embeddings + LayerNorm + mask
+# ---------------------------------------------------------------------------------------------
+def _tail_params(hid, max_frame, max_patch, seed):
+    torch.manual_seed(seed)
+    return {"emb_cls": 0.3 * torch.randn(1, 1, 1, hid), "emb_pos": 0.3 * torch.randn(1, 1, 1 + max_patch ** 2, hid),
+            "emb_len": 0.3 * torch.randn(1, max_frame, 1, hid), "emb_odr": 0.3 * torch.randn(1, 1, 1, hid),
+            "norm.weight": 1 + 0.2 * torch.randn(hid), "norm.bias": 0.1 * torch.randn(hid)}
+
+
+@pytest.mark.parametrize("dtype,out_dtype", [(torch.float32, None), (torch.bfloat16, None), (torch.bfloat16, torch.float32),
+                                             (torch.float16, None)])
+@pytest.mark.parametrize("B,Tn,h,w,hid,use_odr", [(2, 3, 2, 2, 24, False), (3, 4, 2, 3, 768, True), (5, 8, 7, 7, 768, True),
+                                                  (1, 1, 1, 1, 1024, False), (2, 6, 3, 3, 132, True)])
+def test_enc_video_tail_vs_oracle(vsw, dtype, out_dtype, B, Tn, h, w, hid, use_odr):
+    from oracle import enc_video_oracle as EO
+    VF = vsw.functional
+    hw, P = h * w, 1 + h * w
+    p = _tail_params(hid, max(Tn, 6), 14, seed=B * 100 + Tn)
+    torch.manual_seed(hid + Tn)
+    f = torch.randn(B, Tn, hw, hid).to(dtype)
+    odr = torch.stack([torch.randperm(Tn) for _ in range(B)]) if use_odr else None
+    vt = (torch.rand(B, Tn, P) > 0.25).long() if use_odr else None
+    R = torch.randn(B, Tn * P, hid)
+    # oracle in fp64 on the CPU, from the same (storage-rounded) features
+    fr = f.double().requires_grad_(True)
+    pr = {k: v.double().requires_grad_(True) for k, v in p.items()}
+    # the oracle takes the backbone layout (B, L, T, h, w); no fc here
+    o_ref, m_ref = EO.enc_video_tail(fr.view(B, Tn, h, w, hid).permute(0, 4, 1, 2, 3), pr, odr=odr, vt_mask=vt)
+    (o_ref * R.double()).sum().backward()
+    # CUDA path
+    fc = f.cuda().requires_grad_(True)
+    pc = {k: v.cuda().requires_grad_(True) for k, v in p.items()}
+    out, m_img = VF.enc_video_tail(fc, pc["emb_cls"], pc["emb_pos"], pc["emb_len"], pc["emb_odr"], pc["norm.weight"],
+                                   pc["norm.bias"], None if odr is None else odr.to(torch.int32).cuda(),
+                                   None if vt is None else vt.cuda(), out_dtype)
+    assert out.dtype == (out_dtype or dtype) and out.shape == (B, Tn * P, hid)
+    assert m_img.dtype == torch.int64 and torch.equal(m_img.cpu(), m_ref)           # integer domain: bit-exact
+    tol = TOL[out_dtype or dtype]
+    assert rel_l2(out, o_ref) < tol
+    (out.float() * R.cuda()).sum().backward()
+    assert rel_l2(fc.grad, fr.grad) < TOL[dtype]
+    for k in p:
+        ref = pr[k].grad
+        if ref is None or float(ref.abs().max()) == 0.0:       # emb_odr without odr; unused emb_pos / emb_len rows
+            assert pc[k].grad is None or float(pc[k].grad.abs().max()) == 0.0, k
+        else:
+            # fp32 accumulation over dy in the storage dtype of `out`
+            assert rel_l2(pc[k].grad, ref) < (1e-4 if (out_dtype or dtype) == torch.float32 else tol), k
+    assert float(pc["emb_pos"].grad[0, 0, P:].abs().max() if P < pc["emb_pos"].shape[2] else 0.0) == 0.0   # unused rows: exactly 0
+    assert float(pc["emb_len"].grad[0, Tn:].abs().max() if Tn < pc["emb_len"].shape[1] else 0.0) == 0.0
+
+
+def test_enc_video_tail_golden_and_determinism(vsw):
+    """the reference's own outputs (tests/golden/enc_video.pt), and bit-identical reruns (fixed reduction orders)"""
+    import os
+    VF = vsw.functional
+    gold = torch.load(os.path.join(os.path.dirname(__file__), "golden", "enc_video.pt"), weights_only=False)
+    for case in ("plain", "odr", "nofc_vtmask"):
+        g = gold[case]
+        prm = {k: v.cuda().requires_grad_(True) for k, v in g["params"].items()}
+        buf = g["buf"].cuda().requires_grad_(True)
+        B, Tn, h, w, L = buf.shape
+        runs = []
+        for _ in range(2):
+            for t in [buf, *prm.values()]:
+                t.grad = None
+            tok = buf.view(B, Tn, h * w, L)
+            if "fc.weight" in prm:
+                tok = VF.linear(tok.view(-1, L), prm["fc.weight"], prm["fc.bias"]).view(B, Tn, h * w, -1)
+            odr = None if g["odr"] is None else torch.tensor(g["odr"], dtype=torch.int32, device="cuda")
+            vt = None if g["vt_mask"] is None else g["vt_mask"].cuda()
+            out, m_img = VF.enc_video_tail(tok, prm["emb_cls"], prm["emb_pos"], prm["emb_len"], prm["emb_odr"],
+                                           prm["norm.weight"], prm["norm.bias"], odr, vt, None)
+            (out * g["R"].cuda()).sum().backward()
+            runs.append([out.detach().clone(), buf.grad.clone()] + [prm[k].grad.clone() for k in sorted(g["grads"])])
+        assert torch.equal(m_img.cpu(), g["m_img"])
+        assert rel_l2(runs[0][0], g["f_img"]) < 1e-4
+        assert rel_l2(runs[0][1], g["dbuf"]) < 1e-4
+        for k, got in zip(sorted(g["grads"]), runs[0][2:]):
+            assert rel_l2(got, g["grads"][k]) < 1e-4, (case, k)
+        for a, b in zip(runs[0], runs[1]):
+            assert torch.equal(a, b)
+
+
+def test_enc_video_tail_rejects_bad_geometry(vsw):
+    VF = vsw.functional
+    p = {k: v.cuda() for k, v in _tail_params(24, 2, 1, seed=0).items()}
+    args = (p["emb_cls"], p["emb_pos"], p["emb_len"], p["emb_odr"], p["norm.weight"], p["norm.bias"])
+    with pytest.raises(vsw._lib.VswError):       # 3 frames, emb_len holds 2 (the reference's add fails to broadcast)
+        VF.enc_video_tail(torch.zeros(1, 3, 1, 24, device="cuda"), *args)
+    with pytest.raises(vsw._lib.VswError):       # 1 + 4 tokens per frame, emb_pos holds 2
+        VF.enc_video_tail(torch.zeros(1, 2, 4, 24, device="cuda"), *args)
+    with pytest.raises(vsw._lib.VswError):       # CPU tensor: no fallback
+        VF.enc_video_tail(torch.zeros(1, 2, 1, 24), *args)

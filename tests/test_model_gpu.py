@@ -197,3 +197,57 @@ def test_full_size_properties_swin_b_bf16(vsw):
     # final LayerNorm property: every token has ~zero mean / unit variance at init (gamma=1, beta=0)
     t = y.permute(0, 2, 3, 4, 1).float()
     assert float(t.mean(-1).abs().max()) < 2e-2 and abs(float(t.var(-1, unbiased=False).mean()) - 1) < 2e-2
+
+
+@pytest.mark.parametrize("mode", ["fp32", "bf16", "autocast"])
+def test_enc_video_module_vs_oracle(vsw, mode):
+    """EncVideo (model.py:7-78) as a drop-in: same parameter names/shapes, forward(img, odr, vt_mask) -> (f_img, m_img).
+    The backbone is the product Swin (checked against the oracle elsewhere); everything after it is compared with the
+    EncVideo oracle applied to the SAME backbone output, forward and backward down to the backbone output."""
+    import types
+    from oracle import enc_video_oracle as EO
+    from importlib import import_module
+    EncVideo = import_module("pytorch_empirical-mvm_b200.enc_video").EncVideo
+    torch.manual_seed(3)
+    swin = vsw.SwinTransformer3D(embed_dim=32, depths=[1, 1, 1, 1], num_heads=[1, 2, 4, 8], drop_path_rate=0.0)
+    args = types.SimpleNamespace(max_size_frame=8, max_size_patch=4)
+    m = EncVideo(args, 48, swin=swin).cuda().eval()
+    assert m.latent_feat_size == 256 and m.fc is not None
+    assert {k for k in m.state_dict() if not k.startswith("swin.")} == {
+        "fc.weight", "fc.bias", "emb_cls", "emb_pos", "emb_len", "emb_odr", "norm.weight", "norm.bias"}
+    assert m.emb_pos.shape == (1, 1, 17, 48) and m.emb_len.shape == (1, 8, 1, 48)
+    with torch.no_grad():
+        m.norm.weight.uniform_(0.5, 1.5)
+        m.norm.bias.uniform_(-0.5, 0.5)
+    img = torch.randn(2, 8, 3, 128, 128, device="cuda")          # (B,T,3,H,W): h = w = 4
+    odr = [[0, 1, 2, 3, 4, 5, 6, 7], [2, 1, 0, 3, 4, 7, 6, 5]]
+    vt = (torch.rand(2, 8, 17, device="cuda") > 0.3).long()
+    if mode == "bf16":
+        m = m.bfloat16()
+        img = img.bfloat16()
+    # capture the backbone output of this very forward
+    grabbed = {}
+    hook = m.swin.register_forward_hook(lambda mod, i, o: grabbed.__setitem__("y", o))
+    ctx = torch.autocast("cuda", dtype=torch.bfloat16) if mode == "autocast" else torch.autocast("cuda", enabled=False)
+    with ctx:
+        f_img, m_img = m(img, odr=odr, vt_mask=vt)
+    hook.remove()
+    y = grabbed["y"]
+    y.retain_grad()
+    assert f_img.shape == (2, 8 * 17, 48) and m_img.shape == (2, 136) and m_img.dtype == torch.int64
+    assert f_img.dtype == {"fp32": torch.float32, "bf16": torch.bfloat16, "autocast": torch.float32}[mode]
+    R = torch.randn(f_img.shape, device="cuda")
+    (f_img.float() * R).sum().backward()
+    # oracle (fp64, CPU) on the same backbone output
+    yr = y.detach().double().cpu().requires_grad_(True)
+    pr = {k: v.detach().double().cpu().requires_grad_(True) for k, v in m.state_dict().items() if not k.startswith("swin.")}
+    fo, mo = EO.enc_video_tail(yr, pr, odr=odr, vt_mask=vt.cpu())
+    (fo * R.double().cpu()).sum().backward()
+    tol = 1e-4 if mode == "fp32" else 2e-2
+    assert torch.equal(m_img.cpu(), mo)
+    assert rel_l2(f_img, fo) < tol
+    assert rel_l2(y.grad, yr.grad) < tol
+    named = dict(m.named_parameters())
+    for k in pr:
+        assert rel_l2(named[k].grad, pr[k].grad) < (1e-4 if mode == "fp32" else 3e-2), k
+    assert named["swin.patch_embed.proj.weight"].grad is not None      # the gradient reaches the backbone

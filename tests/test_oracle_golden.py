@@ -98,3 +98,40 @@ def test_oracle_tiny_models(oracle, name):
         assert abs(float((v * r).sum()) - p) <= 5e-5 * n * float(r.norm()) / max(1.0, v.numel() ** 0.5) + 1e-7, k
     for k, gref in fx["grad_full"].items():
         assert rel_l2(grads[k], gref) < 2e-5, k
+
+
+# ---------------------------------------------------------------------------------------------
+# EncVideo tail (model.py:32-78): oracle/enc_video_oracle.py vs the unmodified reference class
+# (tests/golden/make_golden_enc_video.py)
+# ---------------------------------------------------------------------------------------------
+@pytest.fixture(scope="module")
+def enc_gold():
+    return torch.load(os.path.join(GOLD, "enc_video.pt"), weights_only=False)
+
+
+@pytest.mark.parametrize("case", ["plain", "odr", "nofc_vtmask"])
+def test_enc_video_oracle_vs_reference(enc_gold, case):
+    from oracle import enc_video_oracle as EO
+    g = enc_gold[case]
+    buf = g["buf"].clone().requires_grad_(True)
+    params = {k: v.clone().requires_grad_(True) for k, v in g["params"].items()}
+    f_img, m_img = EO.enc_video_tail(buf.permute(0, 4, 1, 2, 3), params, odr=g["odr"], vt_mask=g["vt_mask"])
+    assert f_img.shape == g["f_img"].shape and m_img.dtype == torch.int64
+    assert torch.equal(m_img, g["m_img"])                       # integer domain: bit-exact
+    assert rel_l2(f_img, g["f_img"]) < 2e-6
+    (f_img * g["R"]).sum().backward()
+    assert rel_l2(buf.grad, g["dbuf"]) < 2e-5
+    for k, ref in g["grads"].items():
+        assert rel_l2(params[k].grad, ref) < 2e-5, k
+    for k in params:                                            # parameters the reference left without a gradient
+        if k not in g["grads"]:
+            assert params[k].grad is None or float(params[k].grad.abs().max()) == 0.0, k
+
+
+def test_enc_video_oracle_rejects_too_many_frames():
+    from oracle import enc_video_oracle as EO
+    hid = 8
+    p = {"emb_cls": torch.zeros(1, 1, 1, hid), "emb_pos": torch.zeros(1, 1, 5, hid), "emb_len": torch.zeros(1, 2, 1, hid),
+         "emb_odr": torch.zeros(1, 1, 1, hid), "norm.weight": torch.ones(hid), "norm.bias": torch.zeros(hid)}
+    with pytest.raises(ValueError):
+        EO.enc_video_tail(torch.zeros(1, hid, 3, 1, 1), p)
