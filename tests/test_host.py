@@ -136,3 +136,23 @@ def test_bias_codes_are_dense_toeplitz(vsw, oracle):
         e = (n // (wh * ww)) * R1 + ((n // ww) % wh) * R2 + n % ww
         assert torch.equal(rc.cpu().long() - int(rc[0]), e) and torch.equal(int(cc[0]) - cc.cpu().long(), e)
         assert int(rc[0]) + int(cc[0]) == (L - 1) // 2
+
+
+@pytest.mark.parametrize("case", ["match", "bicubic"])
+def test_inflate_weights_vs_reference_golden(vsw, tmp_path, case):
+    """2-D -> 3-D checkpoint inflation (video_swin.py:484-535): same tensors as the unmodified reference produced
+    (tests/golden/make_golden_inflate.py) -- conv weight repeated over time / pd, bias tables tiled 2wd-1 times, bicubic
+    resize when the 2-D window differs, relative_position_index / attn_mask entries dropped."""
+    gold = torch.load(os.path.join(os.path.dirname(__file__), "golden", "inflate.pt"), weights_only=False)
+    c = gold["cases"][case]
+    path = str(tmp_path / "swin2d.pth")
+    torch.save(c["ckpt"], path)
+    m = vsw.SwinTransformer3D(pretrained=path, pretrained2d=True, window_size=tuple(c["window_size"]), **gold["kw"])
+    m.init_weights()
+    sd = m.state_dict()
+    assert len(c["result"]) >= 9
+    for k, ref in c["result"].items():
+        assert sd[k].shape == ref.shape and torch.equal(sd[k], ref), k      # same torch ops on the CPU: bit-exact
+    wd = c["window_size"][0]
+    assert sd["layers.0.blocks.0.attn.relative_position_bias_table"].shape[0] == (2 * wd - 1) * 13 * 13
+    assert sd["layers.0.blocks.0.attn.relative_position_index"].dtype == torch.int64     # buffer re-initialised, not loaded
