@@ -41,6 +41,15 @@ def test_error_path_without_gpu(vsw):
     assert "bad geometry" in L.last_error()
     rc = L.lib().vsw_linear_fwd(None, None, None, None, 4, 4, 4, 0, None, None, None, None, 0, 0, 0, None)
     assert rc == -1 and "vsw_linear_fwd" in L.last_error()
+    # EncVideo tail: hidden size / embedding-table sizes are validated before any launch
+    one = 1   # any non-NULL pointer value: validation fails before it is dereferenced
+    tail = lambda C, pos_rows, len_rows: L.lib().vsw_enc_video_tail_fwd(
+        one, one, one, one, one, None, one, one, None, one, None, None, None, 2, 3, 4, C, pos_rows, len_rows, 1e-5, 0, 0, None)
+    assert tail(770, 197, 6) == -3 and "multiple of 4" in L.last_error()          # VSW_ERR_UNSUPPORTED
+    assert tail(2048, 197, 6) == -3
+    assert tail(768, 4, 6) == -1 and "emb_pos" in L.last_error()                   # needs 1 + h*w = 5 rows
+    assert tail(768, 197, 2) == -1 and "emb_len" in L.last_error()                 # 3 frames, table holds 2
+    assert L.lib().vsw_enc_video_tail_bwd_workspace(2, 3, 4, 768) == (2 * 3 * 5 * 768 + 2 * 3 * 768 + 148 * 2 * 768) * 4
 
 
 def test_no_oracle_on_product_path():
