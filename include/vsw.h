@@ -253,6 +253,31 @@ int vsw_enc_video_tail_bwd(const void* dy, const void* f, const float* emb_cls, 
                            int B, int Tn, int hw, int C, int pos_rows, int len_rows, int dtype, int dy_dtype,
                            void* ws, size_t ws_bytes, void* stream);
 
+/* ------------------------------------------------------------------------------------------------
+ * MVM masking and loss on either side of the encoder (main_pretrain.py).
+ * ---------------------------------------------------------------------------------------------- */
+
+/* Patch masking of the clip fed to the student encoder (main_pretrain.py:355-362):
+ *   img_out[f,c,y,x] = img[f,c,y,x] * (1 - cov[f, y/ps, x/ps]);   mvm_mask[f,c,y,x] = cov[f, y/ps, x/ps]  (fp32)
+ * img / img_out (frames, Cin, H, W) in dtype, may alias (the reference masks in place); cov (frames, H/ps, W/ps) uint8 in
+ * {0,1}; frames = B*T.  img_out may be NULL (only the mask is wanted) and mvm_mask may be NULL (only the clip). */
+int vsw_block_mask_apply(const void* img, const uint8_t* cov, void* img_out, float* mvm_mask,
+                         int frames, int Cin, int H, int W, int ps, int dtype, void* stream);
+
+/* Masked L1 between a prediction and the teacher encoder's tokens (main_pretrain.py:520-522, 427-428, 534-535):
+ *   loss = sum_{r,c} |pred[r,c] - target[r,c]| * row_weight[r] / (sum_r row_weight[r] + 1e-5) / in_c        (fp32 scalar)
+ * pred (rows, C) in dtype, target (rows, C) in target_dtype (dtype or fp32), row_weight (rows) fp32 (the patch coverage:
+ * max_pool2d(mvm_mask, ps).sum(1) / 3).  loss and msum (= sum_r row_weight) are DEVICE scalars; rows with weight 0 are
+ * never read.  Two-stage fixed-order reduction through ws (vsw_masked_l1_workspace() bytes). */
+size_t vsw_masked_l1_workspace(void);
+int vsw_masked_l1_fwd(const void* pred, const void* target, const float* row_weight, float* loss, float* msum,
+                      long long rows, int C, float in_c, int dtype, int target_dtype,
+                      void* ws, size_t ws_bytes, void* stream);
+/* dpred[r,c] = sign(pred - target) * row_weight[r] * dloss / (msum + 1e-5) / in_c ;  dloss, msum: device scalars */
+int vsw_masked_l1_bwd(const void* pred, const void* target, const float* row_weight, const float* msum,
+                      const float* dloss, void* dpred, long long rows, int C, float in_c,
+                      int dtype, int target_dtype, void* stream);
+
 #if defined(__GNUC__)
 #pragma GCC visibility pop
 #endif

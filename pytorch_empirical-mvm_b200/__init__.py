@@ -8,6 +8,7 @@ from . import _lib, dp, functional  # noqa: F401
 from .video_swin import *  # noqa: F401,F403
 from .video_swin import __all__ as _vs_all
 from .enc_video import EncVideo  # noqa: F401  (reference model.py:7-78)
+from . import mvm  # noqa: F401  (reference main_pretrain.py:309-362, 508-524)
 
-__all__ = list(_vs_all) + ["EncVideo", "functional", "_lib", "dp"]
+__all__ = list(_vs_all) + ["EncVideo", "mvm", "functional", "_lib", "dp"]
 __version__ = "0.1.0"

@@ -51,6 +51,10 @@ SIGNATURES = {
     "vsw_enc_video_tail_fwd": (_i, [_vp] * 13 + [_i] * 6 + [_f, _i, _i, _vp]),
     "vsw_enc_video_tail_bwd_workspace": (_sz, [_i] * 4),
     "vsw_enc_video_tail_bwd": (_i, [_vp] * 17 + [_i] * 8 + [_vp, _sz, _vp]),
+    "vsw_block_mask_apply": (_i, [_vp] * 4 + [_i] * 6 + [_vp]),
+    "vsw_masked_l1_workspace": (_sz, []),
+    "vsw_masked_l1_fwd": (_i, [_vp] * 5 + [C.c_longlong, _i, _f, _i, _i, _vp, _sz, _vp]),
+    "vsw_masked_l1_bwd": (_i, [_vp] * 6 + [C.c_longlong, _i, _f, _i, _i, _vp]),
 }
 
 _lock = threading.Lock()

@@ -624,6 +624,61 @@ class _EncVideoTail(torch.autograd.Function):
         return (df, *pg, None, None, None)
 
 
+# ----------------------------------------------------------------------------------------------
+# MVM masking / loss on either side of the encoder (main_pretrain.py:355-362, 520-522)
+# ----------------------------------------------------------------------------------------------
+def block_mask_apply(img, cov, patch_size, inplace=False, want_mask=False):
+    """img (B,T,Cin,H,W) *= 1 - cov[b,t,y/ps,x/ps]; cov (B,T,h,w) uint8 on the device.  Returns (masked clip,
+    mvm_mask (B,T,Cin,H,W) fp32 or None)."""
+    B, Tn, Cin, H, W = img.shape
+    img = _c(img)
+    cov = _c(cov)
+    if cov.dtype != torch.uint8 or tuple(cov.shape) != (B, Tn, H // patch_size, W // patch_size):
+        raise L.VswError(f"block_mask_apply: cov must be uint8 {(B, Tn, H // patch_size, W // patch_size)}, "
+                         f"got {cov.dtype} {tuple(cov.shape)}")
+    out = img if inplace else torch.empty_like(img)
+    mask = _empty(img.shape, torch.float32, img.device) if want_mask else None
+    t0 = PROFILER.begin() if PROFILER is not None else None
+    L.check(L.lib().vsw_block_mask_apply(L.ptr(img), L.ptr(cov), L.ptr(out), L.ptr(mask), B * Tn, Cin, H, W,
+                                         int(patch_size), L.dt(img), L.stream()), "vsw_block_mask_apply")
+    if t0 is not None:
+        PROFILER.end("block_mask_apply", t0, 0.0, img.numel() * (2 * _esz(img) + (4 if want_mask else 0)))
+    return out, mask
+
+
+class _MaskedL1(torch.autograd.Function):
+    """loss = sum |pred - target| * w[row] / (sum w + 1e-5) / in_c  -- fp32 device scalar; gradient to pred only"""
+
+    @staticmethod
+    def forward(ctx, pred2d, target2d, row_weight, in_c):
+        rows, C = pred2d.shape
+        pred2d, target2d = _c(pred2d), _c(target2d)
+        w = _c(row_weight.reshape(rows).float())
+        out = _empty((2,), torch.float32, pred2d.device)       # [loss, sum w]
+        wsb = int(L.lib().vsw_masked_l1_workspace())
+        ws = _empty((wsb,), torch.uint8, pred2d.device)
+        t0 = PROFILER.begin() if PROFILER is not None else None
+        L.check(L.lib().vsw_masked_l1_fwd(L.ptr(pred2d), L.ptr(target2d), L.ptr(w), out.data_ptr(), out.data_ptr() + 4,
+                                          rows, C, float(in_c), L.dt(pred2d), L.dt(target2d), L.ptr(ws), wsb, L.stream()),
+                "vsw_masked_l1_fwd")
+        if t0 is not None:
+            PROFILER.end("masked_l1_fwd", t0, 0.0, rows * C * (_esz(pred2d) + _esz(target2d)))
+        ctx.save_for_backward(pred2d, target2d, w, out)
+        ctx.in_c = float(in_c)
+        return out[0]
+
+    @staticmethod
+    def backward(ctx, dloss):
+        pred2d, target2d, w, out = ctx.saved_tensors
+        rows, C = pred2d.shape
+        dl = _c(dloss.reshape(1).float())
+        dpred = torch.empty_like(pred2d)
+        L.check(L.lib().vsw_masked_l1_bwd(L.ptr(pred2d), L.ptr(target2d), L.ptr(w), out.data_ptr() + 4, L.ptr(dl),
+                                          L.ptr(dpred), rows, C, ctx.in_c, L.dt(pred2d), L.dt(target2d), L.stream()),
+                "vsw_masked_l1_bwd")
+        return dpred, None, None, None
+
+
 # public functional entry points --------------------------------------------------------------
 def attn_branch(x, g1, b1, wqkv, bqkv, table, wproj, bproj, rowscale, plan, rowcode, colcode, dense_mask, nH, scale,
                 cfg_window=None):
@@ -664,3 +719,8 @@ def patch_embed(x, w, b, gamma, beta, patch):
 def enc_video_tail(f, emb_cls, emb_pos, emb_len, emb_odr, gamma, beta, odr=None, vt_mask=None, out_dtype=None):
     """odr: (B,Tn) int32 device tensor or None; vt_mask: (B,Tn,1+hw) int64 device tensor or None"""
     return _EncVideoTail.apply(f, emb_cls, emb_pos, emb_len, emb_odr, gamma, beta, odr, vt_mask, out_dtype)
+
+
+def masked_l1(pred2d, target2d, row_weight, in_c=3.0):
+    """main_pretrain.py:520-522: sum(|pred - target| * w) / (sum(w) + 1e-5) / in_c; target in pred's dtype or fp32"""
+    return _MaskedL1.apply(pred2d, target2d, row_weight, in_c)

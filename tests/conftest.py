@@ -41,3 +41,9 @@ def rel_l2(a: torch.Tensor, b: torch.Tensor) -> float:
     a = a.detach().double().cpu()
     b = b.detach().double().cpu()
     return float((a - b).norm() / (b.norm() + 1e-30))
+
+
+def pattern_clip(B, Tn, H, W):
+    """the deterministic RNG-free clip of tests/golden/make_golden_mvm.py (values in [-0.5, 0.5), none exactly 0)"""
+    n = B * Tn * 3 * H * W
+    return (((torch.arange(n, dtype=torch.int64) * 7919) % 1013).float() + 0.5).div(1013.0).sub(0.5).view(B, Tn, 3, H, W)

@@ -447,3 +447,95 @@ def test_enc_video_tail_rejects_bad_geometry(vsw):
         VF.enc_video_tail(torch.zeros(1, 2, 4, 24, device="cuda"), *args)
     with pytest.raises(vsw._lib.VswError):       # CPU tensor: no fallback
         VF.enc_video_tail(torch.zeros(1, 2, 1, 24), *args)
+
+
+# ---------------------------------------------------------------------------------------------
+# MVM masking / 3d_feature loss (main_pretrain.py:355-362, 508-524)
+# ---------------------------------------------------------------------------------------------
+def test_block_mask_apply_vs_reference_golden(vsw):
+    """the reference's own masked clip (fp32: bit-exact), with the blocks re-drawn by the product sampler"""
+    import os
+    import numpy as np
+    from conftest import pattern_clip
+    g = torch.load(os.path.join(os.path.dirname(__file__), "golden", "mvm.pt"), weights_only=False)["masking"]
+    B, Tn, H, W = g["shape"]
+    np.random.seed(g["np_seed"])
+    cov = vsw.mvm.sample_block_masks(B, Tn, H // 32, W // 32)
+    img = pattern_clip(B, Tn, H, W).cuda()
+    masked, mask = vsw.mvm.apply_block_mask(img, cov, 32)
+    assert masked.data_ptr() != img.data_ptr() and torch.equal(img.cpu(), pattern_clip(B, Tn, H, W))   # not in place
+    assert torch.equal(masked[:, :, :, ::37, :].cpu(), g["check_rows"])
+    assert torch.equal(mask[:, :, :, ::37, :].to(torch.uint8).cpu(), g["mask_rows"])
+    assert float(mask.sum()) == g["mask_sum"]
+    assert torch.equal(torch.nn.functional.max_pool2d(mask.view(B * Tn, 3, H, W), 32).view(B, Tn, 3, 7, 7).to(torch.uint8).cpu(),
+                       g["cover"])
+    # in place, clip only
+    img2 = img.clone()
+    m2, none = vsw.mvm.apply_block_mask(img2, cov, 32, inplace=True, want_mask=False)
+    assert none is None and m2.data_ptr() == img2.data_ptr() and torch.equal(img2, masked)
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16, torch.float16])
+@pytest.mark.parametrize("B,Tn,H,W,ps", [(2, 3, 64, 96, 32), (1, 2, 48, 80, 16), (3, 1, 32, 32, 32)])
+def test_block_mask_apply_vs_oracle(vsw, dtype, B, Tn, H, W, ps):
+    from oracle import mvm_oracle as MO
+    torch.manual_seed(H + W)
+    img = torch.randn(B, Tn, 3, H, W).to(dtype)
+    cov = (torch.rand(B, Tn, H // ps, W // ps) > 0.5)
+    ref, mref = MO.apply_block_mask(img, cov.float(), ps)
+    out, mask = vsw.mvm.apply_block_mask(img.cuda(), cov.to(torch.uint8), ps)
+    assert out.dtype == dtype and torch.equal(out.cpu(), ref) and torch.equal(mask.cpu(), mref)      # exact: x*1, x*0
+    with pytest.raises(vsw._lib.VswError):
+        vsw.mvm.apply_block_mask(img.cuda(), cov[:, :, :1].to(torch.uint8), ps)                        # wrong grid
+
+
+@pytest.mark.parametrize("dtype,tdtype", [(torch.float32, torch.float32), (torch.bfloat16, torch.bfloat16),
+                                          (torch.bfloat16, torch.float32), (torch.float16, torch.float16)])
+@pytest.mark.parametrize("rows,C,frac", [(37, 16, 0.5), (12544, 1024, 0.15), (300, 132, 1.0), (64, 768, 0.0)])
+def test_masked_l1_vs_oracle(vsw, dtype, tdtype, rows, C, frac):
+    VF = vsw.functional
+    torch.manual_seed(rows + C)
+    pred = torch.randn(rows, C).to(dtype)
+    target = torch.randn(rows, C).to(tdtype)
+    target[::3, ::5] = pred[::3, ::5].to(tdtype)                      # exact ties: sign(0) = 0
+    m = (torch.rand(rows) < frac).float()
+    pr = pred.double().requires_grad_(True)
+    ref = (torch.nn.functional.l1_loss(pr, target.double(), reduction="none") * m.double().view(-1, 1)).sum() / (m.double().sum() + 1e-5) / 3
+    ref.backward()
+    pc = pred.cuda().requires_grad_(True)
+    runs = []
+    for _ in range(2):
+        pc.grad = None
+        loss = VF.masked_l1(pc, target.cuda(), m.cuda(), 3.0)
+        (loss * 2.5).backward()
+        runs.append((loss.detach().clone(), pc.grad.clone()))
+    loss, grad = runs[0]
+    assert loss.dtype == torch.float32 and loss.ndim == 0
+    assert abs(float(loss) - float(ref)) <= 2e-5 * abs(float(ref)) + 1e-12
+    gref = pr.grad * 2.5
+    if float(gref.abs().max()) == 0.0:
+        assert float(grad.abs().max()) == 0.0
+    else:
+        assert rel_l2(grad, gref) < (1e-5 if dtype == torch.float32 else TOL[dtype])
+        assert torch.equal(grad == 0, (gref == 0).cuda())             # masked-out rows and exact ties carry no gradient
+    assert torch.equal(runs[0][0], runs[1][0]) and torch.equal(runs[0][1], runs[1][1])   # fixed reduction order
+
+
+def test_mvm_3d_feature_loss_vs_reference_golden(vsw):
+    """main_pretrain.py:508-524 end to end through the C ABI: fc_mvm (vsw_linear) on the non-class rows, masked L1 against
+    the teacher tokens read from a Swin-style permuted view; loss and gradients vs the reference's own values"""
+    import os
+    g = torch.load(os.path.join(os.path.dirname(__file__), "golden", "mvm.pt"), weights_only=False)["loss"]
+    VF = vsw.functional
+    B, Tn, h, w, Cf = g["teacher"].shape
+    P = 1 + h * w
+    out_mvm = g["out_mvm"].cuda().requires_grad_(True)
+    fw, fb = g["fc_w"].cuda().requires_grad_(True), g["fc_b"].cuda().requires_grad_(True)
+    non_cls = out_mvm.view(B, Tn, P, -1)[:, :, 1:].reshape(B * Tn * h * w, -1)
+    pred = VF.linear(non_cls, fw, fb).view(B, Tn, h * w, Cf)
+    teacher_view = g["teacher"].cuda().permute(0, 4, 1, 2, 3)          # (B,C,T,h,w) view of the channels-last buffer
+    loss = vsw.mvm.mvm_3d_feature_loss(pred, teacher_view, g["cov"], 3)
+    assert abs(float(loss) - float(g["loss"])) < 1e-5 * abs(float(g["loss"]))
+    loss.backward()
+    assert rel_l2(out_mvm.grad, g["d_out_mvm"]) < 1e-4
+    assert rel_l2(fw.grad, g["d_fc_w"]) < 1e-4 and rel_l2(fb.grad, g["d_fc_b"]) < 1e-4

@@ -135,3 +135,51 @@ def test_enc_video_oracle_rejects_too_many_frames():
          "emb_odr": torch.zeros(1, 1, 1, hid), "norm.weight": torch.ones(hid), "norm.bias": torch.zeros(hid)}
     with pytest.raises(ValueError):
         EO.enc_video_tail(torch.zeros(1, hid, 3, 1, 1), p)
+
+
+# ---------------------------------------------------------------------------------------------
+# MVM masking + 3d_feature loss (main_pretrain.py:276-372, 508-524): oracle/mvm_oracle.py and the product's host-side
+# block sampler vs the unmodified reference methods (tests/golden/make_golden_mvm.py)
+# ---------------------------------------------------------------------------------------------
+@pytest.fixture(scope="module")
+def mvm_gold():
+    return torch.load(os.path.join(GOLD, "mvm.pt"), weights_only=False)
+
+
+def test_block_sampler_and_masking_vs_reference(mvm_gold, vsw):
+    from conftest import pattern_clip
+    from oracle import mvm_oracle as MO
+    g = mvm_gold["masking"]
+    B, Tn, H, W = g["shape"]
+    h, w = H // 32, W // 32
+    assert g["unmask_equal"] and torch.equal(g["cover"][:, :, 0], g["cover"][:, :, 1])
+    cover_ref = g["cover"][:, :, 0]
+    # oracle sampler (sets + loops) and product sampler (slice assignment): same numpy stream -> same blocks, bit-exact
+    np.random.seed(g["np_seed"])
+    cov_o = torch.stack([MO.cover_grid(MO.block_cells(Tn, h, w), Tn, h, w) for _ in range(B)])
+    np.random.seed(g["np_seed"])
+    cov_p = vsw.mvm.sample_block_masks(B, Tn, h, w)
+    assert torch.equal(cov_o.to(torch.uint8), cover_ref)
+    assert cov_p.dtype == np.uint8 and np.array_equal(cov_p, cover_ref.numpy())
+    # pixel zeroing + full-resolution mask
+    img = pattern_clip(B, Tn, H, W)
+    masked, mask = MO.apply_block_mask(img, cov_o, 32)
+    assert torch.equal(masked[:, :, :, ::37, :], g["check_rows"])
+    assert torch.equal(mask[:, :, :, ::37, :].to(torch.uint8), g["mask_rows"])
+    assert float(mask.sum()) == g["mask_sum"] and abs(float(masked.double().sum()) - g["img_sum"]) < 1e-6 * abs(g["img_sum"]) + 1e-3
+
+
+def test_feature_loss_oracle_vs_reference(mvm_gold):
+    from oracle import mvm_oracle as MO
+    g = mvm_gold["loss"]
+    B, Tn, h, w, Cf = g["teacher"].shape
+    P = 1 + h * w
+    out_mvm = g["out_mvm"].clone().requires_grad_(True)
+    fw, fb = g["fc_w"].clone().requires_grad_(True), g["fc_b"].clone().requires_grad_(True)
+    non_cls = out_mvm.view(B, Tn, P, -1)[:, :, 1:]                     # drop each frame's class row (main_pretrain.py:512)
+    pred = torch.nn.functional.linear(non_cls, fw, fb)
+    loss = MO.feature_loss(pred, g["teacher"].permute(0, 4, 1, 2, 3), g["cov"].float(), 3)
+    assert abs(float(loss) - float(g["loss"])) < 1e-6 * abs(float(g["loss"]))
+    loss.backward()
+    assert rel_l2(out_mvm.grad, g["d_out_mvm"]) < 1e-6
+    assert rel_l2(fw.grad, g["d_fc_w"]) < 1e-6 and rel_l2(fb.grad, g["d_fc_b"]) < 1e-6
