@@ -486,7 +486,7 @@ def test_block_mask_apply_vs_oracle(vsw, dtype, B, Tn, H, W, ps):
     out, mask = vsw.mvm.apply_block_mask(img.cuda(), cov.to(torch.uint8), ps)
     assert out.dtype == dtype and torch.equal(out.cpu(), ref) and torch.equal(mask.cpu(), mref)      # exact: x*1, x*0
     with pytest.raises(vsw._lib.VswError):
-        vsw.mvm.apply_block_mask(img.cuda(), cov[:, :, :1].to(torch.uint8), ps)                        # wrong grid
+        vsw.mvm.apply_block_mask(img.cuda(), torch.zeros(B, Tn, H // ps + 1, W // ps, dtype=torch.uint8), ps)   # wrong grid
 
 
 @pytest.mark.parametrize("dtype,tdtype", [(torch.float32, torch.float32), (torch.bfloat16, torch.bfloat16),
