@@ -12,8 +12,9 @@
 
 namespace vsw {
 
-constexpr int kTailMaxK = 8;         // chunks of 4 channels per lane: C <= 32 * 4 * 8 = 1024
-constexpr int kTailMaxBlocks = 148;  // one persistent block per SM in the backward row kernel (171 registers x 256 threads)
+constexpr int kTailMaxK = 8;         // chunks of 4 channels per lane: C <= 32 * 4 * 8 = 1024 (kernels are templated on KCH <= 8)
+constexpr int kTailBwdOcc = 2;       // persistent blocks per SM in the backward row kernel (<= 128 registers x 256 threads)
+constexpr int kTailMaxBlocks = 148 * kTailBwdOcc;
 
 template <typename T>
 __device__ __forceinline__ void load4(const T* __restrict__ p, float (&o)[4]) {
@@ -30,15 +31,15 @@ __device__ __forceinline__ void store4(T* __restrict__ p, const float (&v)[4]) {
 }
 
 // pre-LayerNorm row (b,t,p) into registers; returns its sum
-template <typename T>
+template <typename T, int KCH>
 __device__ __forceinline__ float tail_row(const T* __restrict__ f, const float* __restrict__ cls,
                                           const float* __restrict__ pos, const float* __restrict__ sel, long long bt,
-                                          int p, int hw, int C, int lane, float (&v)[kTailMaxK][4]) {
+                                          int p, int hw, int C, int lane, float (&v)[KCH][4]) {
     const T* frow = f + (bt * hw + (p > 0 ? p - 1 : 0)) * (long long)C;
     const float* prow = pos + (long long)p * C;
     float s = 0.f;
 #pragma unroll
-    for (int k = 0; k < kTailMaxK; ++k) {
+    for (int k = 0; k < KCH; ++k) {
         const int col = (lane + 32 * k) * 4;
 #pragma unroll
         for (int e = 0; e < 4; ++e) v[k][e] = 0.f;
@@ -55,8 +56,8 @@ __device__ __forceinline__ float tail_row(const T* __restrict__ f, const float* 
     return s;
 }
 
-template <typename T, typename TO>
-__global__ void __launch_bounds__(256) enc_tail_fwd_kernel(const T* __restrict__ f, const float* __restrict__ cls,
+template <typename T, typename TO, int KCH>
+__global__ void __launch_bounds__(256, 4) enc_tail_fwd_kernel(const T* __restrict__ f, const float* __restrict__ cls,
                                                            const float* __restrict__ pos, const float* __restrict__ len,
                                                            const float* __restrict__ odr_emb,
                                                            const int32_t* __restrict__ odr,
@@ -76,18 +77,18 @@ __global__ void __launch_bounds__(256) enc_tail_fwd_kernel(const T* __restrict__
         const int p = (int)(row - bt * P);
         const int t = (int)(bt % Tn);
         const float* sel = (odr && odr[bt] != t) ? odr_emb : len + (long long)t * C;
-        float v[kTailMaxK][4];
-        const float mu = warp_sum(tail_row<T>(f, cls, pos, sel, bt, p, hw, C, lane, v)) * inv_c;
+        float v[KCH][4];
+        const float mu = warp_sum(tail_row<T, KCH>(f, cls, pos, sel, bt, p, hw, C, lane, v)) * inv_c;
         float q = 0.f;
 #pragma unroll
-        for (int k = 0; k < kTailMaxK; ++k)
+        for (int k = 0; k < KCH; ++k)
             if ((lane + 32 * k) * 4 < C) {
 #pragma unroll
                 for (int e = 0; e < 4; ++e) { const float d = v[k][e] - mu; q += d * d; }
             }
         const float rs = rsqrtf(warp_sum(q) * inv_c + eps);
 #pragma unroll
-        for (int k = 0; k < kTailMaxK; ++k) {
+        for (int k = 0; k < KCH; ++k) {
             const int col = (lane + 32 * k) * 4;
             if (col < C) {
                 float g4[4], b4[4], o[4];
@@ -107,61 +108,70 @@ __global__ void __launch_bounds__(256) enc_tail_fwd_kernel(const T* __restrict__
 
 // backward, row part: dpre = rstd * (g - mean(g) - xhat * mean(g * xhat)), g = dy * gamma.  dpre goes to the fp32
 // workspace (all rows; the embedding gradients are column sums of row subsets of it) and, for p > 0, to df in the
-// feature dtype.  dgamma / dbeta partials: per-lane register accumulators -> one fixed-order partial per block.
-template <typename T, typename TDY>
-__global__ void __launch_bounds__(256) enc_tail_bwd_kernel(const TDY* __restrict__ dy, const T* __restrict__ f,
-                                                           const float* __restrict__ cls, const float* __restrict__ pos,
-                                                           const float* __restrict__ len, const float* __restrict__ odr_emb,
-                                                           const int32_t* __restrict__ odr, const float* __restrict__ gamma,
-                                                           const float* __restrict__ mean, const float* __restrict__ rstd,
-                                                           T* __restrict__ df, float* __restrict__ dpre,
-                                                           float* __restrict__ part, int B, int Tn, int hw, int C) {
+// feature dtype.  dgamma / dbeta: every warp accumulates into its PRIVATE shared-memory slice acc[warp][2][C] (float4
+// read-modify-write, lanes on consecutive vectors, no synchronisation) -- register accumulators had put the kernel at 171
+// registers = one 8-warp block per SM (12.5 % warps active, 85 us); the slices are combined in fixed order at the end,
+// one partial per block.
+template <typename T, typename TDY, int KCH>
+__global__ void __launch_bounds__(256, kTailBwdOcc) enc_tail_bwd_kernel(
+    const TDY* __restrict__ dy, const T* __restrict__ f, const float* __restrict__ cls, const float* __restrict__ pos,
+    const float* __restrict__ len, const float* __restrict__ odr_emb, const int32_t* __restrict__ odr,
+    const float* __restrict__ gamma, const float* __restrict__ mean, const float* __restrict__ rstd, T* __restrict__ df,
+    float* __restrict__ dpre, float* __restrict__ part, int B, int Tn, int hw, int C) {
+    extern __shared__ __align__(16) float acc[];          // [8 warps][2][C]
     const int P = hw + 1;
     const long long nrows = (long long)B * Tn * P;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const long long warp0 = (long long)blockIdx.x * (blockDim.x >> 5) + warp;
     const long long wstride = (long long)gridDim.x * (blockDim.x >> 5);
     const float inv_c = 1.0f / (float)C;
-    float ag[kTailMaxK][4], ab[kTailMaxK][4];
-#pragma unroll
-    for (int k = 0; k < kTailMaxK; ++k)
-#pragma unroll
-        for (int e = 0; e < 4; ++e) { ag[k][e] = 0.f; ab[k][e] = 0.f; }
+    float* acc_g = acc + (size_t)warp * 2 * C;
+    float* acc_b = acc_g + C;
+    for (int col = lane * 4; col < C; col += 128) {
+        const float z[4] = {0.f, 0.f, 0.f, 0.f};
+        store4<float>(acc_g + col, z);
+        store4<float>(acc_b + col, z);
+    }
+    __syncwarp();
 
     for (long long row = warp0; row < nrows; row += wstride) {
         const long long bt = row / P;
         const int p = (int)(row - bt * P);
         const int t = (int)(bt % Tn);
         const float* sel = (odr && odr[bt] != t) ? odr_emb : len + (long long)t * C;
-        float xh[kTailMaxK][4], g[kTailMaxK][4];
-        (void)tail_row<T>(f, cls, pos, sel, bt, p, hw, C, lane, xh);
+        float xh[KCH][4], g[KCH][4];
+        (void)tail_row<T, KCH>(f, cls, pos, sel, bt, p, hw, C, lane, xh);
         const float mu = mean[row], rs = rstd[row];
         float s1 = 0.f, s2 = 0.f;
 #pragma unroll
-        for (int k = 0; k < kTailMaxK; ++k) {
+        for (int k = 0; k < KCH; ++k) {
             const int col = (lane + 32 * k) * 4;
 #pragma unroll
             for (int e = 0; e < 4; ++e) g[k][e] = 0.f;
             if (col < C) {
-                float d4[4], g4[4];
+                float d4[4], g4[4], a4[4], b4[4];
                 load4<TDY>(dy + row * C + col, d4);
                 load4<float>(gamma + col, g4);
+                load4<float>(acc_g + col, a4);
+                load4<float>(acc_b + col, b4);
 #pragma unroll
                 for (int e = 0; e < 4; ++e) {
                     const float xv = (xh[k][e] - mu) * rs;
                     xh[k][e] = xv;
-                    ag[k][e] = fmaf(d4[e], xv, ag[k][e]);
-                    ab[k][e] += d4[e];
+                    a4[e] = fmaf(d4[e], xv, a4[e]);
+                    b4[e] += d4[e];
                     const float gg = d4[e] * g4[e];
                     g[k][e] = gg;
                     s1 += gg;
                     s2 += gg * xv;
                 }
+                store4<float>(acc_g + col, a4);
+                store4<float>(acc_b + col, b4);
             }
         }
         const float c1 = warp_sum(s1) * inv_c, c2 = warp_sum(s2) * inv_c;
 #pragma unroll
-        for (int k = 0; k < kTailMaxK; ++k) {
+        for (int k = 0; k < KCH; ++k) {
             const int col = (lane + 32 * k) * 4;
             if (col < C) {
                 float o[4];
@@ -172,26 +182,14 @@ __global__ void __launch_bounds__(256) enc_tail_bwd_kernel(const TDY* __restrict
             }
         }
     }
-    // block partial of dgamma (pass 0) / dbeta (pass 1): 8 warps combined in fixed order
-    __shared__ float red[8][32 * 4 * kTailMaxK];
+    // block partial of dgamma (pass 0) / dbeta (pass 1): the 8 warp slices combined in fixed order
+    __syncthreads();
+    for (int i = threadIdx.x; i < 2 * C; i += blockDim.x) {
+        const int pass = i / C, c = i - pass * C;
+        float tsum = 0.f;
 #pragma unroll
-    for (int pass = 0; pass < 2; ++pass) {
-#pragma unroll
-        for (int k = 0; k < kTailMaxK; ++k) {
-            const int col = (lane + 32 * k) * 4;
-            if (col < C) {
-#pragma unroll
-                for (int e = 0; e < 4; ++e) red[warp][col + e] = pass == 0 ? ag[k][e] : ab[k][e];
-            }
-        }
-        __syncthreads();
-        for (int c = threadIdx.x; c < C; c += blockDim.x) {
-            float tsum = 0.f;
-#pragma unroll
-            for (int w8 = 0; w8 < 8; ++w8) tsum += red[w8][c];
-            part[((size_t)blockIdx.x * 2 + pass) * C + c] = tsum;
-        }
-        __syncthreads();
+        for (int w8 = 0; w8 < 8; ++w8) tsum += acc[((size_t)w8 * 2 + pass) * C + c];
+        part[((size_t)blockIdx.x * 2 + pass) * C + c] = tsum;
     }
 }
 
@@ -274,8 +272,14 @@ static int launch_tail_fwd(const void* f, const float* cls, const float* pos, co
     const long long nrows = (long long)B * Tn * (hw + 1);
     long long grid = (nrows + 7) / 8;
     if (grid > (long long)kNumSMs * 16) grid = (long long)kNumSMs * 16;
-    enc_tail_fwd_kernel<T, TO><<<(int)grid, 256, 0, st>>>((const T*)f, cls, pos, len, odr_emb, odr, gamma, beta, vt_mask,
-                                                          (TO*)out, m_out, mean, rstd, B, Tn, hw, C, eps);
+#define VSW_TAIL_FWD(K)                                                                                              \
+    enc_tail_fwd_kernel<T, TO, K><<<(int)grid, 256, 0, st>>>((const T*)f, cls, pos, len, odr_emb, odr, gamma, beta, vt_mask, \
+                                                             (TO*)out, m_out, mean, rstd, B, Tn, hw, C, eps)
+    if (C <= 256) VSW_TAIL_FWD(2);
+    else if (C <= 512) VSW_TAIL_FWD(4);
+    else if (C <= 768) VSW_TAIL_FWD(6);
+    else VSW_TAIL_FWD(8);
+#undef VSW_TAIL_FWD
     return check_launch("enc_video_tail_fwd");
 }
 
@@ -291,8 +295,23 @@ static int launch_tail_bwd(const void* dy, const void* f, const float* cls, cons
     float* S = dpre + (size_t)nrows * C;
     float* part = S + (size_t)B * Tn * C;
     const int grid = tail_bwd_grid(nrows);
-    enc_tail_bwd_kernel<T, TDY><<<grid, 256, 0, st>>>((const TDY*)dy, (const T*)f, cls, pos, len, odr_emb, odr, gamma, mean,
-                                                      rstd, (T*)df, dpre, part, B, Tn, hw, C);
+    const size_t smem = (size_t)8 * 2 * C * sizeof(float);   // <= 64 KB at C = 1024: two blocks per SM fit
+#define VSW_TAIL_BWD(K)                                                                                              \
+    do {                                                                                                             \
+        auto kern = enc_tail_bwd_kernel<T, TDY, K>;                                                                  \
+        if (smem > 48 * 1024 &&                                                                                      \
+            cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) {     \
+            set_error("enc_video_tail_bwd: cannot reserve %zu bytes of shared memory", smem);                        \
+            return VSW_ERR_CUDA;                                                                                     \
+        }                                                                                                            \
+        kern<<<grid, 256, smem, st>>>((const TDY*)dy, (const T*)f, cls, pos, len, odr_emb, odr, gamma, mean, rstd,   \
+                                      (T*)df, dpre, part, B, Tn, hw, C);                                             \
+    } while (0)
+    if (C <= 256) VSW_TAIL_BWD(2);
+    else if (C <= 512) VSW_TAIL_BWD(4);
+    else if (C <= 768) VSW_TAIL_BWD(6);
+    else VSW_TAIL_BWD(8);
+#undef VSW_TAIL_BWD
     int rc = check_launch("enc_video_tail_bwd");
     if (rc) return rc;
     const dim3 blk(32, 16);

@@ -49,7 +49,7 @@ def test_error_path_without_gpu(vsw):
     assert tail(2048, 197, 6) == -3
     assert tail(768, 4, 6) == -1 and "emb_pos" in L.last_error()                   # needs 1 + h*w = 5 rows
     assert tail(768, 197, 2) == -1 and "emb_len" in L.last_error()                 # 3 frames, table holds 2
-    assert L.lib().vsw_enc_video_tail_bwd_workspace(2, 3, 4, 768) == (2 * 3 * 5 * 768 + 2 * 3 * 768 + 148 * 2 * 768) * 4
+    assert L.lib().vsw_enc_video_tail_bwd_workspace(2, 3, 4, 768) == (2 * 3 * 5 * 768 + 2 * 3 * 768 + 296 * 2 * 768) * 4
 
 
 def test_no_oracle_on_product_path():
