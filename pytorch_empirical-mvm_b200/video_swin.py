@@ -51,6 +51,21 @@ def _compute_dtype(*params) -> torch.dtype:
     return torch.float32
 
 
+_FP16_WARNED = False
+
+
+def _warn_fp16_once(dtype):
+    """fp16 (torch.autocast's default dtype, and what the reference's DeepSpeed config uses) is correct here but runs on
+    the CUDA-core kernel family: the tcgen05 GEMM / attention kernels are bf16.  Say so once instead of being silently slow."""
+    global _FP16_WARNED
+    if dtype == torch.float16 and not _FP16_WARNED:
+        _FP16_WARNED = True
+        import warnings
+        warnings.warn("pytorch_empirical-mvm_b200: float16 runs on the CUDA-core kernels (about 15x slower than the tcgen05 "
+                      "bf16 path on B200); use torch.autocast('cuda', dtype=torch.bfloat16) or model.bfloat16()",
+                      RuntimeWarning, stacklevel=3)
+
+
 def _cast(t: Optional[torch.Tensor], dtype):
     if t is None or t.dtype == dtype:
         return t
@@ -416,6 +431,7 @@ class SwinTransformer3D(nn.Module):
         """x (B,3,D,H,W) -> (B, 8E, D, H/32, W/32), a permuted view of the channels-last buffer
         exactly like the reference returns (video_swin.py:470-482)."""
         _require_cuda(x)
+        _warn_fp16_once(_compute_dtype(self.norm.weight))
         with torch.cuda.device(x.device):
             t = self.patch_embed.forward_tokens(x)
             for layer in self.layers:

@@ -156,3 +156,23 @@ def test_inflate_weights_vs_reference_golden(vsw, tmp_path, case):
     wd = c["window_size"][0]
     assert sd["layers.0.blocks.0.attn.relative_position_bias_table"].shape[0] == (2 * wd - 1) * 13 * 13
     assert sd["layers.0.blocks.0.attn.relative_position_index"].dtype == torch.int64     # buffer re-initialised, not loaded
+
+
+def test_enc_video_state_dict_matches_reference(vsw):
+    """EncVideo's own parameters (everything outside `swin.*`): same names, shapes and dtypes as the reference class
+    produced (tests/golden/enc_video.pt, case "odr": latent 32 -> hidden 24, max_size_frame 6, max_size_patch 14), so
+    `enc_img.*` VIOLET checkpoints load; constructing the module needs no GPU."""
+    import types
+    gold = torch.load(os.path.join(os.path.dirname(__file__), "golden", "enc_video.pt"), weights_only=False)["odr"]["params"]
+    swin = vsw.SwinTransformer3D(embed_dim=4, depths=[1, 1, 1, 1], num_heads=[1, 1, 1, 1])      # latent 8 * 4 = 32
+    m = vsw.EncVideo(types.SimpleNamespace(), 24, swin=swin)
+    own = {k: v for k, v in m.state_dict().items() if not k.startswith("swin.")}
+    assert list(own) == list(gold)                                       # same names in the same order
+    for k in gold:
+        assert own[k].shape == gold[k].shape and own[k].dtype == gold[k].dtype, k
+    assert m.load_state_dict({**m.state_dict(), **gold}, strict=True)
+    assert (m.latent_feat_size, m.img_feature_dim, m.max_size_frame, m.max_size_patch) == (32, 24, 6, 14)
+    with pytest.raises(NotImplementedError):
+        vsw.EncVideo(types.SimpleNamespace(swinbert=True), 24, swin=swin)
+    with pytest.raises(vsw._lib.VswError):                               # CPU tensors: no fallback
+        m(torch.zeros(1, 2, 3, 32, 32))

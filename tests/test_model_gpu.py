@@ -251,3 +251,73 @@ def test_enc_video_module_vs_oracle(vsw, mode):
     for k in pr:
         assert rel_l2(named[k].grad, pr[k].grad) < (1e-4 if mode == "fp32" else 3e-2), k
     assert named["swin.patch_embed.proj.weight"].grad is not None      # the gradient reaches the backbone
+
+
+def test_violet_video_side_step_vs_oracles(vsw, oracle):
+    """One MVM `3d_feature` step of the video side, caller level (main_pretrain.py:309-362 masking -> model.py:32-78
+    student EncVideo; teacher Swin on the unmasked clip -> main_pretrain.py:508-524 loss), every op through the C ABI,
+    against the composition of the three pinned oracles.  fp32: loss 1e-4; gradients 1e-4 (an L1 loss has sign()
+    discontinuities, so allow 5e-4 in case a single |pred - target| ~ 1e-7 flips)."""
+    import types
+    import numpy as np
+    from importlib import import_module
+    from oracle import enc_video_oracle as EO, mvm_oracle as MO
+    EncVideo = import_module("pytorch_empirical-mvm_b200.enc_video").EncVideo
+    kw = dict(embed_dim=32, depths=[1, 1, 1, 1], num_heads=[1, 2, 4, 8])
+    cfg = oracle.SwinCfg(embed_dim=32, depths=(1, 1, 1, 1), num_heads=(1, 2, 4, 8), window_size=(8, 7, 7))
+    sd_s = oracle.make_state_dict(cfg, seed=21, ln_jitter=0.1)
+    sd_t = oracle.make_state_dict(cfg, seed=22, ln_jitter=0.1)
+    student_swin = vsw.SwinTransformer3D(drop_path_rate=0.0, **kw)
+    student_swin.load_state_dict(sd_s)
+    teacher = vsw.SwinTransformer3D(drop_path_rate=0.0, **kw)
+    teacher.load_state_dict(sd_t)
+    teacher = teacher.cuda().eval()
+    torch.manual_seed(5)
+    hid, B, Tn, H = 48, 2, 8, 128
+    enc = EncVideo(types.SimpleNamespace(max_size_frame=8, max_size_patch=4), hid, swin=student_swin).cuda().eval()
+    with torch.no_grad():
+        enc.norm.weight.uniform_(0.5, 1.5)
+        enc.norm.bias.uniform_(-0.5, 0.5)
+    fc_mvm = torch.nn.Linear(hid, 256).cuda()
+    img = torch.randn(B, Tn, 3, H, H)
+    np.random.seed(3)
+    cov = vsw.mvm.sample_block_masks(B, Tn, 4, 4)
+    assert 0 < cov.sum() < cov.size
+
+    # ---- product path
+    masked, _ = vsw.mvm.apply_block_mask(img.cuda(), cov, 32, want_mask=False)
+    f_img, m_img = enc(masked)
+    non_cls = f_img.view(B, Tn, 17, hid)[:, :, 1:].reshape(-1, hid)
+    pred = vsw.functional.linear(non_cls, fc_mvm.weight, fc_mvm.bias).view(B, Tn, 16, 256)
+    with torch.no_grad():
+        t_out = teacher(img.cuda().transpose(1, 2))
+    loss = vsw.mvm.mvm_3d_feature_loss(pred, t_out, cov, 3)
+    loss.backward()
+
+    # ---- oracle composition (fp32, CPU)
+    ps = {k: (v.clone().requires_grad_(True) if v.is_floating_point() else v) for k, v in sd_s.items()}
+    pe = {k: v.detach().cpu().clone().requires_grad_(True) for k, v in enc.state_dict().items() if not k.startswith("swin.")}
+    fw, fb = fc_mvm.weight.detach().cpu().clone().requires_grad_(True), fc_mvm.bias.detach().cpu().clone().requires_grad_(True)
+    cov_t = torch.from_numpy(cov).float()
+    masked_o, _ = MO.apply_block_mask(img, cov_t, 32)
+    assert torch.equal(masked.cpu(), masked_o)
+    y_s = oracle.swin_forward(ps, masked_o.transpose(1, 2), cfg)
+    f_o, m_o = EO.enc_video_tail(y_s, pe)
+    pred_o = torch.nn.functional.linear(f_o.view(B, Tn, 17, hid)[:, :, 1:], fw, fb)
+    with torch.no_grad():
+        y_t = oracle.swin_forward(sd_t, img.transpose(1, 2), cfg)
+    loss_o = MO.feature_loss(pred_o, y_t, cov_t, 3)
+    loss_o.backward()
+
+    assert torch.equal(m_img.cpu(), m_o)
+    assert rel_l2(f_img, f_o) < 1e-4
+    assert abs(float(loss) - float(loss_o)) < 1e-4 * abs(float(loss_o))
+    named = dict(enc.named_parameters())
+    assert rel_l2(fc_mvm.weight.grad, fw.grad) < 5e-4 and rel_l2(fc_mvm.bias.grad, fb.grad) < 5e-4
+    for k in pe:
+        if pe[k].grad is not None and float(pe[k].grad.abs().max()) > 0:
+            assert rel_l2(named[k].grad, pe[k].grad) < 5e-4, k
+    for k in ("patch_embed.proj.weight", "layers.0.blocks.0.attn.qkv.weight", "layers.2.blocks.0.mlp.fc1.weight",
+              "layers.3.blocks.0.attn.relative_position_bias_table", "norm.weight"):
+        assert rel_l2(named["swin." + k].grad, ps[k].grad) < 5e-4, k
+    assert all(p.grad is None for p in teacher.parameters())
