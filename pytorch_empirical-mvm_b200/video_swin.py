@@ -61,8 +61,8 @@ def _warn_fp16_once(dtype):
     if dtype == torch.float16 and not _FP16_WARNED:
         _FP16_WARNED = True
         import warnings
-        warnings.warn("pytorch_empirical-mvm_b200: float16 runs on the CUDA-core kernels (about 15x slower than the tcgen05 "
-                      "bf16 path on B200); use torch.autocast('cuda', dtype=torch.bfloat16) or model.bfloat16()",
+        warnings.warn("pytorch_empirical-mvm_b200: float16 runs on the CUDA-core kernels (about 30x slower than the tcgen05 "
+                      "bf16 path: 13.6 vs 412 clips/s on Swin-B); use torch.autocast('cuda', dtype=torch.bfloat16) or model.bfloat16()",
                       RuntimeWarning, stacklevel=3)
 
 
