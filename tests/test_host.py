@@ -176,3 +176,22 @@ def test_enc_video_state_dict_matches_reference(vsw):
         vsw.EncVideo(types.SimpleNamespace(swinbert=True), 24, swin=swin)
     with pytest.raises(vsw._lib.VswError):                               # CPU tensors: no fallback
         m(torch.zeros(1, 2, 3, 32, 32))
+
+
+def test_block_sampler_edge_cases(vsw):
+    """main_pretrain.py:312-318: a single frame always yields depth-1 blocks; grids too small for the reference's
+    `randint(1, h*2//3)` fail the same way (numpy ValueError) instead of inventing a block size; a private RandomState
+    reproduces the global-stream result."""
+    import numpy as np
+    from oracle import mvm_oracle as MO
+    np.random.seed(11)
+    a = vsw.mvm.sample_block_masks(3, 1, 7, 7)
+    np.random.seed(11)
+    b = np.stack([MO.cover_grid(MO.block_cells(1, 7, 7), 1, 7, 7).numpy() for _ in range(3)]).astype(np.uint8)
+    assert a.shape == (3, 1, 7, 7) and np.array_equal(a, b) and 0 < a.sum() <= 3 * 3 * 3   # one block of at most 3x3 per sample
+    with pytest.raises(ValueError):
+        vsw.mvm.sample_block_masks(1, 4, 1, 7)          # h*2//3 == 0 -> randint(1, 0)
+    np.random.seed(5)
+    g = vsw.mvm.sample_block_masks(2, 8, 7, 7)
+    assert np.array_equal(g, vsw.mvm.sample_block_masks(2, 8, 7, 7, rng=np.random.RandomState(5)))
+    assert g.max() == 1 and g.dtype == np.uint8
