@@ -621,6 +621,8 @@ class _EncVideoTail(torch.autograd.Function):
         if t0 is not None:
             PROFILER.end("enc_video_tail_bwd", t0, 0.0, B * Tn * C * (P * dout.element_size() + 2 * hw * _esz(f)))
         pg = [g.view(shape).to(dtype) for g, (shape, dtype) in zip(grads, ctx.param_meta)]
+        if odr is None:
+            pg[3] = None   # emb_odr took no part (model.py:67): leave its .grad None like the reference, so optimizers skip it
         return (df, *pg, None, None, None)
 
 
