@@ -4,7 +4,9 @@
  *
  * The reference has no FFI layer: its "operator interface" for this path is the set of torch ops
  * inside visbackbone/video_swin.py.  Every entry point below replaces one group of those ops and is
- * what a binding for this path has to bind (INTEGRATION.md shows the ctypes stub).
+ * what a binding for this path has to bind (INTEGRATION.md shows the ctypes stub).  The last two
+ * sections cover what sits directly on either side of the encoder: the EncVideo
+ * tail (model.py:57-76) and the MVM patch masking / masked-L1 loss (main_pretrain.py:355-362, 520-522).
  *
  * Conventions (SURVEY.md section 8b "Lower"):
  *   - plain C symbols, raw device pointers + sizes, no torch types;
