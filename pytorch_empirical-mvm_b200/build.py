@@ -21,7 +21,7 @@ INCLUDE = os.path.join(os.path.dirname(HERE), "include")
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = ["-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo",
          "-Xcompiler", "-fPIC", "-Xcompiler", "-fvisibility=hidden", "--expt-relaxed-constexpr",
-         "-I", INCLUDE, "-DVSW_BUILD"]
+         "-I", INCLUDE, "-DVSW_BUILD"] + os.environ.get("VSW_NVCC_EXTRA", "").split()
 
 
 def _sources():

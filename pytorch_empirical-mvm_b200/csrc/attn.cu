@@ -1,11 +1,20 @@
 // C-ABI entry points of fused window attention; routes to the tcgen05 or CUDA-core family.
 // Reference: WindowAttention3D.forward, visbackbone/video_swin.py:149-169.
+#include <stdlib.h>
 #include "attn.cuh"
 
 namespace vsw {
 int backend();
 static bool attn_want_tc(int dtype, int hd, const void* dmask) {
     if (dtype != VSW_BF16 || hd != 32 || dmask) return false;
+    const int b = backend();
+    return b == VSW_GEMM_TCGEN05 || b == VSW_GEMM_AUTO;
+}
+static bool attn_want_tc2(int dtype, int hd, const void* dmask) {
+    // VSW_ATTN_TC2 = 0 / 1 forces the first- / second-generation kernel for bf16 (fp16 only exists in the second)
+    static const int pref = getenv("VSW_ATTN_TC2") ? atoi(getenv("VSW_ATTN_TC2")) : -1;
+    if ((dtype != VSW_BF16 && dtype != VSW_F16) || hd != 32 || dmask) return false;
+    if (dtype == VSW_BF16 && pref == 0) return false;
     const int b = backend();
     return b == VSW_GEMM_TCGEN05 || b == VSW_GEMM_AUTO;
 }
@@ -24,6 +33,10 @@ extern "C" int vsw_window_attn_fwd(const void* qkv, const void* bias_table, cons
     VSW_ATTN_CHECK("vsw_window_attn_fwd");
     VSW_REQUIRE(out && lse, VSW_ERR_ARG, "vsw_window_attn_fwd: out/lse NULL");
     cudaStream_t st = (cudaStream_t)stream;
+    if (attn_want_tc2(dtype, hd, dense_mask)) {
+        int rc = tc2_attn_fwd(qkv, bias_table, rowcode, colcode, region, out, lse, B_, nW, N, nH, hd, L, scale, window_dims, dtype, st);
+        if (rc != VSW_ERR_UNSUPPORTED) return rc;
+    }
     if (attn_want_tc(dtype, hd, dense_mask)) {
         int rc = tc_attn_fwd(qkv, bias_table, rowcode, colcode, region, out, lse, B_, nW, N, nH, hd, L, scale, window_dims, st);
         if (rc != VSW_ERR_UNSUPPORTED || backend() == VSW_GEMM_TCGEN05) return rc;

@@ -24,4 +24,10 @@ int tc_attn_bwd(const void* qkv, const void* out, const void* dout, const float*
                 int B_, int nW, int N, int nH, int hd, int L, float scale, int window_dims, void* ws, size_t ws_bytes,
                 cudaStream_t st);
 
+// tcgen05 family, second generation (attn_tc2.cu): bf16 / fp16, head_dim 32, window rows of <= 8 tokens, N <= 448 a whole
+// number of rows, the configured window given as layout hint.  UNSUPPORTED otherwise.
+int tc2_attn_fwd(const void* qkv, const void* table, const int32_t* rowcode, const int32_t* colcode,
+                 const uint8_t* region, void* out, float* lse, int B_, int nW, int N, int nH, int hd, int L,
+                 float scale, int window_dims, int dtype, cudaStream_t st);
+
 }  // namespace vsw

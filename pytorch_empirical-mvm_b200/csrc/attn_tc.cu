@@ -300,7 +300,7 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const FwdParams p)
 
     if (warp == 0) {
         // ===================== TMA producer =====================
-        if (lane == 0) {
+        if (tc::elect_one()) {   // elect.sync, not lane == 0: the TMA / MMA operands stay warp-uniform for ptxas
             int it = 0;
             for (int w = w_begin; w < w_end; ++w, ++it) {
                 const int st = it & 1; const uint32_t ph = (it >> 1) & 1;
@@ -318,7 +318,7 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const FwdParams p)
         // Per query tile the key range is handled as two halves with their own S accumulators, so the tensor
         // core recomputes S of one half for the next tile while the softmax warps are busy with the other:
         //   [P half 0 ready] O  = P0 V0 ; S0 = Q(t+1) K0^T      [P half 1 ready] O += P1 V1 ; S1 = Q(t+1) K1^T
-        if (lane == 0) {
+        if (tc::elect_one()) {   // elect.sync, not lane == 0: the TMA / MMA operands stay warp-uniform for ptxas
             int it = 0; uint32_t pph = 0;
             const uint32_t idesc_pv = tc::idesc_bf16(QT, HD, 0, 1);
             const uint32_t idesc_l = tc::idesc_bf16(QT, 16, 0, 1);

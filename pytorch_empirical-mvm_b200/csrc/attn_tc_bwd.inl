@@ -215,7 +215,7 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_const
 
     if (warp == 0) {
         // ===================== TMA producer =====================
-        if (lane == 0) {
+        if (tc::elect_one()) {   // elect.sync, not lane == 0: the TMA / MMA operands stay warp-uniform for ptxas
             uint32_t kvn = 0, blk = 0;
             for (int b_ = gi; b_ < p.B_; b_ += p.groups) {
                 for (int kb = 0; kb < p.nkb; ++kb, ++kvn) {
@@ -236,7 +236,7 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_const
         }
     } else if (warp == 1) {
         // ===================== MMA issuer =====================
-        if (lane == 0) {
+        if (tc::elect_one()) {   // elect.sync, not lane == 0: the TMA / MMA operands stay warp-uniform for ptxas
             uint32_t kvn = 0, blk = 0, pdsph = 0;
             const uint32_t ka = tc::smem_u32(base + BW_KV_OFF), va = ka + BOX_BYTES;
             const uint32_t pa = tc::smem_u32(base + BW_P_OFF), dsa = tc::smem_u32(base + BW_DS_OFF);

@@ -229,7 +229,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 
     if (warp == 0) {
         // ================= TMA producer =================
-        if (lane == 0) {
+        if (tc::elect_one()) {   // elect.sync, not lane == 0: the TMA / MMA operands stay warp-uniform for ptxas
             int stage = 0; uint32_t phase = 0;
             for (int w = unit; w < total; w += n_units) {
                 const int split = w / tiles, t = w - split * tiles;
@@ -281,7 +281,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         }
     } else if (warp == 1) {
         // ================= MMA issuer =================
-        if (lane == 0 && cta_rank == 0) {   // PAIR: the leader issues for both CTAs
+        if (cta_rank == 0 && tc::elect_one()) {   // elect.sync: ptxas then keeps the MMA operands warp-uniform (no R2UR.BROADCAST loop per MMA);   // PAIR: the leader issues for both CTAs
             int stage = 0; uint32_t phase = 0;
             int acc = 0; uint32_t acc_phase = 0;
             for (int w = unit; w < total; w += n_units) {
