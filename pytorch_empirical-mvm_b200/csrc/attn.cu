@@ -14,7 +14,7 @@ static bool attn_want_tc2(int dtype, int hd, const void* dmask) {
     // VSW_ATTN_TC2 = 0 / 1 forces the first- / second-generation kernel for bf16 (fp16 only exists in the second)
     static const int pref = getenv("VSW_ATTN_TC2") ? atoi(getenv("VSW_ATTN_TC2")) : -1;
     if ((dtype != VSW_BF16 && dtype != VSW_F16) || hd != 32 || dmask) return false;
-    if (dtype == VSW_BF16 && pref == 0) return false;
+    if (dtype == VSW_BF16 && pref != 1) return false;   // bf16 default: first generation (faster on masked windows for now)
     const int b = backend();
     return b == VSW_GEMM_TCGEN05 || b == VSW_GEMM_AUTO;
 }
@@ -47,6 +47,8 @@ extern "C" int vsw_window_attn_fwd(const void* qkv, const void* bias_table, cons
 
 extern "C" size_t vsw_window_attn_bwd_workspace(int B_, int N, int nH, int hd, int L) {
     size_t a = simt_attn_bwd_workspace(B_, N, nH, hd, L), b = tc_attn_bwd_workspace(B_, N, nH, hd, L);
+    const size_t c = tc2_attn_bwd_workspace(B_, N, nH, hd, L);
+    if (c > b) b = c;
     return a > b ? a : b;
 }
 
@@ -60,6 +62,11 @@ extern "C" int vsw_window_attn_bwd(const void* qkv, const void* out, const void*
     VSW_REQUIRE(ws_bytes >= vsw_window_attn_bwd_workspace(B_, N, nH, hd, L), VSW_ERR_WORKSPACE,
                 "vsw_window_attn_bwd: workspace too small");
     cudaStream_t st = (cudaStream_t)stream;
+    if (attn_want_tc2(dtype, hd, dense_mask)) {
+        int rc = tc2_attn_bwd(qkv, out, dout, lse, bias_table, rowcode, colcode, region, dqkv, dbias_table, B_, nW, N, nH, hd, L, scale,
+                              window_dims, dtype, ws, ws_bytes, st);
+        if (rc != VSW_ERR_UNSUPPORTED) return rc;
+    }
     if (attn_want_tc(dtype, hd, dense_mask)) {
         int rc = tc_attn_bwd(qkv, out, dout, lse, bias_table, rowcode, colcode, region, dqkv, dbias_table, B_, nW, N,
                              nH, hd, L, scale, window_dims, ws, ws_bytes, st);

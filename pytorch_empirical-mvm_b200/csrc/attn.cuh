@@ -29,5 +29,10 @@ int tc_attn_bwd(const void* qkv, const void* out, const void* dout, const float*
 int tc2_attn_fwd(const void* qkv, const void* table, const int32_t* rowcode, const int32_t* colcode,
                  const uint8_t* region, void* out, float* lse, int B_, int nW, int N, int nH, int hd, int L,
                  float scale, int window_dims, int dtype, cudaStream_t st);
+size_t tc2_attn_bwd_workspace(int B_, int N, int nH, int hd, int L);
+int tc2_attn_bwd(const void* qkv, const void* out, const void* dout, const float* lse, const void* table,
+                 const int32_t* rowcode, const int32_t* colcode, const uint8_t* region, void* dqkv, float* dbias,
+                 int B_, int nW, int N, int nH, int hd, int L, float scale, int window_dims, int dtype, void* ws, size_t ws_bytes,
+                 cudaStream_t st);
 
 }  // namespace vsw

@@ -807,3 +807,5 @@ int tc2_attn_fwd(const void* qkv, const void* table, const int32_t* rowcode, con
 }
 
 }  // namespace vsw
+
+#include "attn_tc2_bwd.inl"

@@ -1,0 +1,578 @@
+// Second-generation tcgen05 / TMEM recompute backward of fused window attention (included by attn_tc2.cu).
+// Formulas: SURVEY A5.  Everything is held TRANSPOSED -- TMEM lane = KEY, TMEM column = QUERY -- so that the two products that
+// reduce over queries take their A operand straight from tensor memory:
+//   per (key tile T of 14 window rows = 128 lanes, query half-block hb of 8 window rows = 64 padded columns):
+//     S^T  = K_T Q_hb^T,  dP^T = V_T dO_hb^T                        tcgen05.mma SS  -> TMEM (128 lanes x 64 columns each)
+//     P^T  = exp2(S^T*scale*log2e + bias [+ mask] - lse*log2e),   dS^T = P^T (dP^T - delta)        8 exp warps, thread = key
+//            P^T, dS^T -> packed 16-bit back into TMEM (aliasing S^T / dP^T);  dS^T also -> shared memory (MN-major A tile)
+//     dV_T += P^T dO_hb,  dK_T += dS^T Q_hb                          tcgen05.mma TS  (A from TMEM, B = dO / Q MN-major)
+//     dQ_qb += dS K_T                                                 tcgen05.mma SS  (A = the dS tile, B = K_T MN-major)
+// Keys AND queries are laid out padded to 8 slots per window row (4-D tensor maps), so the bias of (key j, queries (d_i, h_i,
+// 0..7)) is one 16-byte vector of the per-w_j shifted table copy, and the d(bias table) contribution of those 8 scores is one
+// 32-byte read-modify-write of a per-w_j shifted fp32 histogram -- two LDS.128 + two STS.128 per 8 scores instead of eight
+// scalar gathers, eight scalar loads and eight scalar stores.  Key lanes are dealt to the four TMEM lane quadrants BY w_j
+// (quadrant q holds w_j = 2q, 2q+1), so the four warps of a group never touch the same histogram entry; the two groups (which
+// work on alternate query half-blocks) own one histogram copy each.  Deterministic: fixed-order folds, no atomics.
+namespace vsw {
+namespace {
+
+constexpr int B_THREADS = 384;          // warps 0..7: exp (2 groups x 4 lane quadrants); 8, 9: aux; 10: TMA; 11: MMA
+constexpr int BW_AUX0 = 8, BW_AUX1 = 9, BW_TMA = 10, BW_MMA = 11;
+constexpr int KTR = 14;                 // key rows per key tile (2 x 14 = 28 of the 32 lanes of a quadrant)
+constexpr int QHR = 8;                  // query rows per half-block (64 padded query columns)
+constexpr int NQD = 3;                  // Q / dO half-block stages
+// tensor memory columns
+constexpr int TB_ST = 0, TB_DP = 64, TB_STAGE = 128;        // stage s: S^T at 128 s, dP^T at 128 s + 64
+constexpr int TB_DKV = 256;                                  // dK at 256 + 64 par, dV at + 32   (double-buffered by key-tile parity)
+constexpr int TB_DQ = 384;                                   // dQ of query block qb at 384 + 32 qb
+// shared memory
+constexpr int BO_KV = 0;                                     // 2 stages x (K tile 8 KB + V tile 8 KB)
+constexpr int BO_QD = 32768;                                 // NQD stages x (Q half-block 4 KB + dO half-block 4 KB)
+constexpr int BO_DS = BO_QD + NQD * 8192;                    // dS chunk (even) 16 KB | zeros 16 KB | dS chunk (odd) 16 KB
+constexpr int BO_TAB = BO_DS + 3 * 16384;                    // transposed shifted bias table (bf16), <= 24 KB
+constexpr int BTAB_MAX_BYTES = 22016;                        // 8x7x7 window: 7 * 15 * 13 * 16 B = 21840
+constexpr int BO_HIST = BO_TAB + BTAB_MAX_BYTES;             // 2 fp32 histogram copies (same layout as the table, 4 bytes per entry)
+constexpr int HIST_MAX_BYTES = 2 * BTAB_MAX_BYTES;
+constexpr int BO_LD = BO_HIST + 2 * HIST_MAX_BYTES;          // [2 stages][448] float2 {lse * log2e, delta}
+constexpr int BO_REGQ = BO_LD + 2 * MAXCOLS * 8;             // [2][448] region id per padded query column
+constexpr int BO_REGK = BO_REGQ + 2 * MAXCOLS;               // [2][512] region id per key lane (tile-major)
+constexpr int BO_KOFF = BO_REGK + 2 * 512;                   // int[64]: table row index of query row rho
+constexpr int BO_FLAG = BO_KOFF + 256;                     // int[2]: does the item's window have more than one region?
+constexpr int BO_BARS = BO_FLAG + 16;
+constexpr int BWD_SMEM = BO_BARS + 256 + 1024;
+static_assert(BWD_SMEM <= 227 * 1024, "backward shared-memory layout exceeds 227 KB");
+
+struct BwdParams2 {
+    const uint16_t* tabg; const float* tabstat; const int* poison; const uint8_t* region;
+    const void* out; const void* dout; const float* lse; void* dqkv; float* dbias_part;
+    int B_, nW, N, nH, wh, ww, KR, nT, nhb, tab_bytes, NHt, wdc, L, groups;
+    float scale, scale_log2;
+};
+struct BBars {
+    uint64_t *kv_full, *kv_empty, *qd_full, *qd_empty, *s_full, *p_full, *ds_free, *dkv_full, *dkv_empty, *dq_full, *dq_empty,
+        *aux_full, *aux_empty;
+    uint32_t* tmem_slot;
+};
+__device__ __forceinline__ BBars bbars_of(uint8_t* base) {
+    uint64_t* b = reinterpret_cast<uint64_t*>(base + BO_BARS);
+    BBars s;
+    s.kv_full = b; s.kv_empty = b + 2; s.qd_full = b + 4; s.qd_empty = b + 7; s.s_full = b + 10; s.p_full = b + 12;
+    s.ds_free = b + 14; s.dkv_full = b + 16; s.dkv_empty = b + 18; s.dq_full = b + 20; s.dq_empty = b + 21;
+    s.aux_full = b + 22; s.aux_empty = b + 24; s.tmem_slot = reinterpret_cast<uint32_t*>(b + 26);
+    return s;
+}
+__device__ __forceinline__ void wait2(uint64_t* bar, uint32_t parity, int tag) {
+    for (uint32_t it = 0; it < (1u << 22); ++it)
+        if (tc::mbar_try_wait(bar, parity)) return;
+    printf("vsw attn2 bwd: mbarrier wait timed out (block %d thread %d, wait site %d, parity %u)\n", blockIdx.x, threadIdx.x, tag, parity);
+    __trap();
+}
+// byte offset of the 16-byte unit holding queries [8u, 8u+8) of key row r inside a 128-byte-swizzled dS chunk
+__device__ __forceinline__ uint32_t sw128_unit(int row, int unit) { return row * 128 + ((unit ^ (row & 7)) << 4); }
+__device__ __forceinline__ float4 lds_f4(uint32_t a) {
+    float4 v;
+    asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(a));
+    return v;
+}
+__device__ __forceinline__ void sts_f4(uint32_t a, float4 v) {
+    asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(a), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+}
+
+// one query row (8 padded columns) of this thread's key: exponentials, dS, packed outputs, histogram update
+template <int WW, bool MASKED, bool F16>
+__device__ __forceinline__ void bwd_row(const uint32_t* rs, const uint32_t* rd, uint32_t ld_a, const uint4& bias, uint32_t nq2lo,
+                                        uint32_t nq2hi, float scale_log2, uint32_t hist_a, uint32_t (&pw)[4], uint32_t (&dw)[4]) {
+    // {lse * log2e, delta} of the 8 queries: four broadcast 16-byte loads
+    float l2[8], dl[8];
+#pragma unroll
+    for (int v = 0; v < 4; ++v) {
+        const float4 t = lds_f4(ld_a + v * 16);
+        l2[2 * v] = t.x; dl[2 * v] = t.y; l2[2 * v + 1] = t.z; dl[2 * v + 1] = t.w;
+    }
+    float ds[8], pp[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+        if (e >= WW) { pp[e] = 0.f; ds[e] = 0.f; continue; }
+        const uint32_t w = word_of(bias, e >> 1);
+        float x = fmaf(__uint_as_float(rs[e]), scale_log2, (e & 1) ? bf_hi(w) : bf_lo(w)) - l2[e];
+        if (MASKED) x = (((e < 4 ? nq2lo : nq2hi) >> (8 * (e & 3))) & 0xFFu) ? x + MASKV : x;
+        const float pe = tc::ex2_approx(x);
+        pp[e] = pe;
+        ds[e] = pe * (__uint_as_float(rd[e]) - dl[e]);
+    }
+    // d(bias table): the 8 scores of this (key, query row) are 8 consecutive entries of the key's w_j-shifted histogram copy
+    {
+        float4 h0 = lds_f4(hist_a), h1 = lds_f4(hist_a + 16);
+        h0.x += ds[0]; h0.y += ds[1]; h0.z += ds[2]; h0.w += ds[3];
+        h1.x += ds[4]; h1.y += ds[5]; h1.z += ds[6]; h1.w += ds[7];
+        sts_f4(hist_a, h0); sts_f4(hist_a + 16, h1);
+    }
+#pragma unroll
+    for (int e = 0; e < 8; e += 2) {
+        pw[e >> 1] = pack16<F16>(pp[e], pp[e + 1]);
+        dw[e >> 1] = pack16<F16>(ds[e], ds[e + 1]);
+    }
+}
+__global__ void tc2_dbias_reduce_kernel(const float* __restrict__ part, int groups, int nH, int L, float* __restrict__ out) {
+    const int idx = blockIdx.x * blockDim.x + threadIdx.x;   // out layout (L, nH); fixed summation order over the CTA groups
+    if (idx >= L * nH) return;
+    const int l = idx / nH, h = idx % nH;
+    float t = 0.f;
+    for (int g = 0; g < groups; ++g) t += part[((long long)g * nH + h) * L + l];
+    out[idx] = t;
+}
+
+template <int WW, bool F16>
+__global__ void __launch_bounds__(B_THREADS, 1)
+attn2_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmKV,
+                 const __grid_constant__ CUtensorMap tmDO, const BwdParams2 p) {
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* base = smem_raw + ((1024u - (tc::smem_u32(smem_raw) & 1023u)) & 1023u);
+    const BBars s = bbars_of(base);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int C = p.nH * HD;
+    const int h = blockIdx.x / p.groups, gi = blockIdx.x % p.groups;   // CTA pinned to one head: table + histograms persist
+    const int hist_bytes = p.tab_bytes * 2;                             // fp32 copy of the bf16 table layout
+    int* koff = reinterpret_cast<int*>(base + BO_KOFF);
+    const uint32_t base_a = tc::smem_u32(base);
+
+    if (warp == BW_TMA && lane == 0) {
+        tc::prefetch_tmap(&tmQ); tc::prefetch_tmap(&tmKV); tc::prefetch_tmap(&tmDO);
+        for (int i = 0; i < 2; ++i) {
+            tc::mbar_init(&s.kv_full[i], 1); tc::mbar_init(&s.kv_empty[i], 1);
+            tc::mbar_init(&s.s_full[i], 1); tc::mbar_init(&s.p_full[i], 4); tc::mbar_init(&s.ds_free[i], 1);
+            tc::mbar_init(&s.dkv_full[i], 1); tc::mbar_init(&s.dkv_empty[i], 4);
+            tc::mbar_init(&s.aux_full[i], 2); tc::mbar_init(&s.aux_empty[i], 8);
+        }
+        for (int i = 0; i < NQD; ++i) { tc::mbar_init(&s.qd_full[i], 1); tc::mbar_init(&s.qd_empty[i], 1); }
+        tc::mbar_init(s.dq_full, 1); tc::mbar_init(s.dq_empty, 8);
+        tc::fence_barrier_init();
+    }
+    if (warp == BW_MMA) tc::tmem_alloc(s.tmem_slot, TMEM_COLS);
+    // one-time shared-memory state: zero the K / V tiles (the 4 lanes per quadrant no tensor-map box ever writes must stay 0),
+    // the dS chunks and the zero chunk between them, the histograms; load the head's table; query-row offsets
+    for (int n = threadIdx.x; n < BO_QD / 16; n += B_THREADS) reinterpret_cast<uint4*>(base + BO_KV)[n] = make_uint4(0, 0, 0, 0);
+    for (int n = threadIdx.x; n < 3 * 16384 / 16; n += B_THREADS) reinterpret_cast<uint4*>(base + BO_DS)[n] = make_uint4(0, 0, 0, 0);
+    for (int n = threadIdx.x; n < 2 * hist_bytes / 16; n += B_THREADS) {
+        const int c = n / (hist_bytes / 16), o = n - c * (hist_bytes / 16);
+        reinterpret_cast<uint4*>(base + BO_HIST + c * HIST_MAX_BYTES)[o] = make_uint4(0, 0, 0, 0);
+    }
+    {
+        const uint4* src = reinterpret_cast<const uint4*>(p.tabg + (size_t)h * (p.tab_bytes / 2));
+        for (int n = threadIdx.x; n < p.tab_bytes / 16; n += B_THREADS) reinterpret_cast<uint4*>(base + BO_TAB)[n] = __ldg(src + n);
+    }
+    for (int n = threadIdx.x; n < 64; n += B_THREADS) koff[n] = (n / p.wh) * p.NHt + n % p.wh;
+    tc::fence_proxy_async();
+    tc::tc_fence_before();
+    __syncthreads();
+    tc::tc_fence_after();
+    const uint32_t tmem = *s.tmem_slot;
+    const int n_items = (p.B_ - gi + p.groups - 1) / p.groups;   // windows gi, gi + groups, ...
+    const int hb_per_item = p.nT * p.nhb;
+
+    if (*p.poison) {
+        // codes are not the dense codes of the named window: poison the gradients (NaN) instead of returning wrong numbers
+        for (int n = threadIdx.x; n < p.L; n += B_THREADS) p.dbias_part[((long long)gi * p.nH + h) * p.L + n] = __int_as_float(0x7FC00000);
+    } else if (warp == BW_TMA) {
+        // ===================== TMA producer =====================
+        if (tc::elect_one()) {
+            int kt = 0, c = 0;
+            for (int it = 0; it < n_items; ++it) {
+                const int b_ = gi + it * p.groups;
+                for (int T = 0; T < p.nT; ++T, ++kt) {
+                    const int ks = kt & 1;
+                    wait2(&s.kv_empty[ks], ((kt >> 1) & 1) ^ 1, 1);
+                    tc::mbar_expect_tx(&s.kv_full[ks], 8 * (2 * KTR * HD * 2));
+                    uint8_t* kv = base + BO_KV + ks * 16384;
+                    for (int which = 0; which < 2; ++which)
+                        for (int q = 0; q < 4; ++q)   // quadrant q: w_j = 2q, 2q+1 of the tile's 14 key rows
+                            tc::tma_load_4d(&tmKV, &s.kv_full[ks], kv + which * 8192 + q * 2048, (1 + which) * C + h * HD, 2 * q, T * KTR, b_);
+                    for (int hb = 0; hb < p.nhb; ++hb, ++c) {
+                        const int qs = c % NQD;
+                        wait2(&s.qd_empty[qs], ((c / NQD) & 1) ^ 1, 2);
+                        tc::mbar_expect_tx(&s.qd_full[qs], 2 * (QHR * SLOT * HD * 2));
+                        uint8_t* qd = base + BO_QD + qs * 8192;
+                        tc::tma_load_4d(&tmQ, &s.qd_full[qs], qd, h * HD, 0, hb * QHR, b_);
+                        tc::tma_load_4d(&tmDO, &s.qd_full[qs], qd + 4096, h * HD, 0, hb * QHR, b_);
+                    }
+                }
+            }
+        }
+    } else if (warp == BW_MMA) {
+        // ===================== MMA issuer (one elected thread) =====================
+        if (tc::elect_one()) {
+            if (tmem != 0) __trap();   // the whole tensor memory is allocated: base is column 0
+            const uint32_t fmt = F16 ? 0u : ((1u << 7) | (1u << 10));
+            const uint32_t id_base = (1u << 4) | fmt | ((uint32_t)(128 >> 4) << 24);
+            const uint32_t id_s = id_base | ((uint32_t)(64 >> 3) << 17);                               // A, B K-major, N = 64
+            const uint32_t id_t = id_base | (1u << 16) | ((uint32_t)(HD >> 3) << 17);                  // A from TMEM, B MN-major, N = 32
+            const uint32_t id_q = id_base | (1u << 15) | (1u << 16) | ((uint32_t)(HD >> 3) << 17);     // A MN-major (dS tile), B MN-major
+            // Software pipeline with a lag of one half-block (across tiles and items): S^T / dP^T of half-block c are issued, then
+            // the dV / dK / dQ MMAs of half-block c - 1, whose exp pass ran meanwhile.  One consume site, straight-line code.
+            const int total = n_items * hb_per_item;
+            int i_it = 0, i_T = 0, i_hb = 0, i_kt = 0;          // issue cursor
+            int p_it = 0, p_T = 0, p_hb = 0, p_kt = 0;          // the pending (issued, not yet consumed) half-block
+            int use_ds0 = 0, use_ds1 = 0; (void)use_ds0; (void)use_ds1;
+            for (int c = 0; c <= total; ++c) {
+                if (c < total) {
+                    const int ks = i_kt & 1, st = c & 1, qs = c % NQD;
+                    if (i_hb == 0) wait2(&s.kv_full[ks], (i_kt >> 1) & 1, 4);
+                    wait2(&s.qd_full[qs], (c / NQD) & 1, 7);
+                    tc::tc_fence_after();
+                    const uint32_t kva = base_a + BO_KV + ks * 16384, qda = base_a + BO_QD + qs * 8192;
+                    // into stage st: its previous contents were consumed by the MMAs of half-block c - 2 (issued earlier by this
+                    // thread; the tensor pipe runs in order)
+#pragma unroll
+                    for (int k = 0; k < 2; ++k)
+                        tc::umma_bf16(st * TB_STAGE + TB_ST, tc::smem_desc_sw64(kva + k * 32, 0, 512), tc::smem_desc_sw64(qda + k * 32, 0, 512), id_s, k);
+#pragma unroll
+                    for (int k = 0; k < 2; ++k)
+                        tc::umma_bf16(st * TB_STAGE + TB_DP, tc::smem_desc_sw64(kva + 8192 + k * 32, 0, 512), tc::smem_desc_sw64(qda + 4096 + k * 32, 0, 512), id_s, k);
+                    tc::umma_commit(&s.s_full[st]);
+                }
+                if (c > 0) {
+                    const int cp = c - 1;
+                    const int st = cp & 1, qs = cp % NQD, ks = p_kt & 1, par = p_kt & 1;
+                    if (p_hb == 0 && p_kt >= 2) wait2(&s.dkv_empty[par], ((p_kt >> 1) - 1) & 1, 5);   // dK / dV buffer read out (tile kt - 2)
+                    if (p_T == 0 && p_hb == 0 && p_it > 0) wait2(s.dq_empty, (p_it - 1) & 1, 6);       // dQ of the previous item read out
+                    wait2(&s.p_full[st], (cp >> 1) & 1, 3);
+                    tc::tc_fence_after();
+                    const uint32_t kva = base_a + BO_KV + ks * 16384, qda = base_a + BO_QD + qs * 8192;
+                    const uint32_t acc_kv = p_hb > 0 ? 1u : 0u;
+#pragma unroll
+                    for (int k = 0; k < 4; ++k)   // dV_T (+)= P^T dO_hb : 16 queries per MMA
+                        tc::umma_bf16_ts(TB_DKV + 64 * par + 32, st * TB_STAGE + TB_ST + 8 * k, tc::smem_desc_sw64(qda + 4096 + k * 1024, 0, 512), id_t, k ? 1u : acc_kv);
+#pragma unroll
+                    for (int k = 0; k < 4; ++k)   // dK_T (+)= dS^T Q_hb
+                        tc::umma_bf16_ts(TB_DKV + 64 * par, st * TB_STAGE + TB_DP + 8 * k, tc::smem_desc_sw64(qda + k * 1024, 0, 512), id_t, k ? 1u : acc_kv);
+                    tc::umma_commit(&s.qd_empty[qs]);
+                    // dQ_qb (+)= dS K_T with M = 128 query rows of which this half-block fills 64: the other 64-row chunk of the
+                    // MN-major A operand is the zero chunk (even half-block: data | zeros, odd: zeros | data)
+                    const uint32_t dsa = base_a + BO_DS + ((p_hb & 1) ? 16384 : 0);
+                    const uint32_t acc_q = (p_T == 0 && (p_hb & 1) == 0) ? 0u : 1u;
+                    const int qb = p_hb >> 1;
+#pragma unroll
+                    for (int k = 0; k < 8; ++k)   // 16 keys per MMA
+                        tc::umma_bf16(TB_DQ + 32 * qb, tc::smem_desc_sw128(dsa + k * 2048, 16384, 1024), tc::smem_desc_sw64(kva + k * 1024, 0, 512), id_q, k ? 1u : acc_q);
+                    tc::umma_commit(&s.ds_free[p_hb & 1]);
+                    if (p_hb == p.nhb - 1) {
+                        tc::umma_commit(&s.dkv_full[par]);
+                        tc::umma_commit(&s.kv_empty[ks]);
+                        if (p_T == p.nT - 1) tc::umma_commit(s.dq_full);
+                    }
+                }
+                // the half-block just issued becomes the pending one; advance the issue cursor
+                p_it = i_it; p_T = i_T; p_hb = i_hb; p_kt = i_kt;
+                if (++i_hb == p.nhb) { i_hb = 0; ++i_kt; if (++i_T == p.nT) { i_T = 0; ++i_it; } }
+            }
+        }
+    } else if (warp == BW_AUX0 || warp == BW_AUX1) {
+        // ===================== aux warps: {lse * log2e, delta} per query; region ids =====================
+        for (int it = 0; it < n_items; ++it) {
+            const int st = it & 1;
+            const int b_ = gi + it * p.groups, win = b_ % p.nW;
+            wait2(&s.aux_empty[st], ((it >> 1) & 1) ^ 1, 8);
+            if (warp == BW_AUX0) {
+                float2* ld = reinterpret_cast<float2*>(base + BO_LD + st * MAXCOLS * 8);
+                for (int n = lane; n < MAXCOLS; n += 32) {
+                    const int row = n >> 3, sl = n & 7;
+                    float2 v = make_float2(0.f, 0.f);
+                    if (sl < p.ww && row < p.KR) {
+                        const int i = row * p.ww + sl;
+                        const uint4* op = reinterpret_cast<const uint4*>((const uint16_t*)p.out + ((long long)b_ * p.N + i) * C + h * HD);
+                        const uint4* dp = reinterpret_cast<const uint4*>((const uint16_t*)p.dout + ((long long)b_ * p.N + i) * C + h * HD);
+                        float d = 0.f;
+#pragma unroll
+                        for (int u = 0; u < 4; ++u) {
+                            const uint4 a = __ldg(op + u), b = __ldg(dp + u);
+                            const uint32_t aw[4] = {a.x, a.y, a.z, a.w}, bw[4] = {b.x, b.y, b.z, b.w};
+#pragma unroll
+                            for (int e = 0; e < 4; ++e) {
+                                float2 x, y;
+                                if (F16) { x = __half22float2(*reinterpret_cast<const __half2*>(&aw[e])); y = __half22float2(*reinterpret_cast<const __half2*>(&bw[e])); }
+                                else { x = tc::unpack_bf16(aw[e]); y = tc::unpack_bf16(bw[e]); }
+                                d = fmaf(x.x, y.x, d); d = fmaf(x.y, y.y, d);
+                            }
+                        }
+                        v = make_float2(p.lse[((long long)b_ * p.nH + h) * p.N + i] * LOG2E, d);
+                    }
+                    ld[n] = v;
+                }
+            } else {
+                uint8_t* regq = base + BO_REGQ + st * MAXCOLS;
+                uint8_t* regk = base + BO_REGK + st * 512;
+                int diff = 0;
+                if (p.region) {
+                    const uint8_t* rg = p.region + (long long)win * p.N;
+                    const uint8_t r0 = rg[0];
+                    for (int n = lane; n < MAXCOLS; n += 32) {
+                        const int row = n >> 3, sl = n & 7;
+                        const bool real = sl < p.ww && row < p.KR;
+                        const uint8_t r = real ? rg[row * p.ww + sl] : (uint8_t)0xFF;
+                        regq[n] = r;
+                        diff |= real && r != r0;
+                    }
+                    for (int n = lane; n < 512; n += 32) {   // key lane n of tile n / 128: quadrant (n % 128) / 32, lane l -> (row 14 T + l / 2, w 2 q + l % 2)
+                        const int T = n >> 7, q = (n >> 5) & 3, l = n & 31;
+                        const int row = T * KTR + (l >> 1), w = 2 * q + (l & 1);
+                        regk[n] = (l < 2 * KTR && row < p.KR && w < p.ww) ? rg[row * p.ww + w] : (uint8_t)0xFE;
+                    }
+                }
+                diff = __any_sync(0xffffffffu, diff);
+                if (lane == 0) reinterpret_cast<int*>(base + BO_FLAG)[st] = diff;
+            }
+            __syncwarp();
+            if (lane == 0) tc::mbar_arrive(&s.aux_full[st]);
+        }
+    } else {
+        // ===================== exp / dS / epilogue warps: thread = key =====================
+        const int q = warp & 3, g = warp >> 2;
+        const uint32_t lane_base = (uint32_t)(q * 32) << 16;
+        const int wj = 2 * q + (lane & 1);                 // this thread's key column w_j (7 = dummy for a 7-wide window)
+        const int rl = lane >> 1;                           // key row inside the tile (0..13; 14, 15: unused lanes)
+        const bool lane_real = lane < 2 * KTR && wj < p.ww;
+        const uint32_t tab_a = base_a + BO_TAB, hist_a = base_a + BO_HIST + g * HIST_MAX_BYTES;
+        const int ND = 2 * p.wdc - 1;
+        const int krow = q * 32 + lane;                     // row of this key in the K / V / dS tiles
+        int c = 0, kt = 0;
+        int use_ds[2] = {0, 0};                              // uses so far of the even / odd dS chunk (all half-blocks, owned or not)
+        int pendT = -1, pend_b = 0, pend_kt = 0;            // deferred dK / dV epilogue
+        auto dkv_epilogue = [&](int T_, int eb, int ekt) {
+            const int par = ekt & 1;
+            wait2(&s.dkv_full[par], (ekt >> 1) & 1, 9);
+            tc::tc_fence_after();
+            uint32_t dk[32], dv[32];
+            tc::tmem_ld_32x32(tmem + lane_base + TB_DKV + 64 * par, dk);
+            tc::tmem_ld_32x32(tmem + lane_base + TB_DKV + 64 * par + 32, dv);
+            tc::tmem_ld_wait();
+            const int row = T_ * KTR + rl;
+            if (lane_real && row < p.KR) {
+                const long long tok = (long long)eb * p.N + row * p.ww + wj;
+                uint4* dstk = reinterpret_cast<uint4*>((uint16_t*)p.dqkv + (tok * 3 + 1) * C + h * HD);
+                uint4* dstv = reinterpret_cast<uint4*>((uint16_t*)p.dqkv + (tok * 3 + 2) * C + h * HD);
+#pragma unroll
+                for (int v4 = 0; v4 < 4; ++v4) {
+                    uint4 u, w;
+                    u.x = pack16<F16>(__uint_as_float(dk[8 * v4 + 0]) * p.scale, __uint_as_float(dk[8 * v4 + 1]) * p.scale);
+                    u.y = pack16<F16>(__uint_as_float(dk[8 * v4 + 2]) * p.scale, __uint_as_float(dk[8 * v4 + 3]) * p.scale);
+                    u.z = pack16<F16>(__uint_as_float(dk[8 * v4 + 4]) * p.scale, __uint_as_float(dk[8 * v4 + 5]) * p.scale);
+                    u.w = pack16<F16>(__uint_as_float(dk[8 * v4 + 6]) * p.scale, __uint_as_float(dk[8 * v4 + 7]) * p.scale);
+                    w.x = pack16<F16>(__uint_as_float(dv[8 * v4 + 0]), __uint_as_float(dv[8 * v4 + 1]));
+                    w.y = pack16<F16>(__uint_as_float(dv[8 * v4 + 2]), __uint_as_float(dv[8 * v4 + 3]));
+                    w.z = pack16<F16>(__uint_as_float(dv[8 * v4 + 4]), __uint_as_float(dv[8 * v4 + 5]));
+                    w.w = pack16<F16>(__uint_as_float(dv[8 * v4 + 6]), __uint_as_float(dv[8 * v4 + 7]));
+                    dstk[v4] = u; dstv[v4] = w;
+                }
+            }
+            tc::tc_fence_before();
+            __syncwarp();
+            if (lane == 0) tc::mbar_arrive(&s.dkv_empty[par]);
+        };
+        for (int it = 0; it < n_items; ++it) {
+            const int ast = it & 1;
+            const int b_ = gi + it * p.groups;
+            wait2(&s.aux_full[ast], (it >> 1) & 1, 10);
+            const bool masked = reinterpret_cast<const int*>(base + BO_FLAG)[ast] != 0;
+            const uint32_t ld_base = base_a + BO_LD + ast * MAXCOLS * 8;
+            const uint32_t regq_a = base_a + BO_REGQ + ast * MAXCOLS;
+            const uint8_t* regk = base + BO_REGK + ast * 512;
+            for (int T = 0; T < p.nT; ++T, ++kt) {
+                const int dj = (T * KTR + rl) / p.wh, hj = (T * KTR + rl) % p.wh;
+                const bool key_real = lane_real && T * KTR + rl < p.KR;
+                // table / histogram row of (this key, query row rho) = rowbase + koff[rho]
+                const int rowbase = (wj * ND - dj + p.wdc - 1) * p.NHt - hj + p.wh - 1;
+                const uint32_t regj4 = masked ? (uint32_t)regk[T * 128 + krow] * 0x01010101u : 0u;
+                for (int hb = 0; hb < p.nhb; ++hb, ++c) {
+                    const int ds_use = use_ds[hb & 1]++;
+                    if ((c & 1) != g) continue;
+                    const int st = c & 1;
+                    // the deferred dK / dV epilogue of the previous key tile (this group's turn): its MMAs retired long ago
+                    if (pendT >= 0 && hb >= 2) { dkv_epilogue(pendT, pend_b, pend_kt); pendT = -1; }
+                    wait2(&s.s_full[st], (c >> 1) & 1, 11);
+                    wait2(&s.ds_free[hb & 1], (ds_use & 1) ^ 1, 12);   // the dS chunk's previous contents have been multiplied
+                    tc::tc_fence_after();
+                    const uint32_t trow = tmem + lane_base + st * TB_STAGE;
+                    const uint32_t ds_a = base_a + BO_DS + ((hb & 1) ? 32768 : 0);
+                    const int nrows = min(QHR, p.KR - hb * QHR);      // query rows of this half-block that exist
+#pragma unroll 1
+                    for (int k = 0; k < 4; ++k) {                     // 16 query columns = 2 query rows per step
+                        uint32_t rs[16], rd[16];
+                        tc::tmem_ld_32x16(trow + TB_ST + 16 * k, rs);
+                        tc::tmem_ld_32x16(trow + TB_DP + 16 * k, rd);
+                        uint32_t pw[8], dw[8];
+                        uint32_t nq[4] = {0, 0, 0, 0};
+                        if (masked) {
+                            const uint4 rg = tc::lds_u4(regq_a + hb * 64 + k * 16);
+                            nq[0] = __vcmpne4(rg.x, regj4); nq[1] = __vcmpne4(rg.y, regj4);
+                            nq[2] = __vcmpne4(rg.z, regj4); nq[3] = __vcmpne4(rg.w, regj4);
+                        }
+                        tc::tmem_ld_wait();
+#pragma unroll
+                        for (int r = 0; r < 2; ++r) {
+                            const int rho = hb * QHR + 2 * k + r;
+                            uint32_t* pwr = pw + 4 * r; uint32_t* dwr = dw + 4 * r;
+                            if (2 * k + r < nrows && key_real) {
+                                const int rowidx = rowbase + koff[rho];
+                                const uint4 bias = tc::lds_u4(tab_a + rowidx * 16);
+                                uint32_t (&pw4)[4] = *reinterpret_cast<uint32_t (*)[4]>(pwr);
+                                uint32_t (&dw4)[4] = *reinterpret_cast<uint32_t (*)[4]>(dwr);
+                                if (masked) bwd_row<WW, true, F16>(rs + 8 * r, rd + 8 * r, ld_base + rho * 64, bias, nq[2 * r], nq[2 * r + 1], p.scale_log2, hist_a + rowidx * 32, pw4, dw4);
+                                else bwd_row<WW, false, F16>(rs + 8 * r, rd + 8 * r, ld_base + rho * 64, bias, 0u, 0u, p.scale_log2, hist_a + rowidx * 32, pw4, dw4);
+                            } else {
+#pragma unroll
+                                for (int e = 0; e < 4; ++e) { pwr[e] = 0u; dwr[e] = 0u; }
+                            }
+                        }
+                        tc::tmem_st_32x8(trow + TB_ST + 8 * k, pw);      // P^T  (A operand of dV)
+                        tc::tmem_st_32x8(trow + TB_DP + 8 * k, dw);      // dS^T (A operand of dK)
+                        // dS^T row of this key into the MN-major A tile of dQ = dS K: 16 queries = two 16-byte units
+                        tc::sts_u4(ds_a + sw128_unit(krow, 2 * k), make_uint4(dw[0], dw[1], dw[2], dw[3]));
+                        tc::sts_u4(ds_a + sw128_unit(krow, 2 * k + 1), make_uint4(dw[4], dw[5], dw[6], dw[7]));
+                    }
+                    tc::tmem_st_wait();
+                    tc::fence_proxy_async();   // the dS tile is read by the tensor core
+                    tc::tc_fence_before();
+                    __syncwarp();
+                    if (lane == 0) tc::mbar_arrive(&s.p_full[st]);
+                }
+                // this tile's dK / dV: read out by group T & 1, deferred into its work on the next tile
+                if ((kt & 1) == g) {
+                    if (pendT >= 0) dkv_epilogue(pendT, pend_b, pend_kt);
+                    pendT = T; pend_b = b_; pend_kt = kt;
+                }
+            }
+            // ---- end of the item: flush the pending dK / dV epilogue, then dQ (group g: query blocks g, g + 2)
+            if (pendT >= 0) { dkv_epilogue(pendT, pend_b, pend_kt); pendT = -1; }
+            wait2(s.dq_full, it & 1, 13);
+            tc::tc_fence_after();
+            for (int qb = g; qb < (p.nhb + 1) / 2; qb += 2) {
+                uint32_t o[32];
+                tc::tmem_ld_32x32(tmem + lane_base + TB_DQ + 32 * qb, o);
+                tc::tmem_ld_wait();
+                const int col = qb * 128 + q * 32 + lane, row = col >> 3, sl = col & 7;
+                if (sl < p.ww && row < p.KR) {
+                    uint4* dst = reinterpret_cast<uint4*>((uint16_t*)p.dqkv + (((long long)b_ * p.N + row * p.ww + sl) * 3) * C + h * HD);
+#pragma unroll
+                    for (int v4 = 0; v4 < 4; ++v4) {
+                        uint4 u;
+                        u.x = pack16<F16>(__uint_as_float(o[8 * v4 + 0]) * p.scale, __uint_as_float(o[8 * v4 + 1]) * p.scale);
+                        u.y = pack16<F16>(__uint_as_float(o[8 * v4 + 2]) * p.scale, __uint_as_float(o[8 * v4 + 3]) * p.scale);
+                        u.z = pack16<F16>(__uint_as_float(o[8 * v4 + 4]) * p.scale, __uint_as_float(o[8 * v4 + 5]) * p.scale);
+                        u.w = pack16<F16>(__uint_as_float(o[8 * v4 + 6]) * p.scale, __uint_as_float(o[8 * v4 + 7]) * p.scale);
+                        dst[v4] = u;
+                    }
+                }
+            }
+            tc::tc_fence_before();
+            __syncwarp();
+            if (lane == 0) { tc::mbar_arrive(s.dq_empty); tc::mbar_arrive(&s.aux_empty[ast]); }
+        }
+    }
+
+    __syncwarp();
+    tc::tc_fence_before();
+    __syncthreads();
+    // fold the two histogram copies and the per-w_j shifted layout back into the table column (fixed order)
+    if (!*p.poison) {
+        const int ND = 2 * p.wdc - 1, NW = 2 * p.ww - 1;
+        float* part = p.dbias_part + ((long long)gi * p.nH + h) * p.L;
+        for (int l = threadIdx.x; l < p.L; l += B_THREADS) {
+            const int dw = l % NW, r = l / NW;              // r = dd * NHt + dh
+            float t = 0.f;
+            for (int wj = 0; wj < p.ww; ++wj) {
+                const int wi = dw - (p.ww - 1) + wj;        // table index dw = w_i - w_j + ww - 1
+                if (wi < 0 || wi >= p.ww) continue;
+                const int idx = ((wj * ND * p.NHt) + r) * SLOT + wi;
+                t += reinterpret_cast<const float*>(base + BO_HIST)[idx];
+                t += reinterpret_cast<const float*>(base + BO_HIST + HIST_MAX_BYTES)[idx];
+            }
+            part[l] = t;
+        }
+    }
+    if (warp == BW_MMA) {
+        tc::tc_fence_after();
+        tc::tmem_dealloc(tmem, TMEM_COLS);
+    }
+}
+
+int bwd2_groups(int B_, int nH, int sms) {
+    int g = sms / nH;
+    if (g < 1) g = 1;
+    if (g > B_) g = B_;
+    return g;
+}
+
+}  // namespace
+
+size_t tc2_attn_bwd_workspace(int B_, int N, int nH, int hd, int L) {
+    (void)N; (void)hd;
+    if (nH > kNumSMs) return 0;
+    return (size_t)bwd2_groups(B_, nH, kNumSMs) * nH * L * sizeof(float);
+}
+
+int tc2_attn_bwd(const void* qkv, const void* out, const void* dout, const float* lse, const void* table,
+                 const int32_t* rowcode, const int32_t* colcode, const uint8_t* region, void* dqkv, float* dbias,
+                 int B_, int nW, int N, int nH, int hd, int L, float scale, int window_dims, int dtype, void* ws, size_t ws_bytes,
+                 cudaStream_t st) {
+    Geometry g;
+    int dev = 0, sms = kNumSMs;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    if (sms > kNumSMs) sms = kNumSMs;   // the workspace size is computed for at most kNumSMs CTAs
+    if ((dtype != VSW_BF16 && dtype != VSW_F16) || !geometry_of(N, hd, L, window_dims, &g) || g.tab_bytes > BTAB_MAX_BYTES || nH > sms || !aligned16(qkv) ||
+        !aligned16(out) || !aligned16(dout) || !aligned16(dqkv)) {
+        set_error("tcgen05 window attention bwd: needs bf16/fp16, head_dim 32, the configured window (rows of <= 8 tokens) as "
+                  "layout hint and N <= 448 a whole number of window rows (hd=%d N=%d L=%d window_dims=0x%x)", hd, N, L, window_dims);
+        return VSW_ERR_UNSUPPORTED;
+    }
+    const int groups = bwd2_groups(B_, nH, sms);
+    if (ws_bytes < (size_t)groups * nH * L * sizeof(float)) { set_error("tcgen05 attention bwd: workspace too small"); return VSW_ERR_WORKSPACE; }
+    const int C = nH * HD;
+    CUtensorMap tmQ, tmKV, tmDO;
+    {
+        const uint64_t dims[4] = {(uint64_t)3 * C, (uint64_t)g.ww, (uint64_t)g.KR, (uint64_t)B_};
+        const uint64_t strides[4] = {1, (uint64_t)3 * C, (uint64_t)g.ww * 3 * C, (uint64_t)N * 3 * C};
+        const uint32_t boxq[4] = {HD, SLOT, QHR, 1}, boxk[4] = {HD, 2, KTR, 1};
+        if (!make_tmap_nd_bf16(&tmQ, qkv, 4, dims, strides, boxq, 64) || !make_tmap_nd_bf16(&tmKV, qkv, 4, dims, strides, boxk, 64)) return VSW_ERR_CUDA;
+        const uint64_t dimo[4] = {(uint64_t)C, (uint64_t)g.ww, (uint64_t)g.KR, (uint64_t)B_};
+        const uint64_t strido[4] = {1, (uint64_t)C, (uint64_t)g.ww * C, (uint64_t)N * C};
+        if (!make_tmap_nd_bf16(&tmDO, dout, 4, dimo, strido, boxq, 64)) return VSW_ERR_CUDA;
+    }
+    const size_t tab_total = (size_t)nH * g.tab_bytes;
+    uint8_t* scratch = scratch_for(st, tab_total + (size_t)nH * 8 + 16);
+    if (!scratch) return VSW_ERR_CUDA;
+    uint16_t* tabg = (uint16_t*)scratch;
+    float* tabstat = (float*)(scratch + tab_total);
+    int* poison = (int*)(scratch + tab_total + (size_t)nH * 8);
+    cudaMemsetAsync(poison, 0, 4, st);
+    if (dtype == VSW_BF16)
+        attn2_table_kernel<__nv_bfloat16><<<nH, 256, 0, st>>>((const __nv_bfloat16*)table, rowcode, colcode, N, nH, L, g.wdc, g.wh, g.ww, 1, tabg, tabstat, poison);
+    else
+        attn2_table_kernel<__half><<<nH, 256, 0, st>>>((const __half*)table, rowcode, colcode, N, nH, L, g.wdc, g.wh, g.ww, 1, tabg, tabstat, poison);
+    int rc = check_launch("attn2_table");
+    if (rc) return rc;
+    BwdParams2 p{};
+    p.tabg = tabg; p.tabstat = tabstat; p.poison = poison; p.region = region;
+    p.out = out; p.dout = dout; p.lse = lse; p.dqkv = dqkv; p.dbias_part = (float*)ws;
+    p.B_ = B_; p.nW = nW; p.N = N; p.nH = nH; p.wh = g.wh; p.ww = g.ww; p.KR = g.KR;
+    p.nT = (g.KR + KTR - 1) / KTR; p.nhb = (g.KR + QHR - 1) / QHR;
+    p.tab_bytes = g.tab_bytes; p.NHt = 2 * g.wh - 1; p.wdc = g.wdc; p.L = L; p.groups = groups;
+    p.scale = scale; p.scale_log2 = scale * LOG2E;
+    cudaError_t e = cudaSuccess;
+#define VSW_LAUNCH_BWD2(WWV, F16V)                                                                                        \
+    do {                                                                                                                  \
+        auto kern = attn2_bwd_kernel<WWV, F16V>;                                                                          \
+        e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, BWD_SMEM);                            \
+        if (e == cudaSuccess) kern<<<groups * nH, B_THREADS, BWD_SMEM, st>>>(tmQ, tmKV, tmDO, p);                         \
+    } while (0)
+    if (dtype == VSW_BF16) { if (g.ww == 7) VSW_LAUNCH_BWD2(7, false); else VSW_LAUNCH_BWD2(8, false); }
+    else { if (g.ww == 7) VSW_LAUNCH_BWD2(7, true); else VSW_LAUNCH_BWD2(8, true); }
+#undef VSW_LAUNCH_BWD2
+    if (e != cudaSuccess) { set_error("attn bwd: cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return VSW_ERR_CUDA; }
+    rc = check_launch("attn2_bwd");
+    if (rc) return rc;
+    tc2_dbias_reduce_kernel<<<ceil_div((long long)L * nH, 256), 256, 0, st>>>((const float*)ws, groups, nH, L, dbias);
+    return check_launch("attn2_dbias_reduce");
+}
+
+}  // namespace vsw
