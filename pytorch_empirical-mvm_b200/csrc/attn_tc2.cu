@@ -20,6 +20,7 @@
 #include <stdlib.h>
 #include <map>
 #include <mutex>
+#include <type_traits>
 #include <utility>
 #include "attn.cuh"
 #include "tc_common.cuh"
@@ -225,6 +226,7 @@ __device__ __forceinline__ float block_max(const BlockArgs& a) {
 // call on the MMA thread's path makes ptxas give up uniform registers for the whole issue loop -- every UTCHMMA then pays an
 // ELECT / R2UR.BROADCAST sequence of ~100 cycles, which is what bounded the first version of this kernel.)
 __device__ __forceinline__ void wait_dbg(uint64_t* bar, uint32_t parity, int tag, long long*) {
+#pragma unroll 1
     for (uint32_t it = 0; it < (1u << 22); ++it)
         if (tc::mbar_try_wait(bar, parity)) return;
     printf("vsw attn2: mbarrier wait timed out (block %d thread %d, wait site %d, parity %u)\n", blockIdx.x, threadIdx.x, tag, parity);
@@ -644,19 +646,21 @@ attn2_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
 template <typename T>
 __global__ void attn2_table_kernel(const T* __restrict__ table, const int32_t* __restrict__ rowcode,
                                    const int32_t* __restrict__ colcode, int N, int nH, int L, int wdc, int wh, int ww,
-                                   int transposed, uint16_t* __restrict__ tabg, float* __restrict__ tabstat, int* __restrict__ poison) {
+                                   int transposed, int blk, uint16_t* __restrict__ tabg, float* __restrict__ tabstat, int* __restrict__ poison) {
+    // blk = rows per w block (>= ND * NH; the backward pads it so that neighbouring w blocks start 4 rows apart mod 8 --
+    // the two key columns of a quarter-warp then read distinct shared-memory banks)
     const int h = blockIdx.x;
     const int ND = 2 * wdc - 1, NH = 2 * wh - 1, NW = 2 * ww - 1;
-    const int total = ww * ND * NH * SLOT;
+    const int total = ww * blk * SLOT;
     float mx = -INFINITY, mn = INFINITY;
     for (int idx = threadIdx.x; idx < total; idx += blockDim.x) {
         const int sl = idx & 7;
         int r = idx >> 3;
-        const int dh = r % NH; r /= NH;
-        const int dd = r % ND;
-        const int wl = r / ND;
+        const int wl = r / blk; r -= wl * blk;
+        const int dh = r % NH;
+        const int dd = r / NH;
         uint16_t o = 0xFF80;   // bf16 -inf
-        if (sl < ww) {
+        if (sl < ww && dd < ND) {
             const int dw = transposed ? (sl - wl + ww - 1) : (wl - sl + ww - 1);
             const float v = to_f<T>(table[(long long)((dd * NH + dh) * NW + dw) * nH + h]) * LOG2E;
             mx = fmaxf(mx, v); mn = fminf(mn, v);
@@ -693,13 +697,12 @@ long long* attn2_debug_buffer(const char* which) {
     if (!dbg) return nullptr;
     long long h[32];
     cudaMemcpy(h, dbg, 256, cudaMemcpyDeviceToHost);
-    if (h[2]) fprintf(stderr, "      mma thread lifetime %lld cycles = %lld ns (%.0f MHz)\n", h[20], h[21], h[21] ? 1e3 * (double)h[20] / (double)h[21] : 0.0);
-    if (h[2]) fprintf(stderr, "      mma thread issue phase: total %lld cycles per block; pipeline drained %lld times, waiting %lld (tiles) + %lld (side data) cycles each\n",
-                      h[13] / (h[12] + 1), h[16], h[14] / (h[16] + 1), h[15] / (h[16] + 1));
-    if (h[2]) fprintf(stderr, "[vsw attn2 before this %s launch] exp warp: blocks=%lld wait_s=%lld work=%lld | epilogues=%lld each %lld | waiting for side data %lld in total | lifetime %lld, gaps between own blocks %lld in total\n"
-                              "      mma thread: blocks=%lld wait_p+o=%lld (unused %lld) pv_issue=%lld s_issue=%lld (cycles per block)\n",
-                      which, h[2], h[0] / h[2], h[1] / h[2], h[4], h[3] / (h[4] + 1), h[5], h[6], h[7], h[12], h[8] / (h[12] + 1), h[9] / (h[12] + 1),
-                      h[10] / (h[12] + 1), h[11] / (h[12] + 1));
+    if (h[2]) {
+        fprintf(stderr, "[vsw attn2, the launch before this %s launch] exp warp 0: blocks=%lld wait_s=%lld wait_ds=%lld work=%lld (cycles per block) lifetime=%lld"
+                        " epilogues=%lld x %lld side-data wait=%lld gaps/dq=%lld aux=%lld gap(in tile)=%lld gap(tile start)=%lld gap(item start)=%lld gap(in tile, loop only)=%lld\n", which, h[2], h[0] / h[2], h[3] / h[2], h[1] / h[2], h[6], h[4], h[4] ? h[5] / h[4] : 0, h[5], h[7], h[14], h[15], h[17], h[18], h[19]);
+        fprintf(stderr, "      mma thread: blocks=%lld wait_p=%lld wait_loads=%lld other=%lld issue_phase=%lld (cycles per block) lifetime=%lld drained=%lld\n",
+                h[12], h[8] / (h[12] + 1), h[9] / (h[12] + 1), h[10] / (h[12] + 1), h[13] / (h[12] + 1), h[20], h[16]);
+    }
     cudaMemset(dbg, 0, 256);
     return dbg;
 }
@@ -775,9 +778,9 @@ int tc2_attn_fwd(const void* qkv, const void* table, const int32_t* rowcode, con
     int* poison = (int*)(scratch + tab_total + (size_t)nH * 8);
     cudaMemsetAsync(poison, 0, 4, st);
     if (dtype == VSW_BF16)
-        attn2_table_kernel<__nv_bfloat16><<<nH, 256, 0, st>>>((const __nv_bfloat16*)table, rowcode, colcode, N, nH, L, g.wdc, g.wh, g.ww, 0, tabg, tabstat, poison);
+        attn2_table_kernel<__nv_bfloat16><<<nH, 256, 0, st>>>((const __nv_bfloat16*)table, rowcode, colcode, N, nH, L, g.wdc, g.wh, g.ww, 0, (2 * g.wdc - 1) * (2 * g.wh - 1), tabg, tabstat, poison);
     else
-        attn2_table_kernel<__half><<<nH, 256, 0, st>>>((const __half*)table, rowcode, colcode, N, nH, L, g.wdc, g.wh, g.ww, 0, tabg, tabstat, poison);
+        attn2_table_kernel<__half><<<nH, 256, 0, st>>>((const __half*)table, rowcode, colcode, N, nH, L, g.wdc, g.wh, g.ww, 0, (2 * g.wdc - 1) * (2 * g.wh - 1), tabg, tabstat, poison);
     int rc = check_launch("attn2_table");
     if (rc) return rc;
     FwdParams p{};

@@ -45,8 +45,9 @@ static_assert(BWD_SMEM <= 227 * 1024, "backward shared-memory layout exceeds 227
 struct BwdParams2 {
     const uint16_t* tabg; const float* tabstat; const int* poison; const uint8_t* region;
     const void* out; const void* dout; const float* lse; void* dqkv; float* dbias_part;
-    int B_, nW, N, nH, wh, ww, KR, nT, nhb, tab_bytes, NHt, wdc, L, groups;
+    int B_, nW, N, nH, wh, ww, KR, nT, nhb, tab_bytes, NHt, wdc, L, groups, blk;   // blk = table rows per w_j block (padded)
     float scale, scale_log2;
+    long long* dbg;
 };
 struct BBars {
     uint64_t *kv_full, *kv_empty, *qd_full, *qd_empty, *s_full, *p_full, *ds_free, *dkv_full, *dkv_empty, *dq_full, *dq_empty,
@@ -62,6 +63,7 @@ __device__ __forceinline__ BBars bbars_of(uint8_t* base) {
     return s;
 }
 __device__ __forceinline__ void wait2(uint64_t* bar, uint32_t parity, int tag) {
+#pragma unroll 1
     for (uint32_t it = 0; it < (1u << 22); ++it)
         if (tc::mbar_try_wait(bar, parity)) return;
     printf("vsw attn2 bwd: mbarrier wait timed out (block %d thread %d, wait site %d, parity %u)\n", blockIdx.x, threadIdx.x, tag, parity);
@@ -78,37 +80,52 @@ __device__ __forceinline__ void sts_f4(uint32_t a, float4 v) {
     asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(a), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
 }
 
-// one query row (8 padded columns) of this thread's key: exponentials, dS, packed outputs, histogram update
+// One step = two query rows (16 padded columns) of this thread's key.  All shared-memory loads of the step (statistics, bias
+// vectors, histogram entries) are issued back to back BEFORE the arithmetic and every store comes after it: the loads and
+// stores are volatile asm (the compiler keeps their order), so a row-by-row formulation serialises load -> math -> store chains
+// of ~200 cycles each, which two warps per scheduler cannot hide.
 template <int WW, bool MASKED, bool F16>
-__device__ __forceinline__ void bwd_row(const uint32_t* rs, const uint32_t* rd, uint32_t ld_a, const uint4& bias, uint32_t nq2lo,
-                                        uint32_t nq2hi, float scale_log2, uint32_t hist_a, uint32_t (&pw)[4], uint32_t (&dw)[4]) {
-    // {lse * log2e, delta} of the 8 queries: four broadcast 16-byte loads
-    float l2[8], dl[8];
+__device__ __forceinline__ void bwd_step(const uint32_t (&rs)[16], const uint32_t (&rd)[16], uint32_t ld_a, uint32_t tab0, uint32_t tab1,
+                                         uint32_t hist0, uint32_t hist1, bool ok0, bool ok1, const uint32_t (&nq)[4], float scale_log2,
+                                         uint32_t (&pw)[8], uint32_t (&dw)[8]) {
+    float4 st[8];                      // {lse * log2e, delta} pairs of the 16 queries (broadcast loads)
 #pragma unroll
-    for (int v = 0; v < 4; ++v) {
-        const float4 t = lds_f4(ld_a + v * 16);
-        l2[2 * v] = t.x; dl[2 * v] = t.y; l2[2 * v + 1] = t.z; dl[2 * v + 1] = t.w;
-    }
-    float ds[8], pp[8];
+    for (int v = 0; v < 8; ++v) st[v] = lds_f4(ld_a + v * 16);
+    uint4 bias[2];
+    bias[0] = tc::lds_u4(tab0); bias[1] = tc::lds_u4(tab1);
+    // d(bias table): the 8 scores of a (key, query row) are 8 consecutive entries of the key's w_j-shifted histogram copy.
+    // Query row rho of key row (d_j, h_j) and query row rho + 1 of key row (d_j, h_j + 1) are the SAME histogram row (in two
+    // lanes of this warp), so the two rows' read-modify-writes must not overlap: row 1 is loaded after row 0 is stored.
+    // (A row that does not exist adds zeros to a spare row behind the histogram: the stores stay unconditional.)
+    float4 h0 = lds_f4(hist0), h1 = lds_f4(hist0 + 16);
+    float ds[16], pp[16];
 #pragma unroll
-    for (int e = 0; e < 8; ++e) {
-        if (e >= WW) { pp[e] = 0.f; ds[e] = 0.f; continue; }
-        const uint32_t w = word_of(bias, e >> 1);
-        float x = fmaf(__uint_as_float(rs[e]), scale_log2, (e & 1) ? bf_hi(w) : bf_lo(w)) - l2[e];
-        if (MASKED) x = (((e < 4 ? nq2lo : nq2hi) >> (8 * (e & 3))) & 0xFFu) ? x + MASKV : x;
-        const float pe = tc::ex2_approx(x);
-        pp[e] = pe;
-        ds[e] = pe * (__uint_as_float(rd[e]) - dl[e]);
-    }
-    // d(bias table): the 8 scores of this (key, query row) are 8 consecutive entries of the key's w_j-shifted histogram copy
-    {
-        float4 h0 = lds_f4(hist_a), h1 = lds_f4(hist_a + 16);
-        h0.x += ds[0]; h0.y += ds[1]; h0.z += ds[2]; h0.w += ds[3];
-        h1.x += ds[4]; h1.y += ds[5]; h1.z += ds[6]; h1.w += ds[7];
-        sts_f4(hist_a, h0); sts_f4(hist_a + 16, h1);
+    for (int r = 0; r < 2; ++r) {
+#pragma unroll
+        for (int sl = 0; sl < 8; ++sl) {
+            const int e = r * 8 + sl;
+            if (sl >= WW) { pp[e] = 0.f; ds[e] = 0.f; continue; }
+            const float4 t = st[e >> 1];
+            const float l2 = (e & 1) ? t.z : t.x, dl = (e & 1) ? t.w : t.y;
+            const uint32_t w = word_of(bias[r], sl >> 1);
+            float x = fmaf(__uint_as_float(rs[e]), scale_log2, (sl & 1) ? bf_hi(w) : bf_lo(w)) - l2;
+            // region mismatch byte 0xFF -> 0xFF000000 = -1.7e38 (one PRMT), added to the exponent; 0x00 -> +0.0
+        if (MASKED) x += __uint_as_float(__byte_perm(nq[e >> 2], 0u, 0x0444u | ((uint32_t)(e & 3) << 12)));
+            const float pe = (r ? ok1 : ok0) ? tc::ex2_approx(x) : 0.f;
+            pp[e] = pe;
+            ds[e] = pe * (__uint_as_float(rd[e]) - dl);
+        }
+        h0.x += ds[8 * r + 0]; h0.y += ds[8 * r + 1]; h0.z += ds[8 * r + 2]; h0.w += ds[8 * r + 3];
+        h1.x += ds[8 * r + 4]; h1.y += ds[8 * r + 5]; h1.z += ds[8 * r + 6]; h1.w += ds[8 * r + 7];
+        if (r == 0) {
+            sts_f4(hist0, h0); sts_f4(hist0 + 16, h1);
+            h0 = lds_f4(hist1); h1 = lds_f4(hist1 + 16);
+        } else {
+            sts_f4(hist1, h0); sts_f4(hist1 + 16, h1);
+        }
     }
 #pragma unroll
-    for (int e = 0; e < 8; e += 2) {
+    for (int e = 0; e < 16; e += 2) {
         pw[e >> 1] = pack16<F16>(pp[e], pp[e + 1]);
         dw[e >> 1] = pack16<F16>(ds[e], ds[e + 1]);
     }
@@ -125,7 +142,7 @@ __global__ void tc2_dbias_reduce_kernel(const float* __restrict__ part, int grou
 template <int WW, bool F16>
 __global__ void __launch_bounds__(B_THREADS, 1)
 attn2_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmKV,
-                 const __grid_constant__ CUtensorMap tmDO, const BwdParams2 p) {
+                 const __grid_constant__ CUtensorMap tmDO, const __grid_constant__ CUtensorMap tmDKV, const BwdParams2 p) {
     extern __shared__ uint8_t smem_raw[];
     uint8_t* base = smem_raw + ((1024u - (tc::smem_u32(smem_raw) & 1023u)) & 1023u);
     const BBars s = bbars_of(base);
@@ -137,7 +154,7 @@ attn2_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
     const uint32_t base_a = tc::smem_u32(base);
 
     if (warp == BW_TMA && lane == 0) {
-        tc::prefetch_tmap(&tmQ); tc::prefetch_tmap(&tmKV); tc::prefetch_tmap(&tmDO);
+        tc::prefetch_tmap(&tmQ); tc::prefetch_tmap(&tmKV); tc::prefetch_tmap(&tmDO); tc::prefetch_tmap(&tmDKV);
         for (int i = 0; i < 2; ++i) {
             tc::mbar_init(&s.kv_full[i], 1); tc::mbar_init(&s.kv_empty[i], 1);
             tc::mbar_init(&s.s_full[i], 1); tc::mbar_init(&s.p_full[i], 4); tc::mbar_init(&s.ds_free[i], 1);
@@ -153,8 +170,8 @@ attn2_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
     // the dS chunks and the zero chunk between them, the histograms; load the head's table; query-row offsets
     for (int n = threadIdx.x; n < BO_QD / 16; n += B_THREADS) reinterpret_cast<uint4*>(base + BO_KV)[n] = make_uint4(0, 0, 0, 0);
     for (int n = threadIdx.x; n < 3 * 16384 / 16; n += B_THREADS) reinterpret_cast<uint4*>(base + BO_DS)[n] = make_uint4(0, 0, 0, 0);
-    for (int n = threadIdx.x; n < 2 * hist_bytes / 16; n += B_THREADS) {
-        const int c = n / (hist_bytes / 16), o = n - c * (hist_bytes / 16);
+    for (int n = threadIdx.x; n < 2 * (hist_bytes + 64) / 16; n += B_THREADS) {
+        const int c = n / ((hist_bytes + 64) / 16), o = n - c * ((hist_bytes + 64) / 16);
         reinterpret_cast<uint4*>(base + BO_HIST + c * HIST_MAX_BYTES)[o] = make_uint4(0, 0, 0, 0);
     }
     {
@@ -210,18 +227,46 @@ attn2_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
             // Software pipeline with a lag of one half-block (across tiles and items): S^T / dP^T of half-block c are issued, then
             // the dV / dK / dQ MMAs of half-block c - 1, whose exp pass ran meanwhile.  One consume site, straight-line code.
             const int total = n_items * hb_per_item;
-            int i_it = 0, i_T = 0, i_hb = 0, i_kt = 0;          // issue cursor
-            int p_it = 0, p_T = 0, p_hb = 0, p_kt = 0;          // the pending (issued, not yet consumed) half-block
-            int use_ds0 = 0, use_ds1 = 0; (void)use_ds0; (void)use_ds1;
-            for (int c = 0; c <= total; ++c) {
+            int i_it = 0, i_T = 0, i_hb = 0, i_kt = 0;          // issue cursor (half-block c)
+            int q_it = 0, q_T = 0, q_hb = 0, q_kt = 0;          // half-block c - 1
+            int p_it = 0, p_T = 0, p_hb = 0, p_kt = 0;          // half-block c - 2: the one consumed in this iteration
+            const bool mprof = VSW_ATTN2_PROF && p.dbg && blockIdx.x == 0;
+            long long m_wp = 0, m_wl = 0, m_wk = 0, m_we = 0, m_n = 0;
+            const long long m_t0 = mprof ? clock64() : 0;
+            // Order per iteration c:  dV / dK of half-block c - 2 (they read P^T / dS^T from stage c & 1)  ->  S^T / dP^T of half-block
+            // c into that stage  ->  dQ of half-block c - 2 (shared memory operands only).  The exp group that finished c - 2 gets
+            // its next scores after 12 MMAs instead of 20; the tensor pipe runs in order, so no barrier is needed between them.
+            for (int c = 0; c <= total + 1; ++c) {
+                const int cp = c - 2;
+                const int pst = cp & 1, pqs = (cp + NQD) % NQD, pks = p_kt & 1, par = p_kt & 1;   // (unused while c < 2)
+                if (c >= 2) {
+                    const long long t_e = mprof ? clock64() : 0;
+                    if (p_hb == 0 && p_kt >= 2) wait2(&s.dkv_empty[par], ((p_kt >> 1) - 1) & 1, 5);   // dK / dV buffer read out (tile kt - 2)
+                    long long t_b = 0;
+                    if (mprof) { t_b = clock64(); m_we += t_b - t_e; }
+                    wait2(&s.p_full[pst], (cp >> 1) & 1, 3);
+                    tc::tc_fence_after();
+                    if (mprof) { m_wp += clock64() - t_b; m_n += 1; }
+                    const uint32_t qda = base_a + BO_QD + pqs * 8192;
+                    const uint32_t acc_kv = p_hb > 0 ? 1u : 0u;
+#pragma unroll
+                    for (int k = 0; k < 4; ++k)   // dV_T (+)= P^T dO_hb : 16 queries per MMA
+                        tc::umma_bf16_ts(TB_DKV + 64 * par + 32, pst * TB_STAGE + TB_ST + 8 * k, tc::smem_desc_sw64(qda + 4096 + k * 1024, 0, 512), id_t, k ? 1u : acc_kv);
+#pragma unroll
+                    for (int k = 0; k < 4; ++k)   // dK_T (+)= dS^T Q_hb
+                        tc::umma_bf16_ts(TB_DKV + 64 * par, pst * TB_STAGE + TB_DP + 8 * k, tc::smem_desc_sw64(qda + k * 1024, 0, 512), id_t, k ? 1u : acc_kv);
+                    tc::umma_commit(&s.qd_empty[pqs]);
+                }
                 if (c < total) {
                     const int ks = i_kt & 1, st = c & 1, qs = c % NQD;
+                    long long t_a = 0;
+                    if (mprof) t_a = clock64();
                     if (i_hb == 0) wait2(&s.kv_full[ks], (i_kt >> 1) & 1, 4);
+                    if (mprof) { const long long t_k = clock64(); m_wk += t_k - t_a; t_a = t_k; }
                     wait2(&s.qd_full[qs], (c / NQD) & 1, 7);
                     tc::tc_fence_after();
+                    if (mprof) m_wl += clock64() - t_a;
                     const uint32_t kva = base_a + BO_KV + ks * 16384, qda = base_a + BO_QD + qs * 8192;
-                    // into stage st: its previous contents were consumed by the MMAs of half-block c - 2 (issued earlier by this
-                    // thread; the tensor pipe runs in order)
 #pragma unroll
                     for (int k = 0; k < 2; ++k)
                         tc::umma_bf16(st * TB_STAGE + TB_ST, tc::smem_desc_sw64(kva + k * 32, 0, 512), tc::smem_desc_sw64(qda + k * 32, 0, 512), id_s, k);
@@ -230,24 +275,13 @@ attn2_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
                         tc::umma_bf16(st * TB_STAGE + TB_DP, tc::smem_desc_sw64(kva + 8192 + k * 32, 0, 512), tc::smem_desc_sw64(qda + 4096 + k * 32, 0, 512), id_s, k);
                     tc::umma_commit(&s.s_full[st]);
                 }
-                if (c > 0) {
-                    const int cp = c - 1;
-                    const int st = cp & 1, qs = cp % NQD, ks = p_kt & 1, par = p_kt & 1;
-                    if (p_hb == 0 && p_kt >= 2) wait2(&s.dkv_empty[par], ((p_kt >> 1) - 1) & 1, 5);   // dK / dV buffer read out (tile kt - 2)
+                if (c >= 2) {
+                    const long long t_e = mprof ? clock64() : 0;
                     if (p_T == 0 && p_hb == 0 && p_it > 0) wait2(s.dq_empty, (p_it - 1) & 1, 6);       // dQ of the previous item read out
-                    wait2(&s.p_full[st], (cp >> 1) & 1, 3);
-                    tc::tc_fence_after();
-                    const uint32_t kva = base_a + BO_KV + ks * 16384, qda = base_a + BO_QD + qs * 8192;
-                    const uint32_t acc_kv = p_hb > 0 ? 1u : 0u;
-#pragma unroll
-                    for (int k = 0; k < 4; ++k)   // dV_T (+)= P^T dO_hb : 16 queries per MMA
-                        tc::umma_bf16_ts(TB_DKV + 64 * par + 32, st * TB_STAGE + TB_ST + 8 * k, tc::smem_desc_sw64(qda + 4096 + k * 1024, 0, 512), id_t, k ? 1u : acc_kv);
-#pragma unroll
-                    for (int k = 0; k < 4; ++k)   // dK_T (+)= dS^T Q_hb
-                        tc::umma_bf16_ts(TB_DKV + 64 * par, st * TB_STAGE + TB_DP + 8 * k, tc::smem_desc_sw64(qda + k * 1024, 0, 512), id_t, k ? 1u : acc_kv);
-                    tc::umma_commit(&s.qd_empty[qs]);
+                    if (mprof) m_we += clock64() - t_e;
                     // dQ_qb (+)= dS K_T with M = 128 query rows of which this half-block fills 64: the other 64-row chunk of the
                     // MN-major A operand is the zero chunk (even half-block: data | zeros, odd: zeros | data)
+                    const uint32_t kva = base_a + BO_KV + pks * 16384;
                     const uint32_t dsa = base_a + BO_DS + ((p_hb & 1) ? 16384 : 0);
                     const uint32_t acc_q = (p_T == 0 && (p_hb & 1) == 0) ? 0u : 1u;
                     const int qb = p_hb >> 1;
@@ -257,14 +291,15 @@ attn2_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
                     tc::umma_commit(&s.ds_free[p_hb & 1]);
                     if (p_hb == p.nhb - 1) {
                         tc::umma_commit(&s.dkv_full[par]);
-                        tc::umma_commit(&s.kv_empty[ks]);
                         if (p_T == p.nT - 1) tc::umma_commit(s.dq_full);
                     }
                 }
-                // the half-block just issued becomes the pending one; advance the issue cursor
-                p_it = i_it; p_T = i_T; p_hb = i_hb; p_kt = i_kt;
+                // shift the cursors: c - 1 becomes c - 2, c becomes c - 1; advance the issue cursor
+                p_it = q_it; p_T = q_T; p_hb = q_hb; p_kt = q_kt;
+                q_it = i_it; q_T = i_T; q_hb = i_hb; q_kt = i_kt;
                 if (++i_hb == p.nhb) { i_hb = 0; ++i_kt; if (++i_T == p.nT) { i_T = 0; ++i_it; } }
             }
+            if (mprof) { p.dbg[8] += m_wp; p.dbg[9] += m_wl; p.dbg[10] += m_we; p.dbg[13] += m_wk; p.dbg[12] += m_n; p.dbg[20] += clock64() - m_t0; }
         }
     } else if (warp == BW_AUX0 || warp == BW_AUX1) {
         // ===================== aux warps: {lse * log2e, delta} per query; region ids =====================
@@ -331,25 +366,44 @@ attn2_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
         const int wj = 2 * q + (lane & 1);                 // this thread's key column w_j (7 = dummy for a 7-wide window)
         const int rl = lane >> 1;                           // key row inside the tile (0..13; 14, 15: unused lanes)
         const bool lane_real = lane < 2 * KTR && wj < p.ww;
-        const uint32_t tab_a = base_a + BO_TAB, hist_a = base_a + BO_HIST + g * HIST_MAX_BYTES;
-        const int ND = 2 * p.wdc - 1;
+        // histogram rows of odd w_j sit 16 bytes further: the two key columns of a quarter-warp then hit different banks
+        const uint32_t tab_a = base_a + BO_TAB, hist_a = base_a + BO_HIST + g * HIST_MAX_BYTES + (lane & 1) * 16;
         const int krow = q * 32 + lane;                     // row of this key in the K / V / dS tiles
+        const int dummy_row = p.tab_bytes / 16;             // spare row behind the table and behind each histogram copy
         int c = 0, kt = 0;
-        int use_ds[2] = {0, 0};                              // uses so far of the even / odd dS chunk (all half-blocks, owned or not)
+        long long x_ws = 0, x_wd = 0, x_work = 0, x_n = 0, x_epi = 0, x_nepi = 0, x_dq = 0, x_aux = 0, x_last = 0, x_g0 = 0, x_g1 = 0, x_g2 = 0, x_g3 = 0;
+        const bool xprof = VSW_ATTN2_PROF && p.dbg && blockIdx.x == 0 && warp == 0 && lane == 0;
+        const long long x_t0 = xprof ? clock64() : 0;
+        int use_ds0 = 0, use_ds1 = 0;                        // uses so far of the even / odd dS chunk (all half-blocks, owned or not; scalars: a
+                                                             // dynamically indexed array would live in local memory, ~700 cycles per access here)
         int pendT = -1, pend_b = 0, pend_kt = 0;            // deferred dK / dV epilogue
+        // dK / dV of a finished key tile: TMEM -> registers -> (scaled, packed) into the tile's own K / V shared-memory buffer, whose
+        // rows are in TMEM lane order -> tensor-map stores with the boxes the tile was loaded with (window-row padding and rows
+        // beyond the window are clipped by the map).  Per-lane 16-byte global stores of 64-byte rows cost 32 LSU wavefronts per
+        // instruction -- 10 k cycles per item on the pipe the exp warps are bound by.  The K / V buffer goes back to the loader
+        // only after the stores have read it (kv_release, called after the group's next half-block).
+        int kv_pending = -1;
+        auto kv_release = [&]() {
+            if (kv_pending >= 0) {
+                if (q == 0 && lane == 0) { tc::bulk_wait_read_all(); tc::mbar_arrive(&s.kv_empty[kv_pending]); }
+                kv_pending = -1;
+            }
+        };
         auto dkv_epilogue = [&](int T_, int eb, int ekt) {
             const int par = ekt & 1;
+            const long long x_e0 = xprof ? clock64() : 0;
+            kv_release();
             wait2(&s.dkv_full[par], (ekt >> 1) & 1, 9);
             tc::tc_fence_after();
             uint32_t dk[32], dv[32];
             tc::tmem_ld_32x32(tmem + lane_base + TB_DKV + 64 * par, dk);
             tc::tmem_ld_32x32(tmem + lane_base + TB_DKV + 64 * par + 32, dv);
             tc::tmem_ld_wait();
-            const int row = T_ * KTR + rl;
-            if (lane_real && row < p.KR) {
-                const long long tok = (long long)eb * p.N + row * p.ww + wj;
-                uint4* dstk = reinterpret_cast<uint4*>((uint16_t*)p.dqkv + (tok * 3 + 1) * C + h * HD);
-                uint4* dstv = reinterpret_cast<uint4*>((uint16_t*)p.dqkv + (tok * 3 + 2) * C + h * HD);
+            tc::tc_fence_before();
+            __syncwarp();
+            if (lane == 0) tc::mbar_arrive(&s.dkv_empty[par]);
+            const uint32_t kva = base_a + BO_KV + par * 16384 + krow * 64;
+            if (lane < 2 * KTR) {                      // rows 28..31 of a quadrant stay zero (no box ever covers them)
 #pragma unroll
                 for (int v4 = 0; v4 < 4; ++v4) {
                     uint4 u, w;
@@ -361,17 +415,31 @@ attn2_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
                     w.y = pack16<F16>(__uint_as_float(dv[8 * v4 + 2]), __uint_as_float(dv[8 * v4 + 3]));
                     w.z = pack16<F16>(__uint_as_float(dv[8 * v4 + 4]), __uint_as_float(dv[8 * v4 + 5]));
                     w.w = pack16<F16>(__uint_as_float(dv[8 * v4 + 6]), __uint_as_float(dv[8 * v4 + 7]));
-                    dstk[v4] = u; dstv[v4] = w;
+                    const uint32_t off = (uint32_t)((v4 ^ ((krow >> 1) & 3)) << 4);     // 64-byte swizzle of the tile
+                    tc::sts_u4(kva + off, u);
+                    tc::sts_u4(kva + 8192 + off, w);
                 }
             }
-            tc::tc_fence_before();
-            __syncwarp();
-            if (lane == 0) tc::mbar_arrive(&s.dkv_empty[par]);
+            tc::fence_proxy_async();
+            tc::named_bar_sync(1 + g, 128);            // the four warps of this group
+            if (q == 0 && lane == 0) {
+                const uint8_t* kv = base + BO_KV + par * 16384;
+#pragma unroll
+                for (int which = 0; which < 2; ++which)
+#pragma unroll
+                    for (int qq = 0; qq < 4; ++qq)
+                        tc::tma_store_4d(&tmDKV, kv + which * 8192 + qq * 2048, (1 + which) * C + h * HD, 2 * qq, T_ * KTR, eb);
+                tc::bulk_commit_group();
+            }
+            kv_pending = par;
+            if (xprof) { x_epi += clock64() - x_e0; x_nepi += 1; }
         };
         for (int it = 0; it < n_items; ++it) {
             const int ast = it & 1;
             const int b_ = gi + it * p.groups;
+            const long long x_a0 = xprof ? clock64() : 0;
             wait2(&s.aux_full[ast], (it >> 1) & 1, 10);
+            if (xprof) x_aux += clock64() - x_a0;
             const bool masked = reinterpret_cast<const int*>(base + BO_FLAG)[ast] != 0;
             const uint32_t ld_base = base_a + BO_LD + ast * MAXCOLS * 8;
             const uint32_t regq_a = base_a + BO_REGQ + ast * MAXCOLS;
@@ -380,60 +448,88 @@ attn2_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
                 const int dj = (T * KTR + rl) / p.wh, hj = (T * KTR + rl) % p.wh;
                 const bool key_real = lane_real && T * KTR + rl < p.KR;
                 // table / histogram row of (this key, query row rho) = rowbase + koff[rho]
-                const int rowbase = (wj * ND - dj + p.wdc - 1) * p.NHt - hj + p.wh - 1;
+                const int rowbase = wj * p.blk + (p.wdc - 1 - dj) * p.NHt - hj + p.wh - 1;
                 const uint32_t regj4 = masked ? (uint32_t)regk[T * 128 + krow] * 0x01010101u : 0u;
                 for (int hb = 0; hb < p.nhb; ++hb, ++c) {
-                    const int ds_use = use_ds[hb & 1]++;
+                    const int ds_use = (hb & 1) ? use_ds1++ : use_ds0++;
                     if ((c & 1) != g) continue;
                     const int st = c & 1;
+                    if (xprof && x_last && hb >= 2) x_g3 += clock64() - x_last;
                     // the deferred dK / dV epilogue of the previous key tile (this group's turn): its MMAs retired long ago
                     if (pendT >= 0 && hb >= 2) { dkv_epilogue(pendT, pend_b, pend_kt); pendT = -1; }
+                    long long x_a = 0, x_b = 0, x_c = 0;
+                    if (xprof) {
+                        x_a = clock64();
+                        if (x_last) { if (hb >= 2) x_g0 += x_a - x_last; else if (T > 0) x_g1 += x_a - x_last; else x_g2 += x_a - x_last; }
+                    }
                     wait2(&s.s_full[st], (c >> 1) & 1, 11);
-                    wait2(&s.ds_free[hb & 1], (ds_use & 1) ^ 1, 12);   // the dS chunk's previous contents have been multiplied
+                    if (xprof) x_b = clock64();
                     tc::tc_fence_after();
+                    if (xprof) x_c = clock64();
                     const uint32_t trow = tmem + lane_base + st * TB_STAGE;
                     const uint32_t ds_a = base_a + BO_DS + ((hb & 1) ? 32768 : 0);
                     const int nrows = min(QHR, p.KR - hb * QHR);      // query rows of this half-block that exist
-#pragma unroll 1
-                    for (int k = 0; k < 4; ++k) {                     // 16 query columns = 2 query rows per step
-                        uint32_t rs[16], rd[16];
-                        tc::tmem_ld_32x16(trow + TB_ST + 16 * k, rs);
-                        tc::tmem_ld_32x16(trow + TB_DP + 16 * k, rd);
-                        uint32_t pw[8], dw[8];
-                        uint32_t nq[4] = {0, 0, 0, 0};
-                        if (masked) {
-                            const uint4 rg = tc::lds_u4(regq_a + hb * 64 + k * 16);
-                            nq[0] = __vcmpne4(rg.x, regj4); nq[1] = __vcmpne4(rg.y, regj4);
-                            nq[2] = __vcmpne4(rg.z, regj4); nq[3] = __vcmpne4(rg.w, regj4);
-                        }
+                    // 4 steps of 16 query columns (2 query rows), fully unrolled; the TMEM loads of step k + 1 are in flight while
+                    // step k is computed (two warps per scheduler cannot hide a load-use latency per step)
+                    auto steps = [&](auto masked_tag) {
+                        constexpr bool MK = decltype(masked_tag)::value;
+                        uint32_t rs[2][16], rd[2][16];
+                        uint32_t dwk[8];                 // dS of step 0, stored with step 1's (below)
+                        tc::tmem_ld_32x16(trow + TB_ST, rs[0]);
+                        tc::tmem_ld_32x16(trow + TB_DP, rd[0]);
                         tc::tmem_ld_wait();
 #pragma unroll
-                        for (int r = 0; r < 2; ++r) {
-                            const int rho = hb * QHR + 2 * k + r;
-                            uint32_t* pwr = pw + 4 * r; uint32_t* dwr = dw + 4 * r;
-                            if (2 * k + r < nrows && key_real) {
-                                const int rowidx = rowbase + koff[rho];
-                                const uint4 bias = tc::lds_u4(tab_a + rowidx * 16);
-                                uint32_t (&pw4)[4] = *reinterpret_cast<uint32_t (*)[4]>(pwr);
-                                uint32_t (&dw4)[4] = *reinterpret_cast<uint32_t (*)[4]>(dwr);
-                                if (masked) bwd_row<WW, true, F16>(rs + 8 * r, rd + 8 * r, ld_base + rho * 64, bias, nq[2 * r], nq[2 * r + 1], p.scale_log2, hist_a + rowidx * 32, pw4, dw4);
-                                else bwd_row<WW, false, F16>(rs + 8 * r, rd + 8 * r, ld_base + rho * 64, bias, 0u, 0u, p.scale_log2, hist_a + rowidx * 32, pw4, dw4);
-                            } else {
-#pragma unroll
-                                for (int e = 0; e < 4; ++e) { pwr[e] = 0u; dwr[e] = 0u; }
+                        for (int k = 0; k < 4; ++k) {
+                            const int cur = k & 1;
+                            if (k + 1 < 4) {
+                                tc::tmem_ld_32x16(trow + TB_ST + 16 * (k + 1), rs[cur ^ 1]);
+                                tc::tmem_ld_32x16(trow + TB_DP + 16 * (k + 1), rd[cur ^ 1]);
                             }
+                            uint32_t pw[8], dw[8];
+                            uint32_t nq[4] = {0, 0, 0, 0};
+                            if (MK) {
+                                const uint4 rg = tc::lds_u4(regq_a + hb * 64 + k * 16);
+                                nq[0] = __vcmpne4(rg.x, regj4); nq[1] = __vcmpne4(rg.y, regj4);
+                                nq[2] = __vcmpne4(rg.z, regj4); nq[3] = __vcmpne4(rg.w, regj4);
+                            }
+                            {
+                                const int rho = hb * QHR + 2 * k;
+                                const bool ok0 = 2 * k < nrows && key_real, ok1 = 2 * k + 1 < nrows && key_real;
+                                const int2 ko = *reinterpret_cast<const int2*>(koff + rho);
+                                const int ri0 = ok0 ? rowbase + ko.x : dummy_row, ri1 = ok1 ? rowbase + ko.y : dummy_row;   // a spare row behind the table / histogram stands in for a missing row
+                                bwd_step<WW, MK, F16>(rs[cur], rd[cur], ld_base + rho * 64, tab_a + ri0 * 16, tab_a + ri1 * 16, hist_a + ri0 * 32,
+                                                      hist_a + ri1 * 32, ok0, ok1, nq, p.scale_log2, pw, dw);
+                            }
+                            tc::tmem_st_32x8(trow + TB_ST + 8 * k, pw);      // P^T  (A operand of dV)
+                            tc::tmem_st_32x8(trow + TB_DP + 8 * k, dw);      // dS^T (A operand of dK)
+                            // dS^T row of this key into the MN-major A tile of dQ = dS K: 16 queries = two 16-byte units.  The tile's
+                            // previous contents are still being multiplied (dQ of half-block c - 2 is issued after this half-block's
+                            // scores): step 0 keeps its dS in registers and the wait sits behind step 1's arithmetic.
+                            if (k == 0) {
+#pragma unroll
+                                for (int e = 0; e < 8; ++e) dwk[e] = dw[e];
+                            } else {
+                                if (k == 1) {
+                                    const long long x_w0 = xprof ? clock64() : 0;
+                                    wait2(&s.ds_free[hb & 1], (ds_use & 1) ^ 1, 12);
+                                    if (xprof) x_wd += clock64() - x_w0;
+                                    tc::sts_u4(ds_a + sw128_unit(krow, 0), make_uint4(dwk[0], dwk[1], dwk[2], dwk[3]));
+                                    tc::sts_u4(ds_a + sw128_unit(krow, 1), make_uint4(dwk[4], dwk[5], dwk[6], dwk[7]));
+                                }
+                                tc::sts_u4(ds_a + sw128_unit(krow, 2 * k), make_uint4(dw[0], dw[1], dw[2], dw[3]));
+                                tc::sts_u4(ds_a + sw128_unit(krow, 2 * k + 1), make_uint4(dw[4], dw[5], dw[6], dw[7]));
+                            }
+                            if (k + 1 < 4) tc::tmem_ld_wait();
                         }
-                        tc::tmem_st_32x8(trow + TB_ST + 8 * k, pw);      // P^T  (A operand of dV)
-                        tc::tmem_st_32x8(trow + TB_DP + 8 * k, dw);      // dS^T (A operand of dK)
-                        // dS^T row of this key into the MN-major A tile of dQ = dS K: 16 queries = two 16-byte units
-                        tc::sts_u4(ds_a + sw128_unit(krow, 2 * k), make_uint4(dw[0], dw[1], dw[2], dw[3]));
-                        tc::sts_u4(ds_a + sw128_unit(krow, 2 * k + 1), make_uint4(dw[4], dw[5], dw[6], dw[7]));
-                    }
+                    };
+                    if (masked) steps(std::true_type{}); else steps(std::false_type{});
                     tc::tmem_st_wait();
                     tc::fence_proxy_async();   // the dS tile is read by the tensor core
                     tc::tc_fence_before();
                     __syncwarp();
                     if (lane == 0) tc::mbar_arrive(&s.p_full[st]);
+                    kv_release();
+                    if (xprof) { x_last = clock64(); x_ws += x_b - x_a; x_wd += x_c - x_b; x_work += x_last - x_c; x_n += 1; }
                 }
                 // this tile's dK / dV: read out by group T & 1, deferred into its work on the next tile
                 if ((kt & 1) == g) {
@@ -443,6 +539,7 @@ attn2_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
             }
             // ---- end of the item: flush the pending dK / dV epilogue, then dQ (group g: query blocks g, g + 2)
             if (pendT >= 0) { dkv_epilogue(pendT, pend_b, pend_kt); pendT = -1; }
+            const long long x_q0 = xprof ? clock64() : 0;
             wait2(s.dq_full, it & 1, 13);
             tc::tc_fence_after();
             for (int qb = g; qb < (p.nhb + 1) / 2; qb += 2) {
@@ -466,7 +563,11 @@ attn2_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
             tc::tc_fence_before();
             __syncwarp();
             if (lane == 0) { tc::mbar_arrive(s.dq_empty); tc::mbar_arrive(&s.aux_empty[ast]); }
+            kv_release();
+            if (xprof) x_dq += clock64() - x_q0;
         }
+        if (q == 0 && lane == 0) tc::bulk_wait_all();      // this thread's dK / dV tile stores
+        if (xprof) { p.dbg[0] += x_ws; p.dbg[1] += x_work; p.dbg[2] += x_n; p.dbg[3] += x_wd; p.dbg[6] += clock64() - x_t0; p.dbg[4] += x_nepi; p.dbg[5] += x_epi; p.dbg[7] += x_dq; p.dbg[14] += x_aux; p.dbg[15] += x_g0; p.dbg[17] += x_g1; p.dbg[18] += x_g2; p.dbg[19] += x_g3; }
     }
 
     __syncwarp();
@@ -474,7 +575,7 @@ attn2_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
     __syncthreads();
     // fold the two histogram copies and the per-w_j shifted layout back into the table column (fixed order)
     if (!*p.poison) {
-        const int ND = 2 * p.wdc - 1, NW = 2 * p.ww - 1;
+        const int NW = 2 * p.ww - 1;
         float* part = p.dbias_part + ((long long)gi * p.nH + h) * p.L;
         for (int l = threadIdx.x; l < p.L; l += B_THREADS) {
             const int dw = l % NW, r = l / NW;              // r = dd * NHt + dh
@@ -482,7 +583,7 @@ attn2_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
             for (int wj = 0; wj < p.ww; ++wj) {
                 const int wi = dw - (p.ww - 1) + wj;        // table index dw = w_i - w_j + ww - 1
                 if (wi < 0 || wi >= p.ww) continue;
-                const int idx = ((wj * ND * p.NHt) + r) * SLOT + wi;
+                const int idx = (wj * p.blk + r) * SLOT + wi + (wj & 1) * 4;
                 t += reinterpret_cast<const float*>(base + BO_HIST)[idx];
                 t += reinterpret_cast<const float*>(base + BO_HIST + HIST_MAX_BYTES)[idx];
             }
@@ -494,6 +595,14 @@ attn2_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
         tc::tmem_dealloc(tmem, TMEM_COLS);
     }
 }
+
+// table rows per w_j block, padded so that consecutive blocks start 4 rows apart mod 8 (bank-conflict-free quarter-warps)
+int bwd2_blk(const Geometry& g) {
+    int blk = (2 * g.wdc - 1) * (2 * g.wh - 1);
+    while (blk % 8 != 4) ++blk;
+    return blk;
+}
+int bwd2_tab_bytes(const Geometry& g) { return g.ww * bwd2_blk(g) * SLOT * 2; }
 
 int bwd2_groups(int B_, int nH, int sms) {
     int g = sms / nH;
@@ -519,7 +628,7 @@ int tc2_attn_bwd(const void* qkv, const void* out, const void* dout, const float
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     if (sms > kNumSMs) sms = kNumSMs;   // the workspace size is computed for at most kNumSMs CTAs
-    if ((dtype != VSW_BF16 && dtype != VSW_F16) || !geometry_of(N, hd, L, window_dims, &g) || g.tab_bytes > BTAB_MAX_BYTES || nH > sms || !aligned16(qkv) ||
+    if ((dtype != VSW_BF16 && dtype != VSW_F16) || !geometry_of(N, hd, L, window_dims, &g) || bwd2_tab_bytes(g) + 32 > BTAB_MAX_BYTES || nH > sms || !aligned16(qkv) ||
         !aligned16(out) || !aligned16(dout) || !aligned16(dqkv)) {
         set_error("tcgen05 window attention bwd: needs bf16/fp16, head_dim 32, the configured window (rows of <= 8 tokens) as "
                   "layout hint and N <= 448 a whole number of window rows (hd=%d N=%d L=%d window_dims=0x%x)", hd, N, L, window_dims);
@@ -528,17 +637,19 @@ int tc2_attn_bwd(const void* qkv, const void* out, const void* dout, const float
     const int groups = bwd2_groups(B_, nH, sms);
     if (ws_bytes < (size_t)groups * nH * L * sizeof(float)) { set_error("tcgen05 attention bwd: workspace too small"); return VSW_ERR_WORKSPACE; }
     const int C = nH * HD;
-    CUtensorMap tmQ, tmKV, tmDO;
+    CUtensorMap tmQ, tmKV, tmDO, tmDKV;
     {
         const uint64_t dims[4] = {(uint64_t)3 * C, (uint64_t)g.ww, (uint64_t)g.KR, (uint64_t)B_};
         const uint64_t strides[4] = {1, (uint64_t)3 * C, (uint64_t)g.ww * 3 * C, (uint64_t)N * 3 * C};
         const uint32_t boxq[4] = {HD, SLOT, QHR, 1}, boxk[4] = {HD, 2, KTR, 1};
-        if (!make_tmap_nd_bf16(&tmQ, qkv, 4, dims, strides, boxq, 64) || !make_tmap_nd_bf16(&tmKV, qkv, 4, dims, strides, boxk, 64)) return VSW_ERR_CUDA;
+        if (!make_tmap_nd_bf16(&tmQ, qkv, 4, dims, strides, boxq, 64) || !make_tmap_nd_bf16(&tmKV, qkv, 4, dims, strides, boxk, 64) ||
+            !make_tmap_nd_bf16(&tmDKV, dqkv, 4, dims, strides, boxk, 64)) return VSW_ERR_CUDA;
         const uint64_t dimo[4] = {(uint64_t)C, (uint64_t)g.ww, (uint64_t)g.KR, (uint64_t)B_};
         const uint64_t strido[4] = {1, (uint64_t)C, (uint64_t)g.ww * C, (uint64_t)N * C};
         if (!make_tmap_nd_bf16(&tmDO, dout, 4, dimo, strido, boxq, 64)) return VSW_ERR_CUDA;
     }
-    const size_t tab_total = (size_t)nH * g.tab_bytes;
+    const int blk = bwd2_blk(g), tabb = bwd2_tab_bytes(g);
+    const size_t tab_total = (size_t)nH * tabb;
     uint8_t* scratch = scratch_for(st, tab_total + (size_t)nH * 8 + 16);
     if (!scratch) return VSW_ERR_CUDA;
     uint16_t* tabg = (uint16_t*)scratch;
@@ -546,9 +657,9 @@ int tc2_attn_bwd(const void* qkv, const void* out, const void* dout, const float
     int* poison = (int*)(scratch + tab_total + (size_t)nH * 8);
     cudaMemsetAsync(poison, 0, 4, st);
     if (dtype == VSW_BF16)
-        attn2_table_kernel<__nv_bfloat16><<<nH, 256, 0, st>>>((const __nv_bfloat16*)table, rowcode, colcode, N, nH, L, g.wdc, g.wh, g.ww, 1, tabg, tabstat, poison);
+        attn2_table_kernel<__nv_bfloat16><<<nH, 256, 0, st>>>((const __nv_bfloat16*)table, rowcode, colcode, N, nH, L, g.wdc, g.wh, g.ww, 1, blk, tabg, tabstat, poison);
     else
-        attn2_table_kernel<__half><<<nH, 256, 0, st>>>((const __half*)table, rowcode, colcode, N, nH, L, g.wdc, g.wh, g.ww, 1, tabg, tabstat, poison);
+        attn2_table_kernel<__half><<<nH, 256, 0, st>>>((const __half*)table, rowcode, colcode, N, nH, L, g.wdc, g.wh, g.ww, 1, blk, tabg, tabstat, poison);
     int rc = check_launch("attn2_table");
     if (rc) return rc;
     BwdParams2 p{};
@@ -556,14 +667,15 @@ int tc2_attn_bwd(const void* qkv, const void* out, const void* dout, const float
     p.out = out; p.dout = dout; p.lse = lse; p.dqkv = dqkv; p.dbias_part = (float*)ws;
     p.B_ = B_; p.nW = nW; p.N = N; p.nH = nH; p.wh = g.wh; p.ww = g.ww; p.KR = g.KR;
     p.nT = (g.KR + KTR - 1) / KTR; p.nhb = (g.KR + QHR - 1) / QHR;
-    p.tab_bytes = g.tab_bytes; p.NHt = 2 * g.wh - 1; p.wdc = g.wdc; p.L = L; p.groups = groups;
+    p.tab_bytes = tabb; p.blk = blk; p.NHt = 2 * g.wh - 1; p.wdc = g.wdc; p.L = L; p.groups = groups;
     p.scale = scale; p.scale_log2 = scale * LOG2E;
+    p.dbg = attn2_debug_buffer("bwd");
     cudaError_t e = cudaSuccess;
 #define VSW_LAUNCH_BWD2(WWV, F16V)                                                                                        \
     do {                                                                                                                  \
         auto kern = attn2_bwd_kernel<WWV, F16V>;                                                                          \
         e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, BWD_SMEM);                            \
-        if (e == cudaSuccess) kern<<<groups * nH, B_THREADS, BWD_SMEM, st>>>(tmQ, tmKV, tmDO, p);                         \
+        if (e == cudaSuccess) kern<<<groups * nH, B_THREADS, BWD_SMEM, st>>>(tmQ, tmKV, tmDO, tmDKV, p);                         \
     } while (0)
     if (dtype == VSW_BF16) { if (g.ww == 7) VSW_LAUNCH_BWD2(7, false); else VSW_LAUNCH_BWD2(8, false); }
     else { if (g.ww == 7) VSW_LAUNCH_BWD2(7, true); else VSW_LAUNCH_BWD2(8, true); }

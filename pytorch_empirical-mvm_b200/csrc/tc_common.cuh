@@ -67,6 +67,7 @@ __device__ __forceinline__ bool mbar_test(uint64_t* bar, uint32_t parity) {
 }
 // pure polling wait (mbarrier.test_wait never suspends the thread)
 __device__ __forceinline__ void mbar_wait_spin(uint64_t* bar, uint32_t parity) {
+#pragma unroll 1
     for (uint32_t it = 0; it < (1u << 26); ++it) {
         uint32_t ok;
         asm volatile(
@@ -82,6 +83,7 @@ __device__ __forceinline__ void mbar_wait_spin(uint64_t* bar, uint32_t parity) {
     __trap();
 }
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+#pragma unroll 1
     for (uint32_t it = 0; it < (1u << 24); ++it)
         if (mbar_try_wait(bar, parity)) return;
     printf("vsw: mbarrier wait timed out (block %d thread %d)\n", blockIdx.x, threadIdx.x);
@@ -90,6 +92,7 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
 
 // same, with a site tag in the time-out message (which of a kernel's many waits it was)
 __device__ __forceinline__ void mbar_wait_tag(uint64_t* bar, uint32_t parity, int tag) {
+#pragma unroll 1
     for (uint32_t it = 0; it < (1u << 24); ++it)
         if (mbar_try_wait(bar, parity)) return;
     printf("vsw: mbarrier wait timed out (block %d thread %d, wait site %d, parity %u)\n", blockIdx.x, threadIdx.x, tag, parity);
@@ -125,6 +128,18 @@ __device__ __forceinline__ void tma_load_4d(const CUtensorMap* m, uint64_t* bar,
         ::"r"(smem_u32(dst)), "l"((uint64_t)m), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
         : "memory");
 }
+
+// tile store shared -> global (bulk async-group completion); out-of-range box elements are not written
+__device__ __forceinline__ void tma_store_4d(const CUtensorMap* m, const void* src, int c0, int c1, int c2, int c3) {
+    asm volatile(
+        "cp.async.bulk.tensor.4d.global.shared::cta.bulk_group [%0, {%2, %3, %4, %5}], [%1];"
+        ::"l"((uint64_t)m), "r"(smem_u32(src)), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+        : "memory");
+}
+__device__ __forceinline__ void bulk_commit_group() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+// all of this thread's bulk groups have finished READING shared memory (the global writes may still be in flight)
+__device__ __forceinline__ void bulk_wait_read_all() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
 
 // ---------------------------------------------------------------------------------------------
 // device: TMEM + tcgen05

@@ -1,7 +1,7 @@
 #!/bin/bash
 set -u
 export VSW_ATTN_TC2=1
-for args in "8 7 7 8 7 7 0 0 0 2 1 bf16 0" "8 14 14 8 7 7 0 3 3 2 1 bf16 0" "4 12 12 4 6 6 0 3 3 4 2 bf16 0" "8 56 56 8 7 7 0 0 0 4 32 bf16 5" "8 14 14 8 7 7 0 3 3 16 32 bf16 5"; do
+for args in "8 56 56 8 7 7 0 0 0 4 32 bf16 3" "8 14 14 8 7 7 0 3 3 16 32 bf16 3" "4 12 12 4 6 6 2 3 3 4 4 bf16 1" "8 28 28 8 7 7 0 3 3 8 8 fp16 1"; do
   echo "=== $args"
-  DBG_BWD=1 timeout 120 python scripts/dbg_attn.py $args 2>&1 | grep -v "^Traceback\|^  File\|^    " | tail -6
+  VSW_ATTN_DEBUG=${DBG:-0} DBG_BWD=1 timeout 120 python scripts/dbg_attn.py $args 2>&1 | grep -v "^Traceback\|^  File" | tail -${TAILN:-12} | cut -c1-300
 done

@@ -57,6 +57,58 @@ __device__ __forceinline__ void sts_f32(uint32_t a, float v) { asm volatile("st.
 __device__ __forceinline__ float bf_lo(uint32_t w) { return __uint_as_float(w << 16); }
 __device__ __forceinline__ float bf_hi(uint32_t w) { return __uint_as_float(w & 0xFFFF0000u); }
 
+__device__ __forceinline__ float4 lds_f4(uint32_t a) {
+    float4 v;
+    asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(a));
+    return v;
+}
+__device__ __forceinline__ void sts_f4(uint32_t a, float4 v) {
+    asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(a), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+}
+__device__ __forceinline__ void tmem_st8(uint32_t taddr, const uint32_t* r) {
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};"
+                 ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]) : "memory");
+}
+// the step of the second-generation backward: FLAGS bit 0 = histogram RMW, 1 = {lse, delta} loads, 2 = dS tile stores, 3 = TMEM stores
+template <int FLAGS>
+__device__ __forceinline__ void bwd_step(const uint32_t (&rs)[16], const uint32_t (&rd)[16], uint32_t ld_a, uint32_t tab0, uint32_t tab1,
+                                         uint32_t hist0, uint32_t hist1, uint32_t tile_a, uint32_t trow, float scale_log2) {
+    float4 st[8];
+#pragma unroll
+    for (int v = 0; v < 8; ++v) st[v] = (FLAGS & 2) ? lds_f4(ld_a + v * 16) : make_float4(1.f, 0.1f, 2.f, 0.2f);
+    uint4 bias[2];
+    bias[0] = lds_u4(tab0); bias[1] = lds_u4(tab1);
+    float4 hh[4];
+    if (FLAGS & 1) { hh[0] = lds_f4(hist0); hh[1] = lds_f4(hist0 + 16); hh[2] = lds_f4(hist1); hh[3] = lds_f4(hist1 + 16); }
+    float ds[16], pp[16];
+#pragma unroll
+    for (int e = 0; e < 16; ++e) {
+        const int sl = e & 7, r = e >> 3;
+        if (sl >= 7) { pp[e] = 0.f; ds[e] = 0.f; continue; }
+        const float4 t = st[e >> 1];
+        const float l2 = (e & 1) ? t.z : t.x, dl = (e & 1) ? t.w : t.y;
+        const uint4 bb = bias[r];
+        const uint32_t w = (sl >> 1) == 0 ? bb.x : (sl >> 1) == 1 ? bb.y : (sl >> 1) == 2 ? bb.z : bb.w;
+        const float x = fmaf(__uint_as_float(rs[e]), scale_log2, (sl & 1) ? bf_hi(w) : bf_lo(w)) - l2;
+        const float pe = ex2(x);
+        pp[e] = pe;
+        ds[e] = pe * (__uint_as_float(rd[e]) - dl);
+    }
+    if (FLAGS & 1) {
+        hh[0].x += ds[0]; hh[0].y += ds[1]; hh[0].z += ds[2]; hh[0].w += ds[3];
+        hh[1].x += ds[4]; hh[1].y += ds[5]; hh[1].z += ds[6]; hh[1].w += ds[7];
+        hh[2].x += ds[8]; hh[2].y += ds[9]; hh[2].z += ds[10]; hh[2].w += ds[11];
+        hh[3].x += ds[12]; hh[3].y += ds[13]; hh[3].z += ds[14]; hh[3].w += ds[15];
+        sts_f4(hist0, hh[0]); sts_f4(hist0 + 16, hh[1]); sts_f4(hist1, hh[2]); sts_f4(hist1 + 16, hh[3]);
+    }
+    uint32_t pw[8], dw[8];
+#pragma unroll
+    for (int e = 0; e < 16; e += 2) { pw[e >> 1] = pack_bf16(pp[e], pp[e + 1]); dw[e >> 1] = pack_bf16(ds[e], ds[e + 1]); }
+    if (FLAGS & 8) { tmem_st8(trow, pw); tmem_st8(trow + 64, dw); }
+    if (FLAGS & 4) { sts_u4(tile_a, make_uint4(dw[0], dw[1], dw[2], dw[3])); sts_u4(tile_a + 16, make_uint4(dw[4], dw[5], dw[6], dw[7])); }
+    if (!(FLAGS & 12)) { if (pw[0] == 0x12345678u && dw[3] == 0x9abcdef0u) sts_u4(tile_a, make_uint4(pw[0], dw[1], 0, 0)); }
+}
+
 template <int MODE, int NT>
 __global__ void __launch_bounds__(NT, 1) k_tmem(float* out, int iters) {
     extern __shared__ __align__(1024) uint8_t smem[];
@@ -124,6 +176,16 @@ __global__ void __launch_bounds__(NT, 1) k_tmem(float* out, int iters) {
                     pw[e / 2] = pack_bf16(p0, p1);
                 }
                 tmem_st16(trow + c / 2, pw);   // (aliases the S columns like the real kernel; values stay finite)
+            } else if (MODE >= 16) {
+                // second-generation backward step: S in [c, c+16), dP in [c+16, c+32)
+                uint32_t rs[16], rd[16];
+                tmem_ld16(trow + c, rs); tmem_ld16(trow + c + 16, rd);
+                ld_wait();
+                const int rho = (c >> 5) & 31;
+                const uint32_t rowi = (uint32_t)((threadIdx.x * 7 + rho * 13) % 1360);
+                bwd_step<MODE - 16>(rs, rd, smem_u32(smem) + rho * 128, smem_u32(smem) + 8192 + rowi * 16, smem_u32(smem) + 8192 + ((rowi + 1) % 1360) * 16,
+                                    smem_u32(smem) + 32768 + (warp >> 2 & 1) * 45056 + rowi * 32, smem_u32(smem) + 32768 + (warp >> 2 & 1) * 45056 + ((rowi + 1) % 1360) * 32,
+                                    smem_u32(smem) + 131072 + (threadIdx.x & 127) * 128 + ((c >> 5) & 3) * 32, trow + (c >> 1), sc);
             } else {
                 // backward body: columns [c, c+16) are "S", [c+16, c+32) are "dP"
                 uint32_t rs[16], rd[16];
@@ -154,7 +216,8 @@ __global__ void __launch_bounds__(NT, 1) k_tmem(float* out, int iters) {
                 sts_u4(tile_a + 32768 + ((c >> 4) & 1) * 16384 + 512 * 16, make_uint4(dw[4], dw[5], dw[6], dw[7]));
             }
         }
-        if (MODE >= 3) st_wait();
+        if (MODE >= 3 && MODE < 16) st_wait();
+        if (MODE >= 16 && ((MODE - 16) & 8)) st_wait();
     }
     long long t1 = clock64();
     if (threadIdx.x == 0) out[blockIdx.x] = (float)(t1 - t0);
@@ -181,6 +244,7 @@ void run1(float* d, const char* name) {
 template <int MODE>
 void run(float* d, const char* name) {
     run1<MODE, 128>(d, name); run1<MODE, 256>(d, name); run1<MODE, 384>(d, name); run1<MODE, 512>(d, name);
+    if (MODE >= 16) return;
     run1<MODE, 640>(d, name); run1<MODE, 768>(d, name); run1<MODE, 1024>(d, name);
 }
 
@@ -192,5 +256,11 @@ int main() {
     run<4>(d, "fwd body + bf16 bias tile (LDS.128)");
     run<5>(d, "bwd body: 2 ld + bias + ex2 + dS + 4 STS.128");
     run<6>(d, "bwd body + smem histogram RMW");
+    run<16 + 15>(d, "bwd2 step: full (hist + stats + dS tile + STTM)");
+    run<16 + 14>(d, "bwd2 step: no histogram");
+    run<16 + 13>(d, "bwd2 step: no {lse, delta} loads");
+    run<16 + 11>(d, "bwd2 step: no dS tile stores");
+    run<16 + 7>(d, "bwd2 step: no TMEM stores");
+    run<16 + 0>(d, "bwd2 step: math only");
     printf("%s\n", cudaGetErrorString(cudaGetLastError()));
 }

@@ -221,7 +221,12 @@ def test_window_attention_fwd_bwd(vsw, oracle, dtype, geom, backend):
     assert rel_l2(dtab, tr.grad) < TOL[dtype] * (1 if dtype == torch.float32 else 1.5)
     dqkv_h, dtab_h = VF.attn_bwd(qkv.view(B_ * N, -1), out, dout.view(B_ * N, -1), lse, table, rowcode, colcode, plan.region,
                                  None, B_, nW, N, nH, hd, hd ** -0.5, planes=plan.ws[0], window=window)
-    assert rel_l2(dqkv_h, dqkv) < 1e-3 and rel_l2(dtab_h, tr.grad) < TOL[dtype] * (1 if dtype == torch.float32 else 1.5)
+    # (the hinted call may run a different kernel generation than the un-hinted one: both are held against the fp64 reference)
+    dqh = dqkv_h.view(B_, N, 3, nH, hd)
+    for i, nm in enumerate("qkv"):
+        assert rel_l2(dqh[:, :, i], qr.grad[:, :, i]) < TOL[dtype] * (1 if dtype == torch.float32 else 1.5), nm
+    assert rel_l2(dqkv_h, dqkv) < (1e-5 if dtype == torch.float32 else 2 * TOL[dtype])
+    assert rel_l2(dtab_h, tr.grad) < TOL[dtype] * (1 if dtype == torch.float32 else 1.5)
 
 
 @pytest.mark.parametrize("case", ["huge_logits", "huge_bias"])
