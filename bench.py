@@ -126,6 +126,7 @@ def main():
     ap.add_argument("--batch", type=int, default=32, help="clips per GPU (BASELINE config 2: 32)")
     ap.add_argument("--cpu-batch", type=int, default=2, help="clips per CPU-baseline step (BASELINE config 1: 2)")
     ap.add_argument("--backend", default="auto", choices=["auto", "simt", "tcgen05"])
+    ap.add_argument("--dtype", default="bf16", choices=["bf16", "fp16"], help="16-bit compute type (both run on tcgen05)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     args = ap.parse_args()
@@ -136,7 +137,8 @@ def main():
     world = int(os.environ.get("WORLD_SIZE", 1))
     local_rank = int(os.environ.get("LOCAL_RANK", 0))
     side = 384 if args.model == "swin_l_384" else 224
-    workload = f"Video-{args.model} fwd+bwd, {args.batch} clips/GPU x 8x{side}^2, bf16, drop_path 0.2 train mode"
+    workload = f"Video-{args.model} fwd+bwd, {args.batch} clips/GPU x 8x{side}^2, {args.dtype}, drop_path 0.2 train mode"
+    tdtype = torch.bfloat16 if args.dtype == "bf16" else torch.float16
 
     # ------------------------------------------------------------------ reference arm (host CPU)
     if args.impl == "reference":
@@ -178,7 +180,7 @@ def main():
     torch.manual_seed(0)  # identical weights on every rank
     model = vsw.SwinTransformer3D(pretrained=None, drop_path_rate=0.2, **MODELS[args.model])
     model.init_weights()
-    model = model.to(dev).bfloat16().train()
+    model = model.to(dev).to(tdtype).train()
     net = model
     dp_mode = os.environ.get("VSW_DP_MODE", "coalesced") if world > 1 else "none"
     reducer = vsw.dp.OverlappedGradReducer(model) if dp_mode == "overlap" else None
@@ -192,7 +194,7 @@ def main():
     x_dev = x_host.to(dev, non_blocking=True)
     with torch.no_grad():
         y0 = model(x_dev[:1])
-    Rm = (torch.randn(B, *y0.shape[1:], device=dev) / 1024).to(torch.bfloat16)
+    Rm = (torch.randn(B, *y0.shape[1:], device=dev) / 1024).to(tdtype)
     # inputs (154 MB fp32) + saved activations (GBs) exceed the 126 MB L2 every step: no explicit flush needed
     l2_note = "inputs+activations per step >> 126 MB L2 (no explicit flush)"
 
@@ -330,7 +332,7 @@ def main():
         out = {
             "metric": "Video-Swin-B fwd+bwd clips/sec", "value": value, "unit": "clips/s", "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True,
-            "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+            "scaling": "weak", "vs_baseline": None, "dtype": args.dtype, "data": "synthetic",
             "config": {"workload": workload, "variant": args.model, "clips_per_gpu": B, "global_batch": world * B,
                        "parallelism": f"dp{world}", "gemm_backend": args.backend, "l2": l2_note,
                        "optimizer": "excluded (metric is encoder fwd+bwd, SURVEY 8d)"},

@@ -124,6 +124,13 @@ int vsw_ln_bwd(const void* dy, const void* x, const void* gamma, const float* me
                int B, int Tin, int Tout, int C, int dtype, int dy_dtype, void* ws, size_t ws_bytes,
                void* stream);
 
+/* Residual add with window-reverse scatter, for a residual stream kept wider than the branch (torch.autocast keeps
+ * `shortcut + drop_path(x)` in fp32 while the Linear outputs are 16-bit, video_swin.py:256, 261):
+ *   out[b, map[r], :] = x[b, map[r], :] + rowscale[b] * y[b, r, :]     (rows with map[r] < 0 skipped; map NULL = identity)
+ * x / out (B, dst_rows_per_batch, C) in `dtype`, y (B, rows_per_batch, C) in `y_dtype`; C % 4 == 0. */
+int vsw_residual_add(const void* x, const void* y, const int32_t* rowmap, const float* rowscale, void* out, int B,
+                     int rows_per_batch, int dst_rows_per_batch, int C, int dtype, int y_dtype, void* stream);
+
 /* PatchMerging front half (video_swin.py:276-286): y[b,r,:] = LN_{4C}(concat_g x[b, map4[r,g], :]),
  * map4 < 0 -> zero input (padding BEFORE the norm).  y is (B, Tout, 4C). */
 int vsw_merge_ln_fwd(const void* x, const void* gamma, const void* beta, const int32_t* map4,

@@ -10,11 +10,13 @@ static bool attn_want_tc(int dtype, int hd, const void* dmask) {
     const int b = backend();
     return b == VSW_GEMM_TCGEN05 || b == VSW_GEMM_AUTO;
 }
-static bool attn_want_tc2(int dtype, int hd, const void* dmask) {
-    // VSW_ATTN_TC2 = 0 / 1 forces the first- / second-generation kernel for bf16 (fp16 only exists in the second)
-    static const int pref = getenv("VSW_ATTN_TC2") ? atoi(getenv("VSW_ATTN_TC2")) : -1;
+static bool attn_want_tc2(int dtype, int hd, const void* dmask, bool bwd) {
+    // which generation of the tcgen05 kernel bf16 takes: VSW_ATTN_TC2 is a bit mask read once per process (bit 0: forward,
+    // bit 1: backward use the second generation; default 2 -- the first-generation forward is still ~10% faster on
+    // the 392-token window).  fp16 only exists in the second generation.
+    static const int pref = getenv("VSW_ATTN_TC2") ? atoi(getenv("VSW_ATTN_TC2")) : 2;
     if ((dtype != VSW_BF16 && dtype != VSW_F16) || hd != 32 || dmask) return false;
-    if (dtype == VSW_BF16 && pref != 1) return false;   // bf16 default: first generation (faster on masked windows for now)
+    if (dtype == VSW_BF16 && !(pref & (bwd ? 2 : 1))) return false;
     const int b = backend();
     return b == VSW_GEMM_TCGEN05 || b == VSW_GEMM_AUTO;
 }
@@ -33,7 +35,7 @@ extern "C" int vsw_window_attn_fwd(const void* qkv, const void* bias_table, cons
     VSW_ATTN_CHECK("vsw_window_attn_fwd");
     VSW_REQUIRE(out && lse, VSW_ERR_ARG, "vsw_window_attn_fwd: out/lse NULL");
     cudaStream_t st = (cudaStream_t)stream;
-    if (attn_want_tc2(dtype, hd, dense_mask)) {
+    if (attn_want_tc2(dtype, hd, dense_mask, false)) {
         int rc = tc2_attn_fwd(qkv, bias_table, rowcode, colcode, region, out, lse, B_, nW, N, nH, hd, L, scale, window_dims, dtype, st);
         if (rc != VSW_ERR_UNSUPPORTED) return rc;
     }
@@ -62,7 +64,7 @@ extern "C" int vsw_window_attn_bwd(const void* qkv, const void* out, const void*
     VSW_REQUIRE(ws_bytes >= vsw_window_attn_bwd_workspace(B_, N, nH, hd, L), VSW_ERR_WORKSPACE,
                 "vsw_window_attn_bwd: workspace too small");
     cudaStream_t st = (cudaStream_t)stream;
-    if (attn_want_tc2(dtype, hd, dense_mask)) {
+    if (attn_want_tc2(dtype, hd, dense_mask, true)) {
         int rc = tc2_attn_bwd(qkv, out, dout, lse, bias_table, rowcode, colcode, region, dqkv, dbias_table, B_, nW, N, nH, hd, L, scale,
                               window_dims, dtype, ws, ws_bytes, st);
         if (rc != VSW_ERR_UNSUPPORTED) return rc;

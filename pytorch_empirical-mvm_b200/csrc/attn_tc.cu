@@ -20,6 +20,16 @@
 #include "attn.cuh"
 #include "tc_common.cuh"
 
+// phase counters (VSW_ATTN_DEBUG=1 VSW_ATTN_DEBUG_DUMP=1) exist only in builds with -DVSW_ATTN_PROF=1 (VSW_NVCC_EXTRA of build.py)
+#ifndef VSW_ATTN_PROF
+#define VSW_ATTN_PROF 0
+#endif
+#if VSW_ATTN_PROF
+#define ACLK() clock64()
+#else
+#define ACLK() 0LL
+#endif
+
 namespace vsw {
 namespace {
 
@@ -375,9 +385,9 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const FwdParams p)
         for (int w = w_begin; w < w_end; ++w, ++it) {
             const int st = it & 1; const uint32_t ph = (it >> 1) & 1;
             const int h = w / p.B_, b_ = w - h * p.B_, win = b_ % p.nW;
-            long long ax_a = clock64();
+            long long ax_a = ACLK();
             tc::mbar_wait(&s.aux_empty[st], ph ^ 1);
-            long long ax_b = clock64();
+            long long ax_b = ACLK();
             if (warp == 2) {
                 if (tab_head[st] != h) {
                     tab_head[st] = h;
@@ -417,7 +427,7 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const FwdParams p)
             }
             __syncwarp();
             if (lane == 0) tc::mbar_arrive(&s.aux_full[st]);
-            if (p.dbg && blockIdx.x == 0 && threadIdx.x == 64) { p.dbg[6] += ax_b - ax_a; p.dbg[7] += clock64() - ax_b; }
+            if (VSW_ATTN_PROF && p.dbg && blockIdx.x == 0 && threadIdx.x == 64) { p.dbg[6] += ax_b - ax_a; p.dbg[7] += ACLK() - ax_b; }
         }
     } else if (warp >= 4) {
         // ===================== softmax + epilogue warps =====================
@@ -442,10 +452,10 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const FwdParams p)
         //      start before every warp has passed this point (it needs their p_full[0] arrival).
         auto epilogue = [&](int eb, int eh, int te, float mxe) {   // (window, head) of the tile's item, tile, row max
             const int ie = te * QT + row;
-            long long t_d = clock64();
+            long long t_d = ACLK();
             tc::mbar_wait(s.o_full, oph); oph ^= 1;
             tc::tc_fence_after();
-            long long t_e = clock64();
+            long long t_e = ACLK();
             uint32_t o[16], lr[16];
             tc::tmem_ld_32x16(tmem + lane_base + O_COL + (part & 1) * 16, o);
             tc::tmem_ld_32x16(tmem + lane_base + L_COL, lr);   // 16 identical columns of the row sum
@@ -468,8 +478,8 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const FwdParams p)
                 if (part == 0) p.lse[((long long)eb * p.nH + eh) * p.N + ie] = (mxe + __log2f(l)) * LN2;
             }
             tc::tc_fence_before();  // O reads complete before the next p_full arrive lets P.V overwrite O
-            if (p.dbg && blockIdx.x == 0 && threadIdx.x == 128) {
-                long long t_f = clock64();
+            if (VSW_ATTN_PROF && p.dbg && blockIdx.x == 0 && threadIdx.x == 128) {
+                long long t_f = ACLK();
                 p.dbg[3] += t_e - t_d; p.dbg[4] += t_f - t_e;
             }
         };
@@ -502,11 +512,11 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const FwdParams p)
                 // logits or bias values) fall back to the exact two-pass row max.
                 const float bound = sqrtf(s.q2[st][ic] * k2max) * p.scale_log2;
                 const bool fast = __all_sync(0xffffffffu, bound <= 50.0f) && bias_ok;
-                long long t_a = clock64();
+                long long t_a = ACLK();
                 tc::mbar_wait(&s.s_full[0], sph);
                 if (!fast) tc::mbar_wait(&s.s_full[1], sph);
                 tc::tc_fence_after();
-                long long t_b = clock64();
+                long long t_b = ACLK();
                 float mx;
                 if (fast) {
                     mx = 0.f;   // no subtraction at all: every exponent is within +-100, far inside the fp32 / bf16 range
@@ -541,7 +551,7 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const FwdParams p)
                     tc::named_bar_sync(1 + q, 32 * NPARTS);   // xmax may be rewritten by the next tile
                     if (!(mx > -INFINITY)) mx = 0.f;          // rows beyond the window
                 }
-                long long t_c = clock64();
+                long long t_c = ACLK();
                 // ---- pass 2: p = exp2(s - max) -> packed bf16 into TMEM (aliasing S), row sum in fp32, half by half;
                 //      after each half the MMA warp runs that half of P.V and then the half's S for the next tile
                 const uint32_t tabrow = tc::smem_u32(tab + rci);
@@ -592,8 +602,8 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const FwdParams p)
                 }
                 sph ^= 1;
                 mx_prev = mx;
-                if (p.dbg && blockIdx.x == 0 && threadIdx.x == 128) {
-                    long long t_d = clock64();
+                if (VSW_ATTN_PROF && p.dbg && blockIdx.x == 0 && threadIdx.x == 128) {
+                    long long t_d = ACLK();
                     p.dbg[0] += t_b - t_a; p.dbg[1] += t_c - t_b; p.dbg[2] += t_d - t_c; p.dbg[5] += 1;
                 }
             }
@@ -655,11 +665,12 @@ int tc_attn_fwd(const void* qkv, const void* table, const int32_t* rowcode, cons
             cudaMemset(dbg, 0, 64);
         }
     }
-    static bool configured = false;
-    if (!configured) {
+    static bool configured[kMaxDevices] = {};   // per device; benign race (the attribute is idempotent)
+    const int dev = current_device();
+    if (!configured[dev]) {
         cudaError_t e = cudaFuncSetAttribute(attn_fwd_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
         if (e != cudaSuccess) { set_error("attn fwd: cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return VSW_ERR_CUDA; }
-        configured = true;
+        configured[dev] = true;
     }
     const int items = B_ * nH;
     const int grid = items < kNumSMs ? items : kNumSMs;

@@ -48,6 +48,7 @@ constexpr int W_AUX0 = 4 * NGRP, W_AUX1 = W_AUX0 + 1, W_TMA = W_AUX0 + 2, W_MMA 
 constexpr int O_COL = NSB * BW, TMEM_COLS = 512;   // O: two 32-column buffers behind the four S buffers (448 + 64 = all 512 columns)
 constexpr float LOG2E = 1.4426950408889634f, LN2 = 0.6931471805599453f;
 constexpr float MASKV = -100.0f * LOG2E;   // the reference's additive -100 (video_swin.py:304-306), in log2 units
+constexpr float MASKC = 100.0f * LOG2E / 1.7014118346046923e38f;   // times -2^127 (0xFF000000) = MASKV
 constexpr float SAFE = 50.0f;              // |exponent| bound (log2 units) under which no max is subtracted
 
 // ---- shared-memory carve-up (offsets from a 1024-byte aligned base) ------------------------------------------------------
@@ -121,6 +122,18 @@ __device__ __forceinline__ uint32_t word_of(const uint4& b, int k) { return k ==
 // ---- one 16-column chunk (two key rows) of a block: scores -> exponents -----------------------------------------------
 // r: 16 fp32 scores of this thread's query row; b0 / b1: bias vectors (8 x bf16, x log2e) of the two key rows; nq4: per-byte
 // "region differs" flags of the 16 columns (MASKED only); rows: 1 if only the first key row exists.
+// per byte: MSB set <=> the bytes of a and b differ (any byte values; four integer instructions, no per-byte compare)
+__device__ __forceinline__ uint32_t ne_msb4(uint32_t a, uint32_t b) {
+    const uint32_t d = a ^ b;
+    return d | ((d & 0x7F7F7F7Fu) + 0x7F7F7F7Fu);
+}
+// 0xFF000000 (= -2^127 as a float) if the MSB of byte k of w is set, else 0: one PRMT in sign-replicate mode (selector nibble
+// bit 3; __byte_perm masks that bit off, hence the inline PTX)
+__device__ __forceinline__ uint32_t msb_to_top(uint32_t w, int k) {
+    uint32_t r;
+    asm("prmt.b32 %0, %1, %2, %3;" : "=r"(r) : "r"(w), "r"(0u), "r"(0x8444u | ((uint32_t)k << 12)));
+    return r;
+}
 template <int WW, bool MASKED, bool EXACT>
 __device__ __forceinline__ void chunk_exponents(const uint32_t (&r)[16], const uint4& b0, const uint4& b1, const uint32_t (&nq4)[4],
                                                 float scale_log2, float nm, float (&v)[16]) {
@@ -131,7 +144,8 @@ __device__ __forceinline__ void chunk_exponents(const uint32_t (&r)[16], const u
         const uint32_t w = word_of(e < 8 ? b0 : b1, slot >> 1);
         float x = fmaf(__uint_as_float(r[e]), scale_log2, (slot & 1) ? bf_hi(w) : bf_lo(w));
         if (EXACT) x += nm;
-        if (MASKED) x = (nq4[e >> 2] & (0xFFu << (8 * (e & 3)))) ? x + MASKV : x;
+        // byte MSB = region ids differ; replicated into the top byte it is -2^127 or +0.0 (one PRMT), times MASKC = the additive -100
+        if (MASKED) x = fmaf(__uint_as_float(msb_to_top(nq4[e >> 2], e & 3)), MASKC, x);
         v[e] = x;
     }
 }
@@ -158,8 +172,8 @@ __device__ __forceinline__ float block_exp(const BlockArgs& a) {
         uint32_t nq4[4] = {0, 0, 0, 0};
         if (MASKED) {
             const uint4 rg = tc::lds_u4(a.regk_a + k * 16);
-            nq4[0] = __vcmpne4(rg.x, a.regi4); nq4[1] = __vcmpne4(rg.y, a.regi4);
-            nq4[2] = __vcmpne4(rg.z, a.regi4); nq4[3] = __vcmpne4(rg.w, a.regi4);
+            nq4[0] = ne_msb4(rg.x, a.regi4); nq4[1] = ne_msb4(rg.y, a.regi4);
+            nq4[2] = ne_msb4(rg.z, a.regi4); nq4[3] = ne_msb4(rg.w, a.regi4);
         }
         float v[16];
         chunk_exponents<WW, MASKED, EXACT>(r, b0, b1, nq4, a.scale_log2, a.nm, v);
@@ -210,8 +224,8 @@ __device__ __forceinline__ float block_max(const BlockArgs& a) {
         uint32_t nq4[4] = {0, 0, 0, 0};
         if (MASKED) {
             const uint4 rg = tc::lds_u4(a.regk_a + k * 16);
-            nq4[0] = __vcmpne4(rg.x, a.regi4); nq4[1] = __vcmpne4(rg.y, a.regi4);
-            nq4[2] = __vcmpne4(rg.z, a.regi4); nq4[3] = __vcmpne4(rg.w, a.regi4);
+            nq4[0] = ne_msb4(rg.x, a.regi4); nq4[1] = ne_msb4(rg.y, a.regi4);
+            nq4[2] = ne_msb4(rg.z, a.regi4); nq4[3] = ne_msb4(rg.w, a.regi4);
         }
         tc::tmem_ld_wait();
         float v[16];
@@ -778,9 +792,9 @@ int tc2_attn_fwd(const void* qkv, const void* table, const int32_t* rowcode, con
     int* poison = (int*)(scratch + tab_total + (size_t)nH * 8);
     cudaMemsetAsync(poison, 0, 4, st);
     if (dtype == VSW_BF16)
-        attn2_table_kernel<__nv_bfloat16><<<nH, 256, 0, st>>>((const __nv_bfloat16*)table, rowcode, colcode, N, nH, L, g.wdc, g.wh, g.ww, 0, (2 * g.wdc - 1) * (2 * g.wh - 1), tabg, tabstat, poison);
+        attn2_table_kernel<__nv_bfloat16><<<nH, 1024, 0, st>>>((const __nv_bfloat16*)table, rowcode, colcode, N, nH, L, g.wdc, g.wh, g.ww, 0, (2 * g.wdc - 1) * (2 * g.wh - 1), tabg, tabstat, poison);
     else
-        attn2_table_kernel<__half><<<nH, 256, 0, st>>>((const __half*)table, rowcode, colcode, N, nH, L, g.wdc, g.wh, g.ww, 0, (2 * g.wdc - 1) * (2 * g.wh - 1), tabg, tabstat, poison);
+        attn2_table_kernel<__half><<<nH, 1024, 0, st>>>((const __half*)table, rowcode, colcode, N, nH, L, g.wdc, g.wh, g.ww, 0, (2 * g.wdc - 1) * (2 * g.wh - 1), tabg, tabstat, poison);
     int rc = check_launch("attn2_table");
     if (rc) return rc;
     FwdParams p{};

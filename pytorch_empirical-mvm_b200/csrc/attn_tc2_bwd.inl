@@ -109,8 +109,9 @@ __device__ __forceinline__ void bwd_step(const uint32_t (&rs)[16], const uint32_
             const float l2 = (e & 1) ? t.z : t.x, dl = (e & 1) ? t.w : t.y;
             const uint32_t w = word_of(bias[r], sl >> 1);
             float x = fmaf(__uint_as_float(rs[e]), scale_log2, (sl & 1) ? bf_hi(w) : bf_lo(w)) - l2;
-            // region mismatch byte 0xFF -> 0xFF000000 = -1.7e38 (one PRMT), added to the exponent; 0x00 -> +0.0
-        if (MASKED) x += __uint_as_float(__byte_perm(nq[e >> 2], 0u, 0x0444u | ((uint32_t)(e & 3) << 12)));
+            // region mismatch: the byte's MSB replicated into the top byte (one PRMT) is -2^127 or +0.0; times 100 log2(e) / 2^127
+        // that is the reference's additive -100 (video_swin.py:304-306) in log2 units
+        if (MASKED) x = fmaf(__uint_as_float(msb_to_top(nq[e >> 2], e & 3)), MASKC, x);
             const float pe = (r ? ok1 : ok0) ? tc::ex2_approx(x) : 0.f;
             pp[e] = pe;
             ds[e] = pe * (__uint_as_float(rd[e]) - dl);
@@ -434,6 +435,12 @@ attn2_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
             kv_pending = par;
             if (xprof) { x_epi += clock64() - x_e0; x_nepi += 1; }
         };
+        // (the integer divisions are ~1000 cycles of dependent instructions: once per kernel for the first four key tiles)
+        auto rowbase_of = [&](int T) {
+            const int dj = (T * KTR + rl) / p.wh, hj = (T * KTR + rl) % p.wh;
+            return wj * p.blk + (p.wdc - 1 - dj) * p.NHt - hj + p.wh - 1;
+        };
+        const int rb0 = rowbase_of(0), rb1 = rowbase_of(1), rb2 = rowbase_of(2), rb3 = rowbase_of(3);
         for (int it = 0; it < n_items; ++it) {
             const int ast = it & 1;
             const int b_ = gi + it * p.groups;
@@ -445,10 +452,9 @@ attn2_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
             const uint32_t regq_a = base_a + BO_REGQ + ast * MAXCOLS;
             const uint8_t* regk = base + BO_REGK + ast * 512;
             for (int T = 0; T < p.nT; ++T, ++kt) {
-                const int dj = (T * KTR + rl) / p.wh, hj = (T * KTR + rl) % p.wh;
                 const bool key_real = lane_real && T * KTR + rl < p.KR;
                 // table / histogram row of (this key, query row rho) = rowbase + koff[rho]
-                const int rowbase = wj * p.blk + (p.wdc - 1 - dj) * p.NHt - hj + p.wh - 1;
+                const int rowbase = T == 0 ? rb0 : T == 1 ? rb1 : T == 2 ? rb2 : T == 3 ? rb3 : rowbase_of(T);
                 const uint32_t regj4 = masked ? (uint32_t)regk[T * 128 + krow] * 0x01010101u : 0u;
                 for (int hb = 0; hb < p.nhb; ++hb, ++c) {
                     const int ds_use = (hb & 1) ? use_ds1++ : use_ds0++;
@@ -489,8 +495,8 @@ attn2_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
                             uint32_t nq[4] = {0, 0, 0, 0};
                             if (MK) {
                                 const uint4 rg = tc::lds_u4(regq_a + hb * 64 + k * 16);
-                                nq[0] = __vcmpne4(rg.x, regj4); nq[1] = __vcmpne4(rg.y, regj4);
-                                nq[2] = __vcmpne4(rg.z, regj4); nq[3] = __vcmpne4(rg.w, regj4);
+                                nq[0] = ne_msb4(rg.x, regj4); nq[1] = ne_msb4(rg.y, regj4);   // byte MSB set <=> the region ids differ
+                                nq[2] = ne_msb4(rg.z, regj4); nq[3] = ne_msb4(rg.w, regj4);
                             }
                             {
                                 const int rho = hb * QHR + 2 * k;
@@ -657,9 +663,9 @@ int tc2_attn_bwd(const void* qkv, const void* out, const void* dout, const float
     int* poison = (int*)(scratch + tab_total + (size_t)nH * 8);
     cudaMemsetAsync(poison, 0, 4, st);
     if (dtype == VSW_BF16)
-        attn2_table_kernel<__nv_bfloat16><<<nH, 256, 0, st>>>((const __nv_bfloat16*)table, rowcode, colcode, N, nH, L, g.wdc, g.wh, g.ww, 1, blk, tabg, tabstat, poison);
+        attn2_table_kernel<__nv_bfloat16><<<nH, 1024, 0, st>>>((const __nv_bfloat16*)table, rowcode, colcode, N, nH, L, g.wdc, g.wh, g.ww, 1, blk, tabg, tabstat, poison);
     else
-        attn2_table_kernel<__half><<<nH, 256, 0, st>>>((const __half*)table, rowcode, colcode, N, nH, L, g.wdc, g.wh, g.ww, 1, blk, tabg, tabstat, poison);
+        attn2_table_kernel<__half><<<nH, 1024, 0, st>>>((const __half*)table, rowcode, colcode, N, nH, L, g.wdc, g.wh, g.ww, 1, blk, tabg, tabstat, poison);
     int rc = check_launch("attn2_table");
     if (rc) return rc;
     BwdParams2 p{};

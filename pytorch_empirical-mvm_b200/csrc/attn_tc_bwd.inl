@@ -467,10 +467,10 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_const
                     const int ic = valid ? i : p.N - 1;
                     const int rci = s.rc[ic];
                     const uint8_t regi = masked ? s.regq[st][ic] : 0;
-                    long long t_a = clock64();
+                    long long t_a = ACLK();
                     tc::mbar_wait(s.s_full, sph); sph ^= 1;
                     tc::tc_fence_after();
-                    long long t_b = clock64();
+                    long long t_b = ACLK();
                     if (!warp_valid) {
                         // rows beyond the window: contribute zeros to the reductions over queries
                         for (int u = 0; u < 8; ++u) {
@@ -533,16 +533,16 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_const
                     tc::tc_fence_before();
                     __syncwarp();
                     if (lane == 0) tc::mbar_arrive(s.pds_full);
-                    if (p.dbg && blockIdx.x == 0 && threadIdx.x == 128) {
-                        long long t_c = clock64();
+                    if (VSW_ATTN_PROF && p.dbg && blockIdx.x == 0 && threadIdx.x == 128) {
+                        long long t_c = ACLK();
                         p.dbg[0] += t_b - t_a; p.dbg[1] += t_c - t_b; p.dbg[2] += 1;
                     }
                 }
                 // ---- dK (half 0) / dV (half 1) of this key block
-                long long t_d = clock64();
+                long long t_d = ACLK();
                 tc::mbar_wait(s.dkv_full, dkvph); dkvph ^= 1;
                 tc::tc_fence_after();
-                if (p.dbg && blockIdx.x == 0 && threadIdx.x == 128) { p.dbg[3] += clock64() - t_d; p.dbg[4] += 1; }
+                if (VSW_ATTN_PROF && p.dbg && blockIdx.x == 0 && threadIdx.x == 128) { p.dbg[3] += ACLK() - t_d; p.dbg[4] += 1; }
                 {
                     // TMEM lane `row` of the block = column c' -> key (plane c' % wd, spatial kb*boxhw + c' / wd)
                     const int key = row < nv ? (row % p.wd) * p.hw + kb * p.boxhw + row / p.wd : p.N;
@@ -706,11 +706,12 @@ int tc_attn_bwd(const void* qkv, const void* out, const void* dout, const float*
             cudaMemset(dbg, 0, 64);
         }
     }
-    static bool configured = false;
-    if (!configured) {
+    static bool configured[kMaxDevices] = {};   // per device; benign race (the attribute is idempotent)
+    const int dev = current_device();
+    if (!configured[dev]) {
         cudaError_t e = cudaFuncSetAttribute(attn_bwd_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
         if (e != cudaSuccess) { set_error("attn bwd: cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return VSW_ERR_CUDA; }
-        configured = true;
+        configured[dev] = true;
     }
     attn_bwd_tc_kernel<<<groups * nH, NTHREADS, smem, st>>>(tmQKV, tmKV, tmDO, p);
     int rc = check_launch("attn_bwd_tc");

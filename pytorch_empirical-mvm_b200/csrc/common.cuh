@@ -24,6 +24,8 @@ int check_launch(const char* what);   // cudaGetLastError -> VSW_ERR_CUDA
     } while (0)
 
 constexpr int kNumSMs = 148;  // B200
+constexpr int kMaxDevices = 64;   // per-device caches (function attributes, occupancy) are indexed by the current device
+inline int current_device() { int d = 0; cudaGetDevice(&d); return (d >= 0 && d < kMaxDevices) ? d : 0; }
 
 // ---------------------------------------------------------------------------------------------
 // storage types: float, __nv_bfloat16, __half; all arithmetic is fp32

@@ -100,6 +100,16 @@ bool make_tmap_nd_bf16(CUtensorMap* out, const void* base, int rank, const uint6
 // ---------------------------------------------------------------------------------------------
 namespace {
 
+// phase counters (printed under VSW_GEMM_DEBUG=1) exist only in builds with -DVSW_GEMM_PROF=1 (VSW_NVCC_EXTRA of build.py)
+#ifndef VSW_GEMM_PROF
+#define VSW_GEMM_PROF 0
+#endif
+#if VSW_GEMM_PROF
+#define GCLK() clock64()
+#else
+#define GCLK() 0LL
+#endif
+
 constexpr int BM = 128, BK = 64;
 constexpr int A_BYTES = BM * BK * 2;  // 16 KB
 constexpr int NUM_EPI_WARPS = 16;   // 4 per TMEM lane quadrant: the fused epilogues are latency/MUFU bound, not issue bound
@@ -154,19 +164,27 @@ __device__ __forceinline__ void gelu_both_fast(float x, float& y, float& g) {
     g = fmaf(w, du, phi);
 }
 
-__device__ __forceinline__ void ld8(const __nv_bfloat16* p, float (&o)[8]) {
-    const uint4 u = __ldg(reinterpret_cast<const uint4*>(p));
-    float2 a = tc::unpack_bf16(u.x), b = tc::unpack_bf16(u.y), c = tc::unpack_bf16(u.z), d = tc::unpack_bf16(u.w);
+// The kernels move 16-bit elements; F16 selects IEEE half instead of bfloat16 for the conversions and the MMA operand format
+// (pointers stay typed __nv_bfloat16* = "a 16-bit element").
+template <bool F16> __device__ __forceinline__ uint32_t pack2(float lo, float hi) {
+    if constexpr (F16) { const __half2 v = __floats2half2_rn(lo, hi); return *reinterpret_cast<const uint32_t*>(&v); }
+    else return tc::pack_bf16(lo, hi);
+}
+template <bool F16> __device__ __forceinline__ float2 unpack2(uint32_t u) {
+    if constexpr (F16) return __half22float2(*reinterpret_cast<const __half2*>(&u));
+    else return tc::unpack_bf16(u);
+}
+template <bool F16> __device__ __forceinline__ void unpack8(const uint4& u, float (&o)[8]) {
+    float2 a = unpack2<F16>(u.x), b = unpack2<F16>(u.y), c = unpack2<F16>(u.z), d = unpack2<F16>(u.w);
     o[0] = a.x; o[1] = a.y; o[2] = b.x; o[3] = b.y; o[4] = c.x; o[5] = c.y; o[6] = d.x; o[7] = d.y;
 }
-__device__ __forceinline__ void unpack8(const uint4& u, float (&o)[8]) {
-    float2 a = tc::unpack_bf16(u.x), b = tc::unpack_bf16(u.y), c = tc::unpack_bf16(u.z), d = tc::unpack_bf16(u.w);
-    o[0] = a.x; o[1] = a.y; o[2] = b.x; o[3] = b.y; o[4] = c.x; o[5] = c.y; o[6] = d.x; o[7] = d.y;
+template <bool F16> __device__ __forceinline__ void ld8(const __nv_bfloat16* p, float (&o)[8]) {
+    unpack8<F16>(__ldg(reinterpret_cast<const uint4*>(p)), o);
 }
-__device__ __forceinline__ void st8(__nv_bfloat16* p, const float (&v)[8]) {
+template <bool F16> __device__ __forceinline__ void st8(__nv_bfloat16* p, const float (&v)[8]) {
     uint4 u;
-    u.x = tc::pack_bf16(v[0], v[1]); u.y = tc::pack_bf16(v[2], v[3]);
-    u.z = tc::pack_bf16(v[4], v[5]); u.w = tc::pack_bf16(v[6], v[7]);
+    u.x = pack2<F16>(v[0], v[1]); u.y = pack2<F16>(v[2], v[3]);
+    u.z = pack2<F16>(v[4], v[5]); u.w = pack2<F16>(v[6], v[7]);
     *reinterpret_cast<uint4*>(p) = u;
 }
 
@@ -183,7 +201,7 @@ __device__ __forceinline__ void st8(__nv_bfloat16* p, const float (&v)[8]) {
 // bound by that port (~64 B/clk/SM), not by the tensor pipe.  Each CTA keeps its own 128 accumulator lanes, so the
 // epilogue is unchanged.  Barriers: `full` lives in the leader (both producers arrive + their bytes), `empty` / `tfull`
 // are multicast commits to both CTAs, `tempty` of the leader collects the epilogue warps of both CTAs.
-template <int BN, bool A_MN, bool B_MN, int STAGES, int EPI, bool COLSUM = false, bool PAIR = false>
+template <int BN, bool A_MN, bool B_MN, int STAGES, int EPI, bool COLSUM = false, bool PAIR = false, bool F16 = false>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const TcParams p) {
     static_assert(!COLSUM || (A_MN && EPI == TE_PARTIAL), "COLSUM is a wgrad-only variant");
@@ -194,7 +212,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     constexpr int B_BYTES = BNL * BK * 2;
     constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
     constexpr uint32_t TMEM_COLS = 2 * BN;  // power of two for BN in {64,128,256}
-    constexpr uint32_t IDESC = tc::idesc_bf16(PAIR ? 2 * BM : BM, BN, A_MN ? 1 : 0, B_MN ? 1 : 0);
+    constexpr uint32_t IDESC = tc::idesc_bf16(PAIR ? 2 * BM : BM, BN, A_MN ? 1 : 0, B_MN ? 1 : 0) & (F16 ? ~((1u << 7) | (1u << 10)) : ~0u);   // A / B format field: 1 = bf16, 0 = f16
     const uint32_t cta_rank = PAIR ? tc::cluster_ctarank() : 0u;
     const int unit = PAIR ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;
     const int n_units = PAIR ? (int)(gridDim.x >> 1) : (int)gridDim.x;
@@ -288,17 +306,17 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 const int split = w / tiles;
                 const int kbeg = split * p.k_per_split;
                 const int kend = min(p.K, kbeg + p.k_per_split);
-                long long m_a = clock64();
+                long long m_a = GCLK();
                 tc::mbar_wait(&tempty[acc], acc_phase ^ 1);
                 tc::tc_fence_after();
-                long long m_b = clock64(), m_wait_full = 0;
+                long long m_b = GCLK(), m_wait_full = 0;
                 const uint32_t d_tmem = tmem_base + acc * BN;
                 uint32_t accumulate = 0;
                 for (int k0 = kbeg; k0 < kend; k0 += BK) {
-                    long long f_a = clock64();
+                    long long f_a = GCLK();
                     tc::mbar_wait(&full[stage], phase);
                     tc::tc_fence_after();
-                    m_wait_full += clock64() - f_a;
+                    m_wait_full += GCLK() - f_a;
                     const uint32_t aaddr = tc::smem_u32(smem + stage * STAGE_BYTES);
                     const uint32_t baddr = aaddr + A_BYTES;
 #pragma unroll
@@ -317,7 +335,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 }
                 // accumulator complete -> epilogue
                 if constexpr (PAIR) tc::umma_commit_2cta(&tfull[acc]); else tc::umma_commit(&tfull[acc]);
-                if (p.dbg && blockIdx.x == 0) { p.dbg[0] += m_b - m_a; p.dbg[1] += m_wait_full; p.dbg[2] += clock64() - m_b; p.dbg[3] += 1; }
+                if (VSW_GEMM_PROF && p.dbg && blockIdx.x == 0) { p.dbg[0] += m_b - m_a; p.dbg[1] += m_wait_full; p.dbg[2] += GCLK() - m_b; p.dbg[3] += 1; }
                 if (++acc == 2) { acc = 0; acc_phase ^= 1; }
             }
         }
@@ -346,7 +364,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 #pragma unroll
                     for (int i = 0; i < 8; ++i) {
                         const uint4 v = tc::lds_u4(sA + (rcl + 8 * i) * 128);
-                        const float2 a = tc::unpack_bf16(v.x), b = tc::unpack_bf16(v.y), c = tc::unpack_bf16(v.z), d = tc::unpack_bf16(v.w);
+                        const float2 a = unpack2<F16>(v.x), b = unpack2<F16>(v.y), c = unpack2<F16>(v.z), d = unpack2<F16>(v.w);
                         cs[0] += a.x; cs[1] += a.y; cs[2] += b.x; cs[3] += b.y; cs[4] += c.x; cs[5] += c.y; cs[6] += d.x; cs[7] += d.y;
                     }
                 }
@@ -377,10 +395,10 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         for (int w = unit; w < total; w += n_units) {
             const int split = w / tiles, t = w - split * tiles;
             const int m0 = (t / p.n_tiles_n) * TILE_M + (int)cta_rank * BM, n0 = (t % p.n_tiles_n) * BN;
-            long long e_a = clock64(), dbg_ld = 0, dbg_math = 0, dbg_st = 0;
+            long long e_a = GCLK(), dbg_ld = 0, dbg_math = 0, dbg_st = 0;
             tc::mbar_wait(&tfull[acc], acc_phase);
             tc::tc_fence_after();
-            long long e_b = clock64();
+            long long e_b = GCLK();
             const int row = m0 + q * 32 + lane;
             const bool row_in = row < p.M;
             long long drow = row;
@@ -402,7 +420,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             for (int c = half; c < BN / 32; c += EPI_WARPS / 4) {
                 uint32_t r32[32];
                 __syncwarp();
-                long long c_a = clock64();
+                long long c_a = GCLK();
                 tc::tmem_ld_32x32(tmem_base + acc * BN + c * 32 + ((uint32_t)(q * 32) << 16), r32);
                 const int col0 = n0 + c * 32;
                 // Side tensor of the epilogue (residual / GELU' / pre-activation), same (row, column) footprint as the output:
@@ -432,7 +450,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                     for (int g = 0; g < 4; ++g) side[g] = tc::lds_u4(stg + lane * 64 + ((g ^ ((lane >> 1) & 3)) << 4));
                 }
                 tc::tmem_ld_wait();
-                long long c_b = clock64();
+                long long c_b = GCLK();
                 if constexpr (EPI == TE_PARTIAL) {
                     if (row_ok) {
 #pragma unroll
@@ -459,14 +477,14 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                     if (col < p.N) {
                         if (p.bias) {
                             float bb[8];
-                            ld8(p.bias + col, bb);
+                            ld8<F16>(p.bias + col, bb);
 #pragma unroll
                             for (int e = 0; e < 8; ++e) v[e] += bb[e];
                         }
                         if constexpr (EPI == TE_GELU) {
                             if (p.aux_out) {
 #pragma unroll
-                                for (int e = 0; e < 4; ++e) packed_aux[g * 4 + e] = tc::pack_bf16(v[2 * e], v[2 * e + 1]);
+                                for (int e = 0; e < 4; ++e) packed_aux[g * 4 + e] = pack2<F16>(v[2 * e], v[2 * e + 1]);
                             }
 #pragma unroll
                             for (int e = 0; e < 8; ++e) v[e] = gelu_fast(v[e]);
@@ -475,10 +493,10 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 #pragma unroll
                             for (int e = 0; e < 8; ++e) gelu_both_fast(v[e], v[e], gd[e]);
 #pragma unroll
-                            for (int e = 0; e < 4; ++e) packed_aux[g * 4 + e] = tc::pack_bf16(gd[2 * e], gd[2 * e + 1]);
+                            for (int e = 0; e < 4; ++e) packed_aux[g * 4 + e] = pack2<F16>(gd[2 * e], gd[2 * e + 1]);
                         } else if constexpr (HAS_SIDE) {
                             float u[8];
-                            unpack8(side[g], u);
+                            unpack8<F16>(side[g], u);
                             if constexpr (EPI == TE_DGRAD_MUL) {
 #pragma unroll
                                 for (int e = 0; e < 8; ++e) v[e] *= u[e];
@@ -492,9 +510,9 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                         }
                     }
 #pragma unroll
-                    for (int e = 0; e < 4; ++e) packed[g * 4 + e] = tc::pack_bf16(v[2 * e], v[2 * e + 1]);
+                    for (int e = 0; e < 4; ++e) packed[g * 4 + e] = pack2<F16>(v[2 * e], v[2 * e + 1]);
                 }
-                long long c_c = clock64();
+                long long c_c = GCLK();
                 // ---- transposed, coalesced stores (one or two outputs)
                 const int npass = ((EPI == TE_GELU && p.aux_out) || EPI == TE_GELU_GRAD) ? 2 : 1;
                 for (int pass = 0; pass < npass; ++pass) {
@@ -517,7 +535,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                         if (okr && colu < p.N) *reinterpret_cast<uint4*>(outp + dr * p.ldc + colu) = val;
                     }
                 }
-                if (p.dbg && blockIdx.x == 0 && threadIdx.x == 64) { dbg_ld += c_b - c_a; dbg_math += c_c - c_b; dbg_st += clock64() - c_c; }
+                if (VSW_GEMM_PROF && p.dbg && blockIdx.x == 0 && threadIdx.x == 64) { dbg_ld += c_b - c_a; dbg_math += c_c - c_b; dbg_st += GCLK() - c_c; }
                 }
             }
             tc::tc_fence_before();
@@ -526,7 +544,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 if constexpr (PAIR) tc::mbar_arrive_cluster(tc::mapa_u32(tc::smem_u32(&tempty[acc]), 0));   // the leader's barrier
                 else tc::mbar_arrive(&tempty[acc]);
             }
-            if (p.dbg && blockIdx.x == 0 && threadIdx.x == 64) { p.dbg[4] += e_b - e_a; p.dbg[5] += clock64() - e_b; p.dbg[6] += 1; p.dbg[8] += dbg_ld; p.dbg[9] += dbg_math; p.dbg[10] += dbg_st; }
+            if (VSW_GEMM_PROF && p.dbg && blockIdx.x == 0 && threadIdx.x == 64) { p.dbg[4] += e_b - e_a; p.dbg[5] += GCLK() - e_b; p.dbg[6] += 1; p.dbg[8] += dbg_ld; p.dbg[9] += dbg_math; p.dbg[10] += dbg_st; }
             if (++acc == 2) { acc = 0; acc_phase ^= 1; }
         }
     }
@@ -543,6 +561,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 }
 
 // rows gather + per-batch scale:  out[m,:] = scale[b] * in[b*src_rows + map[r], :]  (zero row if map < 0)
+template <bool F16>
 __global__ void __launch_bounds__(256) gather_rows_kernel(const __nv_bfloat16* __restrict__ in,
                                                           __nv_bfloat16* __restrict__ out, const int32_t* __restrict__ map,
                                                           const float* __restrict__ scale, int M, int C,
@@ -558,14 +577,14 @@ __global__ void __launch_bounds__(256) gather_rows_kernel(const __nv_bfloat16* _
 #pragma unroll
         for (int e = 0; e < 8; ++e) v[e] = 0.f;
         if (s >= 0) {
-            ld8(in + ((long long)b * src_rows_per_batch + s) * C + vcol * 8, v);
+            ld8<F16>(in + ((long long)b * src_rows_per_batch + s) * C + vcol * 8, v);
             if (scale) {
                 const float sc = __ldg(scale + b);
 #pragma unroll
                 for (int e = 0; e < 8; ++e) v[e] *= sc;
             }
         }
-        st8(out + (long long)m * C + vcol * 8, v);
+        st8<F16>(out + (long long)m * C + vcol * 8, v);
     }
 }
 
@@ -588,17 +607,18 @@ long long* gemm_dbg_buffer(int bn, bool amn, bool bmn, const TcParams& p) {
     return dbg;
 }
 
-template <int BN, bool A_MN, bool B_MN, int EPI, bool COLSUM = false, bool PAIR = false>
+template <int BN, bool A_MN, bool B_MN, int EPI, bool COLSUM = false, bool PAIR = false, bool F16 = false>
 int launch_tc_epi(const CUtensorMap& tmA, const CUtensorMap& tmB, const TcParams& p, cudaStream_t st) {
     constexpr int STAGE = A_BYTES + (PAIR ? BN / 2 : BN) * BK * 2;
     constexpr int STAGES = PAIR ? 6 : (BN <= 128 ? 5 : 4);
     constexpr size_t SMEM = (size_t)STAGES * STAGE + 1024 + 256 + NUM_EPI_WARPS * 32 * 64;
-    auto kern = tc_gemm_kernel<BN, A_MN, B_MN, STAGES, EPI, COLSUM, PAIR>;
-    static bool configured = false;  // benign race: the attribute is idempotent
-    if (!configured) {
+    auto kern = tc_gemm_kernel<BN, A_MN, B_MN, STAGES, EPI, COLSUM, PAIR, F16>;
+    const int dev = current_device();
+    static bool configured[kMaxDevices] = {};  // per device (function attributes are); benign race: the attribute is idempotent
+    if (!configured[dev]) {
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM);
         if (e != cudaSuccess) { set_error("tc gemm: cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return VSW_ERR_CUDA; }
-        configured = true;
+        configured[dev] = true;
     }
     const int total = p.n_tiles_m * p.n_tiles_n * p.splits;
     TcParams q = p;
@@ -612,14 +632,14 @@ int launch_tc_epi(const CUtensorMap& tmA, const CUtensorMap& tmB, const TcParams
         attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
         cfg.attrs = attr; cfg.numAttrs = 1;
         // a persistent grid must be fully resident: not every TPC has both SMs enabled, so ask how many pairs fit
-        static int max_pairs = 0;
-        if (!max_pairs) {
+        static int max_pairs_dev[kMaxDevices] = {};   // cached per device
+        if (!max_pairs_dev[dev]) {
             cfg.gridDim = dim3(kNumSMs);
             int n = 0;
             if (cudaOccupancyMaxActiveClusters(&n, kern, &cfg) != cudaSuccess || n < 1) n = kNumSMs / 4;
-            max_pairs = n < kNumSMs / 2 ? n : kNumSMs / 2;
-            if (getenv("VSW_GEMM_DEBUG")) fprintf(stderr, "[vsw gemm] resident CTA pairs: %d\n", max_pairs);
+            max_pairs_dev[dev] = n < kNumSMs / 2 ? n : kNumSMs / 2;
         }
+        const int max_pairs = max_pairs_dev[dev];
         const int pairs = total < max_pairs ? total : max_pairs;
         cfg.gridDim = dim3(2 * pairs);
         cudaError_t e = cudaLaunchKernelEx(&cfg, kern, tmA, tmB, q);
@@ -633,23 +653,28 @@ int launch_tc_epi(const CUtensorMap& tmA, const CUtensorMap& tmB, const TcParams
 }
 
 // PAIR = CTA-pair (cta_group::2) 256 x 256 tiles; wgrad keeps single-CTA tiles (its column-sum warps need a local barrier)
-template <int BN, bool A_MN, bool B_MN, bool PAIR = false>
-int launch_tc(const CUtensorMap& tmA, const CUtensorMap& tmB, const TcParams& p, cudaStream_t st) {
+template <int BN, bool A_MN, bool B_MN, bool PAIR, bool F16>
+int launch_tc_t(const CUtensorMap& tmA, const CUtensorMap& tmB, const TcParams& p, cudaStream_t st) {
     if constexpr (A_MN && B_MN) {
-        return p.colsum ? launch_tc_epi<BN, true, true, TE_PARTIAL, true>(tmA, tmB, p, st)
-                        : launch_tc_epi<BN, true, true, TE_PARTIAL>(tmA, tmB, p, st);
+        return p.colsum ? launch_tc_epi<BN, true, true, TE_PARTIAL, true, false, F16>(tmA, tmB, p, st)
+                        : launch_tc_epi<BN, true, true, TE_PARTIAL, false, false, F16>(tmA, tmB, p, st);
     } else if constexpr (B_MN) {
-        if (p.gelu_pre && p.epi == TE_DGRAD_MUL) return launch_tc_epi<BN, false, true, TE_DGRAD_MUL, false, PAIR>(tmA, tmB, p, st);
-        return p.gelu_pre ? launch_tc_epi<BN, false, true, TE_DGRAD_GELU, false, PAIR>(tmA, tmB, p, st)
-                          : launch_tc_epi<BN, false, true, TE_DGRAD, false, PAIR>(tmA, tmB, p, st);
+        if (p.gelu_pre && p.epi == TE_DGRAD_MUL) return launch_tc_epi<BN, false, true, TE_DGRAD_MUL, false, PAIR, F16>(tmA, tmB, p, st);
+        return p.gelu_pre ? launch_tc_epi<BN, false, true, TE_DGRAD_GELU, false, PAIR, F16>(tmA, tmB, p, st)
+                          : launch_tc_epi<BN, false, true, TE_DGRAD, false, PAIR, F16>(tmA, tmB, p, st);
     } else {
         switch (p.epi) {
-            case TE_GELU: return launch_tc_epi<BN, false, false, TE_GELU, false, PAIR>(tmA, tmB, p, st);
-            case TE_GELU_GRAD: return launch_tc_epi<BN, false, false, TE_GELU_GRAD, false, PAIR>(tmA, tmB, p, st);
-            case TE_RESIDUAL: return launch_tc_epi<BN, false, false, TE_RESIDUAL, false, PAIR>(tmA, tmB, p, st);
-            default: return launch_tc_epi<BN, false, false, TE_BIAS, false, PAIR>(tmA, tmB, p, st);
+            case TE_GELU: return launch_tc_epi<BN, false, false, TE_GELU, false, PAIR, F16>(tmA, tmB, p, st);
+            case TE_GELU_GRAD: return launch_tc_epi<BN, false, false, TE_GELU_GRAD, false, PAIR, F16>(tmA, tmB, p, st);
+            case TE_RESIDUAL: return launch_tc_epi<BN, false, false, TE_RESIDUAL, false, PAIR, F16>(tmA, tmB, p, st);
+            default: return launch_tc_epi<BN, false, false, TE_BIAS, false, PAIR, F16>(tmA, tmB, p, st);
         }
     }
+}
+// f16: IEEE half operands (the same kernels with the other operand format and conversions)
+template <int BN, bool A_MN, bool B_MN, bool PAIR = false>
+int launch_tc(const CUtensorMap& tmA, const CUtensorMap& tmB, const TcParams& p, bool f16, cudaStream_t st) {
+    return f16 ? launch_tc_t<BN, A_MN, B_MN, PAIR, true>(tmA, tmB, p, st) : launch_tc_t<BN, A_MN, B_MN, PAIR, false>(tmA, tmB, p, st);
 }
 
 bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
@@ -696,8 +721,9 @@ int tc_linear(const TcLinearArgs& a, cudaStream_t st) {
     p.bias = (const __nv_bfloat16*)a.bias; p.out = (__nv_bfloat16*)a.y; p.aux_out = (__nv_bfloat16*)a.aux_out;
     p.res = (const __nv_bfloat16*)a.res; p.rowmap = a.rowmap; p.rowscale = a.rowscale;
     p.rows_per_batch = a.rows_per_batch; p.dst_rows_per_batch = a.dst_rows_per_batch; p.ldc = a.N;
-    if (pair) return launch_tc<256, false, false, true>(tmA, tmB, p, st);
-    return BN == 256 ? launch_tc<256, false, false>(tmA, tmB, p, st) : launch_tc<128, false, false>(tmA, tmB, p, st);
+    const bool f16 = a.dtype == VSW_F16;
+    if (pair) return launch_tc<256, false, false, true>(tmA, tmB, p, f16, st);
+    return BN == 256 ? launch_tc<256, false, false>(tmA, tmB, p, f16, st) : launch_tc<128, false, false>(tmA, tmB, p, f16, st);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -710,12 +736,15 @@ int tc_dgrad(const TcDgradArgs& a, cudaStream_t st) {
         return VSW_ERR_UNSUPPORTED;
     }
     const void* A = a.dy;
+    const bool f16 = a.dtype == VSW_F16;
     if (a.a_rowmap || a.a_rowscale) {
         if (!a.a_out) { set_error("tcgen05 dgrad: gathered A needs the a_out buffer"); return VSW_ERR_UNSUPPORTED; }
         const long long total = (long long)a.M * (a.N / 8);
         int blocks = (int)((total + 255) / 256 < (long long)kNumSMs * 16 ? (total + 255) / 256 : (long long)kNumSMs * 16);
-        gather_rows_kernel<<<blocks, 256, 0, st>>>((const __nv_bfloat16*)a.dy, (__nv_bfloat16*)a.a_out, a.a_rowmap,
-                                                   a.a_rowscale, a.M, a.N, a.rows_per_batch, a.src_rows_per_batch);
+        if (f16) gather_rows_kernel<true><<<blocks, 256, 0, st>>>((const __nv_bfloat16*)a.dy, (__nv_bfloat16*)a.a_out, a.a_rowmap,
+                                                                 a.a_rowscale, a.M, a.N, a.rows_per_batch, a.src_rows_per_batch);
+        else gather_rows_kernel<false><<<blocks, 256, 0, st>>>((const __nv_bfloat16*)a.dy, (__nv_bfloat16*)a.a_out, a.a_rowmap,
+                                                              a.a_rowscale, a.M, a.N, a.rows_per_batch, a.src_rows_per_batch);
         int rc = check_launch("gather_rows");
         if (rc) return rc;
         A = a.a_out;
@@ -730,8 +759,8 @@ int tc_dgrad(const TcDgradArgs& a, cudaStream_t st) {
     p.n_tiles_m = ceil_div(a.M, pair ? 2 * BM : BM); p.n_tiles_n = ceil_div(a.K, BN); p.splits = 1; p.k_per_split = ceil_div(a.N, BK) * BK;
     p.epi = (a.gelu_pre && a.pre_is_grad) ? TE_DGRAD_MUL : TE_DGRAD;
     p.out = (__nv_bfloat16*)a.dx; p.gelu_pre = (const __nv_bfloat16*)a.gelu_pre; p.ldc = a.K;
-    if (pair) return launch_tc<256, false, true, true>(tmA, tmB, p, st);
-    return BN == 256 ? launch_tc<256, false, true>(tmA, tmB, p, st) : launch_tc<128, false, true>(tmA, tmB, p, st);
+    if (pair) return launch_tc<256, false, true, true>(tmA, tmB, p, f16, st);
+    return BN == 256 ? launch_tc<256, false, true>(tmA, tmB, p, f16, st) : launch_tc<128, false, true>(tmA, tmB, p, f16, st);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -798,7 +827,7 @@ size_t tc_wgrad_workspace(int M, int N, int K) {
 }
 
 // dw = dy^T x and (db != nullptr) db = column sums of dy, both from ONE pass over dy
-int tc_wgrad(const void* dy, const void* x, void* dw, void* db, int M, int N, int K, int grad_dtype, void* ws,
+int tc_wgrad(const void* dy, const void* x, void* dw, void* db, int M, int N, int K, int dtype, int grad_dtype, void* ws,
              size_t ws_bytes, cudaStream_t st) {
     if ((K % 8) || (N % 8) || !aligned16(dy) || !aligned16(x) || !aligned16(ws)) {
         set_error("tcgen05 wgrad: needs K %% 8 == 0, N %% 8 == 0 and 16-byte aligned pointers");
@@ -817,7 +846,8 @@ int tc_wgrad(const void* dy, const void* x, void* dw, void* db, int M, int N, in
     p.epi = TE_PARTIAL; p.partial = (float*)ws; p.ldc = K;
     float* cpart = (float*)ws + (size_t)splits * N * K;
     p.colsum = db ? cpart : nullptr;
-    int rc = BN == 256 ? launch_tc<256, true, true>(tmA, tmB, p, st) : launch_tc<128, true, true>(tmA, tmB, p, st);
+    const bool f16 = dtype == VSW_F16;
+    int rc = BN == 256 ? launch_tc<256, true, true>(tmA, tmB, p, f16, st) : launch_tc<128, true, true>(tmA, tmB, p, f16, st);
     if (rc) return rc;
     const long long elemsW = (long long)N * K, total = elemsW + (db ? N : 0);
     int blocks = (int)((total + 255) / 256);

@@ -92,3 +92,47 @@ extern "C" int vsw_merge_map(int D, int H, int W, int32_t* out, void* stream) {
     merge_map_kernel<<<ceil_div(total, 256), 256, 0, (cudaStream_t)stream>>>(D, H, W, out);
     return check_launch("vsw_merge_map");
 }
+
+// ---------------------------------------------------------------------------------------------
+// residual add with window-reverse scatter:  out[b, map[r], :] = x[b, map[r], :] + scale[b] * y[b, r, :]
+// (x / out in TX, the branch output y in TY).  Used when the residual stream is kept in a wider type than the branch
+// (torch.autocast: fp32 stream, 16-bit Linear outputs -- video_swin.py:256, 261 under autocast promote to fp32).
+// ---------------------------------------------------------------------------------------------
+namespace vsw {
+template <typename TX, typename TY>
+__global__ void __launch_bounds__(256) residual_add_kernel(const TX* __restrict__ x, const TY* __restrict__ y,
+                                                           const int32_t* __restrict__ map, const float* __restrict__ scale,
+                                                           TX* __restrict__ out, int B, int R, int T, int C) {
+    const int vpr = C / 4;
+    const long long total = (long long)B * R * vpr;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        const long long row = i / vpr;
+        const int v = (int)(i - row * vpr);
+        const int b = (int)(row / R), r = (int)(row - (long long)b * R);
+        const int t = map ? __ldg(map + r) : r;
+        if (t < 0) continue;
+        const float sc = scale ? __ldg(scale + b) : 1.f;
+        const TY* yp = y + row * C + v * 4;
+        const long long o = ((long long)b * T + t) * C + v * 4;
+#pragma unroll
+        for (int e = 0; e < 4; ++e) out[o + e] = from_f<TX>(fmaf(sc, to_f<TY>(yp[e]), to_f<TX>(x[o + e])));
+    }
+}
+}  // namespace vsw
+
+extern "C" int vsw_residual_add(const void* x, const void* y, const int32_t* rowmap, const float* rowscale, void* out, int B,
+                                int rows_per_batch, int dst_rows_per_batch, int C, int dtype, int y_dtype, void* stream) {
+    using namespace vsw;
+    VSW_REQUIRE(x && y && out && B > 0 && rows_per_batch > 0 && dst_rows_per_batch > 0 && C > 0 && C % 4 == 0, VSW_ERR_ARG,
+                "vsw_residual_add: bad args");
+    VSW_REQUIRE(rowmap || rows_per_batch == dst_rows_per_batch, VSW_ERR_ARG, "vsw_residual_add: identity map needs equal row counts");
+    const long long total = (long long)B * rows_per_batch * (C / 4);
+    long long blocks = (total + 255) / 256;
+    if (blocks > (long long)kNumSMs * 16) blocks = (long long)kNumSMs * 16;
+    cudaStream_t st = (cudaStream_t)stream;
+    VSW_DISPATCH_DTYPE(dtype, TX,
+        VSW_DISPATCH_DTYPE(y_dtype, TY,
+            (residual_add_kernel<TX, TY><<<(int)blocks, 256, 0, st>>>((const TX*)x, (const TY*)y, rowmap, rowscale, (TX*)out, B,
+                                                                     rows_per_batch, dst_rows_per_batch, C))));
+    return check_launch("residual_add");
+}

@@ -1,4 +1,4 @@
-// C-ABI entry points of the Linear family; routes to the tcgen05 (bf16) or CUDA-core kernels.
+// C-ABI entry points of the Linear family; routes to the tcgen05 (bf16 / fp16) or CUDA-core kernels.
 // Reference ops replaced: nn.Linear qkv/proj (video_swin.py:139-141,149,170), Mlp fc1/fc2 (:70-79),
 // PatchMerging.reduction (:270,287) and their autograd backward.
 #include "common.cuh"
@@ -9,7 +9,7 @@ namespace vsw {
 int backend();
 
 static bool want_tc(int dtype) {
-    if (dtype != VSW_BF16) return false;
+    if (dtype != VSW_BF16 && dtype != VSW_F16) return false;
     const int b = backend();
     return b == VSW_GEMM_TCGEN05 || b == VSW_GEMM_AUTO;
 }
@@ -35,7 +35,7 @@ extern "C" int vsw_linear_fwd(const void* x, const void* w, const void* bias, vo
         TcLinearArgs a{};
         a.x = x; a.w = w; a.bias = bias; a.y = y; a.M = M; a.N = N; a.K = K; a.epi = epilogue;
         a.aux_out = aux_out; a.res = res; a.rowmap = rowmap; a.rowscale = rowscale;
-        a.rows_per_batch = rows_per_batch; a.dst_rows_per_batch = dst_rows_per_batch; a.gelu_pre = nullptr;
+        a.rows_per_batch = rows_per_batch; a.dst_rows_per_batch = dst_rows_per_batch; a.gelu_pre = nullptr; a.dtype = dtype;
         int rc = tc_linear(a, st);
         if (rc != VSW_ERR_UNSUPPORTED || backend() == VSW_GEMM_TCGEN05) return rc;
         // AUTO: shapes the tcgen05 tiling cannot take (K % 8 != 0 etc.) run on the CUDA-core kernel
@@ -63,7 +63,7 @@ static int linear_dgrad_impl(const void* dy, const void* w, void* dx, int M, int
         TcDgradArgs a{};
         a.dy = dy; a.w = w; a.dx = dx; a.M = M; a.N = N; a.K = K; a.a_rowmap = a_rowmap; a.a_rowscale = a_rowscale;
         a.rows_per_batch = rows_per_batch; a.src_rows_per_batch = src_rows_per_batch; a.a_out = a_out;
-        a.gelu_pre = gelu_pre; a.pre_is_grad = pre_is_grad;
+        a.gelu_pre = gelu_pre; a.pre_is_grad = pre_is_grad; a.dtype = dtype;
         int rc = tc_dgrad(a, st);
         if (rc != VSW_ERR_UNSUPPORTED || backend() == VSW_GEMM_TCGEN05) return rc;
     }
@@ -124,7 +124,7 @@ extern "C" int vsw_linear_wgrad(const void* dy, const void* x, void* dw, void* d
     cudaStream_t st = (cudaStream_t)stream;
     int rc = VSW_ERR_UNSUPPORTED;
     if (want_tc(dtype)) {
-        rc = tc_wgrad(dy, x, dw, db, M, N, K, grad_dtype, ws, ws_bytes, st);   // db: fused column sums of dy
+        rc = tc_wgrad(dy, x, dw, db, M, N, K, dtype, grad_dtype, ws, ws_bytes, st);   // db: fused column sums of dy
         if (rc != VSW_OK && (rc != VSW_ERR_UNSUPPORTED || backend() == VSW_GEMM_TCGEN05)) return rc;
         if (rc == VSW_OK) return VSW_OK;
     }

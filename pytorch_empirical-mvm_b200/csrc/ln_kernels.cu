@@ -491,6 +491,11 @@ extern "C" int vsw_ln_fwd(const void* x, const void* gamma, const void* beta, co
         VSW_DISPATCH_DTYPE(dtype, T,
                            return (launch_ln_fwd<T, T, 1>(x, gamma, beta, map, y, mean, rstd, B, Tin, Tout, C, eps, st)));
     }
+    if (dtype == VSW_F32) {   // fp32 residual stream, 16-bit branch input (autocast: LN reads fp32, the Linear behind it runs in 16 bit)
+        VSW_REQUIRE(out_dtype == VSW_BF16 || out_dtype == VSW_F16, VSW_ERR_DTYPE, "vsw_ln_fwd: bad out_dtype %d", out_dtype);
+        if (out_dtype == VSW_BF16) return launch_ln_fwd<float, __nv_bfloat16, 1>(x, gamma, beta, map, y, mean, rstd, B, Tin, Tout, C, eps, st);
+        return launch_ln_fwd<float, __half, 1>(x, gamma, beta, map, y, mean, rstd, B, Tin, Tout, C, eps, st);
+    }
     VSW_REQUIRE(out_dtype == VSW_F32, VSW_ERR_DTYPE, "vsw_ln_fwd: out_dtype must equal dtype or be fp32");
     VSW_DISPATCH_DTYPE(dtype, T,
                        return (launch_ln_fwd<T, float, 1>(x, gamma, beta, map, y, mean, rstd, B, Tin, Tout, C, eps, st)));
@@ -508,6 +513,12 @@ extern "C" int vsw_ln_bwd(const void* dy, const void* x, const void* gamma, cons
         VSW_DISPATCH_DTYPE(dtype, T,
                            return (launch_ln_bwd<T, T, 1>(dy, x, gamma, mean, rstd, map, dres, dx, dgamma, dbeta, B, Tin,
                                                           Tout, C, ws, ws_bytes, st)));
+    }
+    if (dtype == VSW_F32) {   // fp32 x / dres / dx with a 16-bit dy (the autocast case of vsw_ln_fwd above)
+        VSW_REQUIRE(dy_dtype == VSW_BF16 || dy_dtype == VSW_F16, VSW_ERR_DTYPE, "vsw_ln_bwd: bad dy_dtype %d", dy_dtype);
+        if (dy_dtype == VSW_BF16)
+            return launch_ln_bwd<float, __nv_bfloat16, 1>(dy, x, gamma, mean, rstd, map, dres, dx, dgamma, dbeta, B, Tin, Tout, C, ws, ws_bytes, st);
+        return launch_ln_bwd<float, __half, 1>(dy, x, gamma, mean, rstd, map, dres, dx, dgamma, dbeta, B, Tin, Tout, C, ws, ws_bytes, st);
     }
     VSW_REQUIRE(dy_dtype == VSW_F32, VSW_ERR_DTYPE, "vsw_ln_bwd: dy_dtype must equal dtype or be fp32");
     VSW_DISPATCH_DTYPE(dtype, T,

@@ -180,6 +180,18 @@ def ln_bwd(dy, x, gamma, mean, rstd, gmap, dres, B, Tin, Tout, C, need_dx=True, 
     return dx, dg, db
 
 
+def residual_add(x, y, rowmap, rowscale, B, R, T, C):
+    """out[b, map[r]] = x[b, map[r]] + rowscale[b] * y[b, r]  with x / out in x.dtype (the wider residual stream) and the
+    branch output y in its own 16-bit dtype"""
+    out = _empty((B, T, C), x.dtype, x.device)
+    t0 = PROFILER.begin() if PROFILER is not None else None
+    L.check(L.lib().vsw_residual_add(L.ptr(x), L.ptr(y), L.ptr(rowmap), L.ptr(rowscale), L.ptr(out), B, R, T, C, L.dt(x),
+                                     L.dt(y), L.stream()), "vsw_residual_add")
+    if t0 is not None:
+        PROFILER.end("residual_add", t0, 0.0, B * C * (2 * T * _esz(x) + R * _esz(y)))
+    return out
+
+
 def linear_fwd(x2d, w, bias, M, N, K, epi=L.EPI_BIAS, out=None, aux_out=None, res=None, rowmap=None, rowscale=None,
                rows_per_batch=0, dst_rows_per_batch=0, out_rows=None):
     y = out if out is not None else _empty((out_rows if out_rows is not None else M, N), x2d.dtype, x2d.device)
@@ -286,12 +298,19 @@ class _AttnBranch(torch.autograd.Function):
         hd = C // nH
         R = nW * N
         x = _c(x)
-        xw, mean, rstd = ln_fwd(x, g1, b1, plan.gather, B, T, R, C)
+        # wide = the residual stream is kept in a wider dtype (fp32) than the branch computes in (autocast, stage 0 of the
+        # reference: LN reads fp32, `shortcut + drop_path(x)` promotes back to fp32); g1 / b1 then come in x.dtype
+        wide = x.dtype != wqkv.dtype
+        xw, mean, rstd = ln_fwd(x, g1, b1, plan.gather, B, T, R, C, out_dtype=wqkv.dtype)
         qkv = linear_fwd(xw.view(B * R, C), wqkv, bqkv, B * R, 3 * C, C)
         region = plan.region if (plan.shifted and dense_mask is None) else None
         o, lse = attn_fwd(qkv, table, rowcode, colcode, region, dense_mask, B * nW, nW, N, nH, hd, scale, window=cfg_window)
-        x1 = linear_fwd(o, wproj, bproj, B * R, C, C, epi=L.EPI_RESIDUAL, res=x, rowmap=plan.gather,
-                        rowscale=rowscale, rows_per_batch=R, dst_rows_per_batch=T, out_rows=B * T).view(B, T, C)
+        if wide:
+            y = linear_fwd(o, wproj, bproj, B * R, C, C)
+            x1 = residual_add(x, y, plan.gather, rowscale, B, R, T, C)
+        else:
+            x1 = linear_fwd(o, wproj, bproj, B * R, C, C, epi=L.EPI_RESIDUAL, res=x, rowmap=plan.gather,
+                            rowscale=rowscale, rows_per_batch=R, dst_rows_per_batch=T, out_rows=B * T).view(B, T, C)
         ctx.save_for_backward(x, g1, wqkv, table, wproj, rowscale, xw, mean, rstd, qkv, o, lse, rowcode, colcode,
                               dense_mask)
         ctx.plan, ctx.nH, ctx.scale, ctx.cfg_window = plan, nH, scale, cfg_window
@@ -308,10 +327,13 @@ class _AttnBranch(torch.autograd.Function):
         R = nW * N
         M = B * R
         dx1 = _c(dx1)
+        cd = wproj.dtype
+        dx1c = dx1 if dx1.dtype == cd else dx1.to(cd)     # wide residual stream: the branch sees the 16-bit rounding of dx1
         # proj: A = gather(dx1) * rowscale ; dO = A Wp ; dWp = A^T O ; dbp = sum A
-        a_buf = _empty((M, C), x.dtype, x.device)
-        dO = linear_dgrad(dx1, wproj, M, C, C, a_rowmap=plan.gather, a_rowscale=rowscale, rows_per_batch=R,
+        a_buf = _empty((M, C), cd, x.device)
+        dO = linear_dgrad(dx1c, wproj, M, C, C, a_rowmap=plan.gather, a_rowscale=rowscale, rows_per_batch=R,
                           src_rows_per_batch=T, a_out=a_buf)
+        del dx1c
         dwp, dbp = linear_wgrad(a_buf, o, M, C, C)
         del a_buf
         region = plan.region if (plan.shifted and dense_mask is None) else None
@@ -336,12 +358,17 @@ class _MlpBranch(torch.autograd.Function):
         Hd = w1.shape[0]
         M = B * T
         x = _c(x)
-        n2, mean, rstd = ln_fwd(x, g2, b2, None, B, T, T, C)
+        wide = x.dtype != w1.dtype       # fp32 residual stream around a 16-bit branch (see _AttnBranch)
+        n2, mean, rstd = ln_fwd(x, g2, b2, None, B, T, T, C, out_dtype=w1.dtype)
         need_grad = any(ctx.needs_input_grad)
-        u = _empty((M, Hd), x.dtype, x.device) if need_grad else None   # gelu'(fc1 pre-activation), consumed by the backward
+        u = _empty((M, Hd), w1.dtype, x.device) if need_grad else None   # gelu'(fc1 pre-activation), consumed by the backward
         g = linear_fwd(n2.view(M, C), w1, bb1, M, Hd, C, epi=L.EPI_GELU_GRAD if need_grad else L.EPI_GELU, aux_out=u)
-        out = linear_fwd(g, w2, bb2, M, C, Hd, epi=L.EPI_RESIDUAL, res=x, rowscale=rowscale, rows_per_batch=T,
-                         dst_rows_per_batch=T).view(B, T, C)
+        if wide:
+            y = linear_fwd(g, w2, bb2, M, C, Hd)
+            out = residual_add(x, y, None, rowscale, B, T, T, C)
+        else:
+            out = linear_fwd(g, w2, bb2, M, C, Hd, epi=L.EPI_RESIDUAL, res=x, rowscale=rowscale, rows_per_batch=T,
+                             dst_rows_per_batch=T).view(B, T, C)
         if need_grad:
             ctx.save_for_backward(x, g2, w1, w2, rowscale, n2, mean, rstd, u, g)
         return out
@@ -353,11 +380,13 @@ class _MlpBranch(torch.autograd.Function):
         Hd = w1.shape[0]
         M = B * T
         dout = _c(dout)
-        a_buf = _empty((M, C), x.dtype, x.device) if rowscale is not None else None
-        du = linear_dgrad(dout.view(M, C), w2, M, C, Hd, a_rowscale=rowscale, rows_per_batch=T, src_rows_per_batch=T,
+        cd = w2.dtype
+        doutc = dout if dout.dtype == cd else dout.to(cd)
+        a_buf = _empty((M, C), cd, x.device) if rowscale is not None else None
+        du = linear_dgrad(doutc.view(M, C), w2, M, C, Hd, a_rowscale=rowscale, rows_per_batch=T, src_rows_per_batch=T,
                           a_out=a_buf, mul=u)
-        dw2, db2 = linear_wgrad(a_buf if a_buf is not None else dout.view(M, C), g, M, C, Hd)
-        del a_buf
+        dw2, db2 = linear_wgrad(a_buf if a_buf is not None else doutc.view(M, C), g, M, C, Hd)
+        del a_buf, doutc
         dn2 = linear_dgrad(du, w1, M, Hd, C)
         dw1, db1 = linear_wgrad(du, n2.view(M, C), M, Hd, C)
         del du
@@ -517,7 +546,7 @@ class _PatchEmbed(torch.autograd.Function):
     """x (B,Cin,D,H,W) any float dtype -> tokens (B, Dout*Hp*Wp, E) in the compute dtype of ``w``."""
 
     @staticmethod
-    def forward(ctx, x, w, b, gamma, beta, patch: Triple):
+    def forward(ctx, x, w, b, gamma, beta, patch: Triple, out_dtype=None):
         B, Cin, D, H, W = x.shape
         pd, ph, pw = patch
         E = w.shape[0]
@@ -532,7 +561,8 @@ class _PatchEmbed(torch.autograd.Function):
         w2d = w.reshape(E, Kv)
         y = linear_fwd(col, w2d, b, B * T, E, Kv).view(B, T, E)
         if gamma is not None:
-            yn, mean, rstd = ln_fwd(y, gamma, beta, None, B, T, T, E)
+            # out_dtype fp32: the patch norm's output under autocast (LayerNorm is an fp32 op there, video_swin.py:401-405)
+            yn, mean, rstd = ln_fwd(y, gamma, beta, None, B, T, T, E, out_dtype=out_dtype)
         else:
             yn, mean, rstd = y, None, None
         ctx.save_for_backward(col, w2d, y if gamma is not None else None, gamma, mean, rstd)
@@ -563,7 +593,7 @@ class _PatchEmbed(torch.autograd.Function):
             L.check(L.lib().vsw_patch_col2im(L.ptr(dcol), L.ptr(dx), B, Cin, D, H, W, pd, ph, pw, L.dt(xdtype),
                                              L.dt(col), L.stream()), "vsw_patch_col2im")
         return (dx, dw.view(wshape), db, _grad_to(dg, gamma) if gamma is not None else None,
-                _grad_to(dbeta, gamma) if gamma is not None else None, None)
+                _grad_to(dbeta, gamma) if gamma is not None else None, None, None)
 
 
 # ----------------------------------------------------------------------------------------------
@@ -714,8 +744,8 @@ def patch_merge(x, gamma, beta, wred, grid):
     return _PatchMerge.apply(x, gamma, beta, wred, grid)
 
 
-def patch_embed(x, w, b, gamma, beta, patch):
-    return _PatchEmbed.apply(x, w, b, gamma, beta, patch)
+def patch_embed(x, w, b, gamma, beta, patch, out_dtype=None):
+    return _PatchEmbed.apply(x, w, b, gamma, beta, patch, out_dtype)
 
 
 def enc_video_tail(f, emb_cls, emb_pos, emb_len, emb_odr, gamma, beta, odr=None, vt_mask=None, out_dtype=None):

@@ -51,19 +51,8 @@ def _compute_dtype(*params) -> torch.dtype:
     return torch.float32
 
 
-_FP16_WARNED = False
-
-
-def _warn_fp16_once(dtype):
-    """fp16 (torch.autocast's default dtype, and what the reference's DeepSpeed config uses) is correct here but runs on
-    the CUDA-core kernel family: the tcgen05 GEMM / attention kernels are bf16.  Say so once instead of being silently slow."""
-    global _FP16_WARNED
-    if dtype == torch.float16 and not _FP16_WARNED:
-        _FP16_WARNED = True
-        import warnings
-        warnings.warn("pytorch_empirical-mvm_b200: float16 runs on the CUDA-core kernels (about 30x slower than the tcgen05 "
-                      "bf16 path: 13.6 vs 412 clips/s on Swin-B); use torch.autocast('cuda', dtype=torch.bfloat16) or model.bfloat16()",
-                      RuntimeWarning, stacklevel=3)
+def _autocast_on() -> bool:
+    return torch.is_autocast_enabled("cuda") and torch.get_autocast_dtype("cuda") != torch.float32
 
 
 def _cast(t: Optional[torch.Tensor], dtype):
@@ -272,7 +261,7 @@ class SwinTransformerBlock3D(nn.Module):
             dense = _cast(mask_matrix, cd).contiguous()
         rowcode, colcode = self.attn.bias_codes(plan.N)
         wq, bq, tab, wp, bp = self.attn.params(cd)
-        y = VF.attn_branch(x.view(B, D * H * W, C), _cast(self.norm1.weight, cd), _cast(self.norm1.bias, cd), wq, bq,
+        y = VF.attn_branch(x.view(B, D * H * W, C), _cast(self.norm1.weight, x.dtype), _cast(self.norm1.bias, x.dtype), wq, bq,
                            tab, wp, bp, self._dp_scale(x), plan, rowcode, colcode, dense, self.num_heads,
                            self.attn.scale, cfg_window=self.attn.window_size)
         return y.view(B, D, H, W, C)
@@ -280,7 +269,7 @@ class SwinTransformerBlock3D(nn.Module):
     def _part2(self, x, cd):
         B, D, H, W, C = x.shape
         m = self.mlp
-        y = VF.mlp_branch(x.view(B, D * H * W, C), _cast(self.norm2.weight, cd), _cast(self.norm2.bias, cd),
+        y = VF.mlp_branch(x.view(B, D * H * W, C), _cast(self.norm2.weight, x.dtype), _cast(self.norm2.bias, x.dtype),
                           _cast(m.fc1.weight, cd), _cast(m.fc1.bias, cd), _cast(m.fc2.weight, cd),
                           _cast(m.fc2.bias, cd), self._dp_scale(x))
         return y.view(B, D, H, W, C)
@@ -288,7 +277,12 @@ class SwinTransformerBlock3D(nn.Module):
     def forward(self, x, mask_matrix=None):
         _require_cuda(x)
         cd = _compute_dtype(self.norm1.weight)
-        x = _cast(x, cd).contiguous()
+        # Under autocast an fp32 residual stream stays fp32, as in the reference (LayerNorm reads and `shortcut +
+        # drop_path(x)` produces fp32 there: stage 0, behind the fp32 patch norm); a 16-bit stream (behind a PatchMerging
+        # Linear) stays 16-bit.  Otherwise the stream is in the parameters' dtype.
+        if not (_autocast_on() and x.dtype == torch.float32):
+            x = _cast(x, cd)
+        x = x.contiguous()
         # residual adds and drop-path are fused into the proj / fc2 epilogues (video_swin.py:256, 261)
         if self.use_checkpoint and torch.is_grad_enabled():
             x = checkpoint.checkpoint(self._part1, x, mask_matrix, cd, use_reentrant=False)
@@ -387,7 +381,8 @@ class PatchEmbed3D(nn.Module):
         b = _cast(self.norm.bias, cd) if self.norm is not None else None
         if x.dtype not in (torch.float32, torch.bfloat16, torch.float16):
             x = x.float()
-        y = VF.patch_embed(x, _cast(self.proj.weight, cd), _cast(self.proj.bias, cd), g, b, self.patch_size)
+        y = VF.patch_embed(x, _cast(self.proj.weight, cd), _cast(self.proj.bias, cd), g, b, self.patch_size,
+                           out_dtype=torch.float32 if (_autocast_on() and self.norm is not None) else None)
         return y.view(B, D + 2 - pd, -(-H // ph), -(-W // pw), self.embed_dim)
 
     def forward(self, x):
@@ -431,7 +426,6 @@ class SwinTransformer3D(nn.Module):
         """x (B,3,D,H,W) -> (B, 8E, D, H/32, W/32), a permuted view of the channels-last buffer
         exactly like the reference returns (video_swin.py:470-482)."""
         _require_cuda(x)
-        _warn_fp16_once(_compute_dtype(self.norm.weight))
         with torch.cuda.device(x.device):
             t = self.patch_embed.forward_tokens(x)
             for layer in self.layers:
