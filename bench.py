@@ -182,8 +182,11 @@ def main():
     model.init_weights()
     model = model.to(dev).to(tdtype).train()
     net = model
-    dp_mode = os.environ.get("VSW_DP_MODE", "coalesced") if world > 1 else "none"
+    # gradient exchange (the one collective of the path): "flat" = gradients written into one flat buffer, 4 contiguous ranges
+    # all-reduced while backward runs (dp.FlatGradReducer); "coalesced" / "overlap" / "ddp" are the earlier forms, kept for A/B
+    dp_mode = os.environ.get("VSW_DP_MODE", "flat") if world > 1 else os.environ.get("VSW_DP_MODE", "none")
     reducer = vsw.dp.OverlappedGradReducer(model) if dp_mode == "overlap" else None
+    flat_red = vsw.dp.FlatGradReducer(model, n_chunks=int(os.environ.get("VSW_DP_CHUNKS", "4"))) if dp_mode == "flat" else None
     if world > 1 and dp_mode == "ddp":
         from torch.nn.parallel import DistributedDataParallel as DDP
         net = DDP(model, device_ids=[local_rank], gradient_as_bucket_view=True,
@@ -199,12 +202,17 @@ def main():
     l2_note = "inputs+activations per step >> 126 MB L2 (no explicit flush)"
 
     def step(x, module=None):
-        for p in model.parameters():
-            p.grad = None
+        if flat_red is not None and module is None:
+            flat_red.zero_grad()
+        else:
+            for p in model.parameters():
+                p.grad = None
         y = (module or net)(x)
         loss = (y * Rm).sum(dtype=torch.float32)
         loss.backward()
-        if dp_mode == "coalesced" and module is None:
+        if flat_red is not None and module is None:
+            flat_red.finish()
+        elif dp_mode == "coalesced" and module is None:
             vsw.dp.all_reduce_gradients_coalesced(model.parameters())   # the one exchange step (NCCL, in place, averaged)
         elif dp_mode == "overlap" and module is None:
             reducer.finish()   # per-block coalesced all-reduces were launched from autograd hooks during backward
@@ -280,6 +288,8 @@ def main():
 
     if reducer is not None:
         reducer.remove()   # the next leg runs on rank 0 alone: no collective may be issued from its backward
+    if flat_red is not None:
+        flat_red.remove()
     # ---- roofline of the dominant kernel family: per-launch CUDA events on the launching stream
     roofline, families = None, None
     if rank == 0:
@@ -334,7 +344,7 @@ def main():
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": args.dtype, "data": "synthetic",
             "config": {"workload": workload, "variant": args.model, "clips_per_gpu": B, "global_batch": world * B,
-                       "parallelism": f"dp{world}", "gemm_backend": args.backend, "l2": l2_note,
+                       "parallelism": f"dp{world}", "grad_exchange": dp_mode, "gemm_backend": args.backend, "l2": l2_note,
                        "optimizer": "excluded (metric is encoder fwd+bwd, SURVEY 8d)"},
             "clocks": sampler.result(), "e2e": e2e, "gpu_launches": int(launches),
             "step_tflops_per_gpu": step_tflops / world,

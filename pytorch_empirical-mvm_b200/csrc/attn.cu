@@ -12,9 +12,8 @@ static bool attn_want_tc(int dtype, int hd, const void* dmask) {
 }
 static bool attn_want_tc2(int dtype, int hd, const void* dmask, bool bwd) {
     // which generation of the tcgen05 kernel bf16 takes: VSW_ATTN_TC2 is a bit mask read once per process (bit 0: forward,
-    // bit 1: backward use the second generation; default 2 -- the first-generation forward is still ~10% faster on
-    // the 392-token window).  fp16 only exists in the second generation.
-    static const int pref = getenv("VSW_ATTN_TC2") ? atoi(getenv("VSW_ATTN_TC2")) : 2;
+    // bit 1: backward use the second generation; default 3 = both).  fp16 only exists in the second generation.
+    static const int pref = getenv("VSW_ATTN_TC2") ? atoi(getenv("VSW_ATTN_TC2")) : 3;
     if ((dtype != VSW_BF16 && dtype != VSW_F16) || hd != 32 || dmask) return false;
     if (dtype == VSW_BF16 && !(pref & (bwd ? 2 : 1))) return false;
     const int b = backend();

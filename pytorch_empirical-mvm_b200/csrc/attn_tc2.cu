@@ -50,6 +50,7 @@ constexpr float LOG2E = 1.4426950408889634f, LN2 = 0.6931471805599453f;
 constexpr float MASKV = -100.0f * LOG2E;   // the reference's additive -100 (video_swin.py:304-306), in log2 units
 constexpr float MASKC = 100.0f * LOG2E / 1.7014118346046923e38f;   // times -2^127 (0xFF000000) = MASKV
 constexpr float SAFE = 50.0f;              // |exponent| bound (log2 units) under which no max is subtracted
+constexpr float F16_TOP = 8.0f;            // fp16 single pass: largest exponent after the uniform shift (P <= 256)
 
 // ---- shared-memory carve-up (offsets from a 1024-byte aligned base) ------------------------------------------------------
 constexpr int OFF_STAGE = 0;
@@ -309,10 +310,20 @@ attn2_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
     const uint32_t tmem = *s.tmem_slot;
     const uint32_t stage_a = tc::smem_u32(base + OFF_STAGE);
     auto rows_of = [&](int kb) { return min(KRB, p.KR - kb * KRB); };   // key rows of block kb
+    // bf16: the exponents may be used as they are while |exponent| <= 2 SAFE (2^100 is no problem for bf16 / fp32).
+    // fp16: P must stay inside half's range.  With bound >= every |exponent| of the item (Cauchy-Schwarz + bias range) and the
+    // uniform shift c = bound - F16_TOP, P = 2^(x - c) <= 2^F16_TOP = 256, and the largest P of any row is >= 2^(F16_TOP - 2 bound)
+    // >= 2^-8 while bound <= F16_TOP (normal halves, full precision); beyond that the two-pass path with the true row maximum.
+    auto f16_bound = [&](int st) {
+        const StageFlags f = flags[st];
+        return sqrtf(f.q2max * f.k2max) * p.scale_log2 + fmaxf(fabsf(f.bmax), fabsf(f.bmin));
+    };
     auto is_exact = [&](int st) {
+        if (p.force_exact) return true;
+        if (F16) return !(f16_bound(st) <= F16_TOP);
         const StageFlags f = flags[st];
         const bool bias_ok = f.bmax <= SAFE && f.bmin >= -SAFE;
-        return p.force_exact || !bias_ok || !(f.q2max * f.k2max * p.scale_log2 * p.scale_log2 <= SAFE * SAFE);
+        return !bias_ok || !(f.q2max * f.k2max * p.scale_log2 * p.scale_log2 <= SAFE * SAFE);
     };
 
     // Register re-partitioning (65536 = 3 x 128 x 152 + 128 x 56): the exp warps need ~150 registers for a software-pipelined
@@ -583,7 +594,7 @@ attn2_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
                 const int ic = min(i, p.N - 1);
                 const uint32_t arow = tab_a + reinterpret_cast<const uint32_t*>(base + OFF_AROW)[t * QT + row];
                 const uint32_t regi4 = masked ? (uint32_t)regq[ic] * 0x01010101u : 0u;
-                float mx = 0.f;
+                float mx = (F16 && !exact) ? f16_bound(st) - F16_TOP : 0.f;   // fp16 single pass: uniform shift instead of the row maximum
                 const int xslot = etile & 3;
                 for (int pass = exact ? 0 : 1; pass < 2; ++pass) {
                     if (exact && pass == 1) {
@@ -616,8 +627,10 @@ attn2_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
                         }
                         if (active) {
                             float ls;
-                            if (exact) ls = masked ? block_exp<WW, true, true, F16>(a) : block_exp<WW, false, true, F16>(a);
-                            else ls = masked ? block_exp<WW, true, false, F16>(a) : block_exp<WW, false, false, F16>(a);
+                            // one instantiation per mask flavour: the single-pass case runs the same code with nm = 0 (bf16) or the
+                            // uniform shift (fp16).  A separate no-offset variant saved one FADD per score but pushed the kernel over
+                            // its 128-register budget (900 bytes of spills through a ~1 KB L1).
+                            ls = masked ? block_exp<WW, true, true, F16>(a) : block_exp<WW, false, true, F16>(a);
                             lpart[((otile & 3) * MAXNKB + kb) * QT + row] = ls;
                         }
                         tc::tmem_st_wait();
@@ -802,7 +815,7 @@ int tc2_attn_fwd(const void* qkv, const void* table, const int32_t* rowcode, con
     p.B_ = B_; p.nW = nW; p.N = N; p.nH = nH; p.wh = g.wh; p.ww = g.ww; p.KR = g.KR; p.nq = g.nq; p.nkb = g.nkb;
     p.tab_bytes = g.tab_bytes; p.NHt = 2 * g.wh - 1; p.wdc = g.wdc;
     p.scale_log2 = scale * LOG2E;
-    p.force_exact = dtype == VSW_F16 ? 1 : 0;
+    { static const int fx = getenv("VSW_ATTN2_EXACT") ? atoi(getenv("VSW_ATTN2_EXACT")) : 0; p.force_exact = fx; }   // 1: always the two-pass softmax (tests)
     { static const int pair = getenv("VSW_ATTN2_PAIR") ? atoi(getenv("VSW_ATTN2_PAIR")) : 1; p.pair = pair < 1 ? 1 : (pair > 2 ? 2 : pair); }
     p.dbg = attn2_debug_buffer("fwd");
     int dev = 0, sms = kNumSMs;

@@ -62,6 +62,22 @@ __device__ __forceinline__ void store_vec(T* __restrict__ p, const float (&in)[V
     *reinterpret_cast<Pack<T, N>*>(p) = pk;
 }
 
+// N consecutive elements of T (N * sizeof(T) bytes, aligned to that): the narrow-type side of a mixed-width kernel whose vector
+// length is set by the WIDER type (fp32 rows with a 16-bit output or gradient: 4 elements = 8 bytes)
+template <typename T, int N>
+__device__ __forceinline__ void load_n(const T* __restrict__ p, float (&out)[N]) {
+    Pack<T, N> pk = *reinterpret_cast<const Pack<T, N>*>(p);
+#pragma unroll
+    for (int i = 0; i < N; ++i) out[i] = to_f<T>(pk.v[i]);
+}
+template <typename T, int N>
+__device__ __forceinline__ void store_n(T* __restrict__ p, const float (&in)[N]) {
+    Pack<T, N> pk;
+#pragma unroll
+    for (int i = 0; i < N; ++i) pk.v[i] = from_f<T>(in[i]);
+    *reinterpret_cast<Pack<T, N>*>(p) = pk;
+}
+
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);

@@ -90,6 +90,8 @@ __global__ void __launch_bounds__(256) ln_fwd_kernel(const T* __restrict__ x, co
                     constexpr int VO = Vec16<TO>::N;
                     if constexpr (VO == VN) {
                         store_vec<TO>(y + row * Cw + vi * VN, o);
+                    } else if constexpr (VO > VN) {   // TO narrower than T (16-bit output of an fp32 row): one 8-byte store
+                        store_n<TO, VN>(y + row * Cw + vi * VN, o);
                     } else {
 #pragma unroll
                         for (int h = 0; h < VN / VO; ++h) {
@@ -172,8 +174,8 @@ __global__ void __launch_bounds__(256, (VPL == 1 ? 4 : (VPL == 2 ? 2 : 1))) ln_b
 #pragma unroll
         for (int k = 0; k < VPL; ++k) {
             constexpr int VD = Vec16<TDY>::N;
-            if constexpr (VD == VN) {
-                load_vec<TDY>(dy + rowc * Cw + vic[k] * VN, g[k]);
+            if constexpr (VD >= VN) {   // same width, or a 16-bit dy against fp32 rows (one 8-byte load)
+                load_n<TDY, VN>(dy + rowc * Cw + vic[k] * VN, g[k]);
             } else {
 #pragma unroll
                 for (int h = 0; h < VN / VD; ++h) {
@@ -283,8 +285,8 @@ __global__ void __launch_bounds__(256) ln_colsum_kernel(const TDY* __restrict__ 
             if (GROUPS == 1 && src < 0) continue;  // zeroed output row: no gradient
             float d[VN];
             constexpr int VD = Vec16<TDY>::N;
-            if constexpr (VD == VN) {
-                load_vec<TDY>(dy + row * Cw + vi * VN, d);
+            if constexpr (VD >= VN) {
+                load_n<TDY, VN>(dy + row * Cw + vi * VN, d);
             } else {
 #pragma unroll
                 for (int h = 0; h < VN / VD; ++h) {

@@ -148,3 +148,156 @@ class OverlappedGradReducer:
         for h in self._hooks:
             h.remove()
         self._hooks.clear()
+
+
+class FlatGradReducer:
+    """The exchange step as a few large messages overlapped with backward (the reference's DDP, agent.py:195-201).
+
+    Every parameter gets a fixed slot in ONE flat buffer per dtype, laid out in reverse registration order (the order in which
+    backward produces gradients).  While this object is installed, the wgrad / LayerNorm-backward kernels write each gradient
+    straight into its slot (``functional.GRAD_SINK``) and autograd adopts that view as ``p.grad``; a gradient that arrives any
+    other way is copied into its slot by the hook.  The buffer is cut into ``n_chunks`` contiguous, equally sized ranges; as soon
+    as every parameter of a range has its gradient, the range is averaged in place by one asynchronous all-reduce.  The tensor
+    list of every collective is a fixed slice of the flat buffer: it does not depend on which parameters received a gradient on
+    which rank (slots without a gradient hold zeros).
+
+        red = FlatGradReducer(model)
+        for batch in loader:
+            red.zero_grad()            # instead of setting p.grad = None
+            loss(model(batch)).backward()
+            red.finish()               # waits; p.grad are views of the averaged flat buffer
+    """
+
+    ALIGN = 64   # elements: every slot starts 128-byte aligned for 16-bit types (the kernels need 16 bytes)
+
+    def __init__(self, module: torch.nn.Module, n_chunks: int = 4, install_sink: bool = True):
+        self.params = [p for p in reversed(list(module.parameters())) if p.requires_grad]
+        self.flat = {}          # dtype -> flat tensor
+        self.slot = {}          # id(p) -> (dtype, offset, numel)
+        self._by_ptr = {}       # data_ptr -> parameter
+        sizes = {}
+        for p in self.params:
+            off = sizes.get(p.dtype, 0)
+            self.slot[id(p)] = (p.dtype, off, p.numel())
+            sizes[p.dtype] = off + (p.numel() + self.ALIGN - 1) // self.ALIGN * self.ALIGN
+            self._by_ptr[p.data_ptr()] = p
+        dev = self.params[0].device if self.params else torch.device("cpu")
+        for dt, n in sizes.items():
+            self.flat[dt] = torch.zeros(n, dtype=dt, device=dev)
+        # chunks: contiguous ranges of each flat buffer with about equal bytes, cut at slot boundaries
+        self.chunks = []        # (dtype, begin, end)
+        self._chunk_of = {}     # id(p) -> chunk index
+        for dt, n in sizes.items():
+            ps = [p for p in self.params if p.dtype == dt]
+            k = max(1, min(n_chunks, len(ps)))
+            target = n / k
+            begin, ci = 0, len(self.chunks)
+            for i, p in enumerate(ps):
+                _, off, num = self.slot[id(p)]
+                end = off + (num + self.ALIGN - 1) // self.ALIGN * self.ALIGN
+                self._chunk_of[id(p)] = len(self.chunks)
+                last = i == len(ps) - 1
+                if last or (end >= target * (len(self.chunks) - ci + 1) and len(self.chunks) - ci < k - 1):
+                    self.chunks.append((dt, begin, end))
+                    begin = end
+        self._members = [0] * len(self.chunks)
+        for p in self.params:
+            self._members[self._chunk_of[id(p)]] += 1
+        self._left = list(self._members)
+        self._launched = [False] * len(self.chunks)
+        self._written = set()
+        self._works = []
+        self._hooks = [p.register_post_accumulate_grad_hook(self._on_grad) for p in self.params]
+        self._sink_installed = False
+        if install_sink:
+            self.install()
+
+    # ---- the sink the autograd Functions ask for a gradient buffer
+    def install(self):
+        from . import functional as VF
+        VF.GRAD_SINK = self._sink
+        self._sink_installed = True
+
+    def _view(self, p):
+        dt, off, n = self.slot[id(p)]
+        return self.flat[dt][off:off + n].view(p.shape)
+
+    def _sink(self, key, shape, dtype):
+        p = self._by_ptr.get(key)
+        if p is None or tuple(p.shape) != tuple(shape) or p.dtype != dtype or id(p) in self._written:
+            return None
+        self._written.add(id(p))
+        return self._view(p)
+
+    # ---- per step
+    def zero_grad(self):
+        """zero the flat buffers (one memset each) and detach every ``.grad`` so that autograd adopts the slot views"""
+        for f in self.flat.values():
+            f.zero_()
+        for p in self.params:
+            p.grad = None
+        self._written.clear()
+        self._left = list(self._members)
+        self._launched = [False] * len(self.chunks)
+
+    def _on_grad(self, p):
+        dt, off, n = self.slot[id(p)]
+        flat = self.flat[dt]
+        g = p.grad
+        if g is not None and not (g.untyped_storage().data_ptr() == flat.untyped_storage().data_ptr()
+                                  and g.storage_offset() == off and g.is_contiguous()):
+            v = self._view(p)
+            v.copy_(g)
+            p.grad = v
+        ci = self._chunk_of[id(p)]
+        self._left[ci] -= 1
+        if self._left[ci] == 0 and not self._launched[ci]:
+            self._launch(ci)
+
+    def _launch(self, ci):
+        self._launched[ci] = True
+        if not dist.is_initialized() or dist.get_world_size() == 1:
+            return
+        dt, a, b = self.chunks[ci]
+        buf = self.flat[dt][a:b]
+        if dist.get_backend() == "nccl":
+            self._works.append((dist.all_reduce(buf, op=dist.ReduceOp.AVG, async_op=True), None))
+        else:   # gloo has no AVG
+            self._works.append((dist.all_reduce(buf, op=dist.ReduceOp.SUM, async_op=True), buf))
+
+    def finish(self) -> int:
+        """after ``backward()``: send the ranges still waiting for a gradient (their missing slots hold zeros), wait for all
+        collectives; returns the number of collectives of this step"""
+        for ci in range(len(self.chunks)):
+            if not self._launched[ci]:
+                self._launch(ci)
+        n = len(self._works)
+        distributed = dist.is_initialized() and dist.get_world_size() > 1
+        present = None
+        if distributed:
+            # which parameters received a gradient on ANY rank (a tiny extra collective, like DDP's unused-parameter bitmap):
+            # those get their averaged slot as .grad on every rank, so that all replicas take the same optimizer step
+            dev = next(iter(self.flat.values())).device
+            present = torch.tensor([0 if p.grad is None else 1 for p in self.params], dtype=torch.int32).to(dev)
+            pw = dist.all_reduce(present, op=dist.ReduceOp.SUM, async_op=True)
+        for w, buf in self._works:
+            w.wait()
+            if buf is not None:
+                buf.div_(dist.get_world_size())
+        self._works.clear()
+        if distributed:
+            pw.wait()
+            for p, c in zip(self.params, present.tolist()):
+                if c and p.grad is None:
+                    p.grad = self._view(p)
+        # parameters without a gradient on every rank keep p.grad = None (their slots are zero), as plain autograd leaves them
+        return n
+
+    def remove(self):
+        for h in self._hooks:
+            h.remove()
+        self._hooks.clear()
+        if self._sink_installed:
+            from . import functional as VF
+            VF.GRAD_SINK = None
+            self._sink_installed = False

@@ -226,10 +226,32 @@ def linear_dgrad(dy, w, M, N, K, a_rowmap=None, a_rowscale=None, rows_per_batch=
     return dx
 
 
-def linear_wgrad(dy, x2d, M, N, K, need_bias=True, grad_dtype=None):
+# Gradient sink (dp.FlatGradReducer): when set, maps the data_ptr of a parameter to a fresh view of its slot in one flat
+# gradient buffer, so the wgrad kernels write where the all-reduce reads (no per-parameter copy).  Returns None for unknown
+# parameters, wrong shape / dtype, or a slot already written in this step (autograd then accumulates the usual way).
+GRAD_SINK = None
+
+
+def _sink_view(key, shape, dtype):
+    if GRAD_SINK is None or not key:
+        return None
+    return GRAD_SINK(key, tuple(shape), dtype)
+
+
+def _key(t):
+    return t.data_ptr() if t is not None else 0
+
+
+def linear_wgrad(dy, x2d, M, N, K, need_bias=True, grad_dtype=None, w_key=0, b_key=0):
     grad_dtype = grad_dtype or dy.dtype
-    dw = _empty((N, K), grad_dtype, dy.device)
-    db = _empty((N,), grad_dtype, dy.device) if need_bias else None
+    dw = _sink_view(w_key, (N, K), grad_dtype)
+    if dw is None:
+        dw = _empty((N, K), grad_dtype, dy.device)
+    db = None
+    if need_bias:
+        db = _sink_view(b_key, (N,), grad_dtype)
+        if db is None:
+            db = _empty((N,), grad_dtype, dy.device)
     wsb = int(L.lib().vsw_linear_wgrad_workspace(M, N, K))
     ws = _empty((max(wsb, 4),), torch.uint8, dy.device)
     t0 = PROFILER.begin() if PROFILER is not None else None
@@ -281,8 +303,15 @@ def _c(t):
     return t if t is None or t.is_contiguous() else t.contiguous()
 
 
-def _grad_to(g, like):
-    return None if g is None else g.to(like.dtype)
+def _grad_to(g, like, key=0):
+    """fp32 kernel output -> gradient in the parameter's dtype (into its flat-buffer slot when a sink is installed)"""
+    if g is None:
+        return None
+    v = _sink_view(key, g.shape, like.dtype)
+    if v is not None:
+        v.copy_(g)
+        return v
+    return g.to(like.dtype)
 
 
 # ----------------------------------------------------------------------------------------------
@@ -315,6 +344,7 @@ class _AttnBranch(torch.autograd.Function):
                               dense_mask)
         ctx.plan, ctx.nH, ctx.scale, ctx.cfg_window = plan, nH, scale, cfg_window
         ctx.has_qkv_bias = bqkv is not None
+        ctx.keys = (_key(g1), _key(b1), _key(bqkv), _key(bproj))
         return x1
 
     @staticmethod
@@ -334,17 +364,18 @@ class _AttnBranch(torch.autograd.Function):
         dO = linear_dgrad(dx1c, wproj, M, C, C, a_rowmap=plan.gather, a_rowscale=rowscale, rows_per_batch=R,
                           src_rows_per_batch=T, a_out=a_buf)
         del dx1c
-        dwp, dbp = linear_wgrad(a_buf, o, M, C, C)
+        kg1, kb1, kbq, kbp = ctx.keys
+        dwp, dbp = linear_wgrad(a_buf, o, M, C, C, w_key=_key(wproj), b_key=kbp)
         del a_buf
         region = plan.region if (plan.shifted and dense_mask is None) else None
         dqkv, dtable = attn_bwd(qkv, o, dO, lse, table, rowcode, colcode, region, dense_mask, B * nW, nW, N, nH, hd, scale,
                                 planes=plan.ws[0], window=ctx.cfg_window)
         del dO
         dxw = linear_dgrad(dqkv, wqkv, M, 3 * C, C)
-        dwq, dbq = linear_wgrad(dqkv, xw.view(M, C), M, 3 * C, C, need_bias=ctx.has_qkv_bias)
+        dwq, dbq = linear_wgrad(dqkv, xw.view(M, C), M, 3 * C, C, need_bias=ctx.has_qkv_bias, w_key=_key(wqkv), b_key=kbq)
         del dqkv
         dx, dg1, db1 = ln_bwd(dxw, x, g1, mean, rstd, plan.gather, dx1, B, T, R, C)
-        return (dx, _grad_to(dg1, g1), _grad_to(db1, g1), dwq, dbq, _grad_to(dtable, table), dwp, dbp,
+        return (dx, _grad_to(dg1, g1, kg1), _grad_to(db1, g1, kb1), dwq, dbq, _grad_to(dtable, table, _key(table)), dwp, dbp,
                 None, None, None, None, None, None, None, None)
 
 
@@ -371,6 +402,7 @@ class _MlpBranch(torch.autograd.Function):
                              dst_rows_per_batch=T).view(B, T, C)
         if need_grad:
             ctx.save_for_backward(x, g2, w1, w2, rowscale, n2, mean, rstd, u, g)
+            ctx.keys = (_key(g2), _key(b2), _key(bb1), _key(bb2))
         return out
 
     @staticmethod
@@ -385,13 +417,14 @@ class _MlpBranch(torch.autograd.Function):
         a_buf = _empty((M, C), cd, x.device) if rowscale is not None else None
         du = linear_dgrad(doutc.view(M, C), w2, M, C, Hd, a_rowscale=rowscale, rows_per_batch=T, src_rows_per_batch=T,
                           a_out=a_buf, mul=u)
-        dw2, db2 = linear_wgrad(a_buf if a_buf is not None else doutc.view(M, C), g, M, C, Hd)
+        kg2, kb2, kbb1, kbb2 = ctx.keys
+        dw2, db2 = linear_wgrad(a_buf if a_buf is not None else doutc.view(M, C), g, M, C, Hd, w_key=_key(w2), b_key=kbb2)
         del a_buf, doutc
         dn2 = linear_dgrad(du, w1, M, Hd, C)
-        dw1, db1 = linear_wgrad(du, n2.view(M, C), M, Hd, C)
+        dw1, db1 = linear_wgrad(du, n2.view(M, C), M, Hd, C, w_key=_key(w1), b_key=kbb1)
         del du
         dx, dg2, dbeta2 = ln_bwd(dn2, x, g2, mean, rstd, None, dout, B, T, T, C)
-        return dx, _grad_to(dg2, g2), _grad_to(dbeta2, g2), dw1, db1, dw2, db2, None
+        return dx, _grad_to(dg2, g2, kg2), _grad_to(dbeta2, g2, kb2), dw1, db1, dw2, db2, None
 
 
 # ----------------------------------------------------------------------------------------------

@@ -128,6 +128,74 @@ def test_overlapped_grad_reducer_gloo(tmp_path):
     assert all(os.path.exists(os.path.join(str(tmp_path), f"ok{r}")) for r in range(world))
 
 
+def _worker_flat(rank, world, port, tmpdir):
+    """FlatGradReducer: gradients live in one flat buffer, a few fixed contiguous ranges are all-reduced as they fill;
+    a parameter that gets a gradient on ONE rank only must not change the collective's shape (zeros travel instead)"""
+    sys.path.insert(0, ROOT)
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        dp = importlib.import_module("pytorch_empirical-mvm_b200.dp")
+
+        class Net(torch.nn.Module):
+            def __init__(self):
+                super().__init__()
+                self.embed = torch.nn.Linear(4, 8)
+                self.blocks = torch.nn.ModuleList([torch.nn.Linear(8, 8) for _ in range(5)])
+                self.unused = torch.nn.Linear(3, 3)      # never receives a gradient
+                self.sometimes = torch.nn.Linear(8, 1)   # receives a gradient on rank 0 only
+                self.head = torch.nn.Linear(8, 2)
+
+            def forward(self, x, extra):
+                x = self.embed(x)
+                for b in self.blocks:
+                    x = x + torch.tanh(b(x))
+                y = self.head(x)
+                return y + self.sometimes(x).sum() * 0.01 if extra else y
+
+        torch.manual_seed(0)
+        net, ref = Net().double(), Net().double()
+        ref.load_state_dict(net.state_dict())
+        red = dp.FlatGradReducer(net, n_chunks=3, install_sink=False)
+        assert len(red.chunks) == 3 and red.chunks[0][1] == 0 and red.chunks[-1][2] == red.flat[torch.float64].numel()
+        g = torch.Generator().manual_seed(3)
+        x, t = torch.randn(6, 4, generator=g).double(), torch.randn(6, 2, generator=g).double()
+        sl = dp.clip_shard(6, rank, world)
+        for _ in range(2):   # two steps: zero_grad() re-arms the reducer
+            red.zero_grad()
+            ((net(x[sl], rank == 0) - t[sl]) ** 2).sum().mul(world / 6).backward()
+            assert red.finish() == 3
+        # reference: the same two shards on one process, gradients averaged by hand
+        tot = {}
+        for r in range(world):
+            ref.zero_grad(set_to_none=True)
+            s2 = dp.clip_shard(6, r, world)
+            ((ref(x[s2], r == 0) - t[s2]) ** 2).sum().mul(world / 6).backward()
+            for n, q in ref.named_parameters():
+                if q.grad is not None:
+                    tot[n] = tot.get(n, 0) + q.grad / world
+        flat = red.flat[torch.float64]
+        for n, p in net.named_parameters():
+            if n.startswith("unused"):
+                assert p.grad is None, n
+                continue
+            # (`sometimes` has no local gradient on rank 1: finish() hands it the averaged slot, so both replicas step alike)
+            assert p.grad.untyped_storage().data_ptr() == flat.untyped_storage().data_ptr(), n   # a view of the flat buffer
+            assert torch.allclose(p.grad, tot[n], rtol=1e-9, atol=1e-12), n
+        red.remove()
+        with open(os.path.join(tmpdir, f"ok{rank}"), "w") as f:
+            f.write("ok")
+    finally:
+        dist.destroy_process_group()
+
+
+def test_flat_grad_reducer_gloo(tmp_path):
+    world, port = 2, 29000 + os.getpid() % 1000 + 2
+    mp.spawn(_worker_flat, args=(world, port, str(tmp_path)), nprocs=world, join=True)
+    assert all(os.path.exists(os.path.join(str(tmp_path), f"ok{r}")) for r in range(world))
+
+
 def test_clip_shard_covers_batch():
     dp = importlib.import_module("pytorch_empirical-mvm_b200.dp")
     for n in (1, 5, 32, 33):
