@@ -36,6 +36,8 @@ MODELS = {
     "violet": dict(embed_dim=96, depths=[2, 2, 18, 2], num_heads=[3, 6, 12, 24], window_size=(8, 7, 7)),
     "swin_l_384": dict(embed_dim=192, depths=[2, 2, 18, 2], num_heads=[6, 12, 24, 48], window_size=(8, 12, 12)),
 }
+# kernel symbol behind each profiler family in the default configuration (roofline.traffic is only reported for a capture of it)
+CURRENT_KERNEL = {"window_attn_bwd": "attn2_bwd_kernel", "window_attn_fwd": "attn2_fwd_kernel"}
 FWD_BWD_GFLOP_PER_CLIP = {"swin_b": 844.0, "violet": 497.0, "swin_l_384": 6319.1}  # SURVEY 8d (3 x fwd)
 
 
@@ -82,6 +84,38 @@ class ClockSampler(threading.Thread):
         return dict(sm_mhz=(s[len(s) // 2] if s else None), sm_max_mhz=self.max_mhz, reasons=sorted(self.reasons))
 
 
+def reference_available():
+    return os.path.isdir("/root/reference/visbackbone")
+
+
+def cpu_true_reference_run(model_name, batch, steps, warmup, threads):
+    """the UNMODIFIED reference module (visbackbone/video_swin.py, imported where it lies) forward+backward on the host cores.
+    Only possible where /root/reference exists (the build container); the GPU box has no copy of it."""
+    sys.path.insert(0, os.path.join(ROOT, "tests", "golden"))
+    from make_golden import import_reference
+    vs = import_reference()
+    torch.set_num_threads(threads)
+    kw = MODELS[model_name]
+    torch.manual_seed(0)
+    m = vs.SwinTransformer3D(pretrained=None, drop_path_rate=0.0, **kw)
+    m.train()
+    side = 384 if model_name == "swin_l_384" else 224
+    x = torch.randn(batch, 3, 8, side, side)
+    with torch.no_grad():
+        y0 = m(x[:1])
+    R = torch.randn(batch, *y0.shape[1:]) / 1024
+    times = []
+    for i in range(warmup + steps):
+        t0 = time.perf_counter()
+        for p in m.parameters():
+            p.grad = None
+        (m(x) * R).sum().backward()
+        dt = time.perf_counter() - t0
+        if i >= warmup:
+            times.append(dt)
+    return batch * len(times) / sum(times), sum(times) / len(times)
+
+
 def cpu_reference_run(model_name, batch, steps, warmup, threads):
     """the reference algorithm (oracle port, fp32) forward+backward on the host cores -> clips/s"""
     from oracle import swin3d_oracle as O
@@ -103,6 +137,87 @@ def cpu_reference_run(model_name, batch, steps, warmup, threads):
         if i >= warmup:
             times.append(dt)
     return batch * len(times) / sum(times), sum(times) / len(times)
+
+
+def attn_sweep(args):
+    """BASELINE config 5: WindowAttention3D core (QK^T + relative-position bias + shift mask + softmax + PV, forward and
+    backward) over window 8x7x7 vs 8x12x12, shifted vs unshifted, heads 4-32, next to the reference algorithm on the same
+    tensors on the host cores (video_swin.py:152-169 restated with torch ops; bounded sample of windows).  One JSON line."""
+    vsw = importlib.import_module(PKG)
+    VF, L = vsw.functional, vsw._lib
+    from oracle import swin3d_oracle as O   # host-side checker only (mask + index of the CPU reference leg)
+    dev = torch.device("cuda", 0)
+    torch.cuda.set_device(dev)
+    hd, clips = 32, args.batch
+    threads = os.cpu_count() or 1
+    torch.set_num_threads(threads)
+    w0 = torch.randn(4, 4, 392, 32, requires_grad=True)     # warm the host thread pool / allocator before the first timed case
+    (torch.softmax(w0 @ w0.transpose(-1, -2), -1) @ w0).sum().backward()
+    cases = []
+    for window, grid in (((8, 7, 7), (8, 14, 14)), ((8, 12, 12), (8, 24, 24))):
+        for shifted in (False, True):
+            for nH in (4, 8, 16, 32):
+                shift = tuple(w // 2 for w in window) if shifted else (0, 0, 0)
+                plan = VF.window_plan(grid, window, shift, dev)
+                nW, N = plan.nW, plan.N
+                B_, C = clips * nW, nH * hd
+                Lt = (2 * window[0] - 1) * (2 * window[1] - 1) * (2 * window[2] - 1)
+                g = torch.Generator().manual_seed(nH * 7 + N + shifted)
+                qkv_h = torch.randn(B_ * N, 3 * C, generator=g)
+                table_h = torch.randn(Lt, nH, generator=g) * 0.1
+                dout_h = torch.randn(B_ * N, C, generator=g)
+                qkv, table, dout = (t.to(dev).bfloat16() for t in (qkv_h, table_h, dout_h))
+                rc, cc = VF.bias_codes(VF.rel_pos_index(window, dev), N)   # product path: no oracle
+                region = plan.region if plan.shifted else None
+                scale = hd ** -0.5
+
+                def fwd():
+                    return VF.attn_fwd(qkv, table, rc, cc, region, None, B_, nW, N, nH, hd, scale, window=window)
+                out, lse = fwd()
+
+                def bwd():
+                    return VF.attn_bwd(qkv, out, dout, lse, table, rc, cc, region, None, B_, nW, N, nH, hd, scale,
+                                       planes=plan.ws[0], window=window)
+                ms = []
+                for fn in (fwd, bwd):
+                    for _ in range(3):
+                        fn()
+                    torch.cuda.synchronize()
+                    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                    e0.record()
+                    for _ in range(args.steps):
+                        fn()
+                    e1.record()
+                    torch.cuda.synchronize()
+                    ms.append(e0.elapsed_time(e1) / args.steps)
+                # ---- the same tensors through the reference algorithm on the host (first clip's windows only)
+                ns = nW   # windows of one clip
+                q3 = qkv_h[: ns * N].view(ns, N, 3, nH, hd).clone().requires_grad_(True)
+                tb = table_h.clone().requires_grad_(True)
+                mask = O.shift_mask(plan.pgrid, plan.ws, plan.ss) if plan.shifted else None
+                idx = torch.from_numpy(O.relative_position_index(window))[:N, :N].reshape(-1)
+                t0 = time.perf_counter()
+                q, k, v = q3[:, :, 0].transpose(1, 2) * scale, q3[:, :, 1].transpose(1, 2), q3[:, :, 2].transpose(1, 2)
+                sc = q @ k.transpose(-1, -2) + tb[idx].view(N, N, nH).permute(2, 0, 1)[None]
+                if mask is not None:
+                    sc = sc + mask[:, None]
+                o_ref = (torch.softmax(sc, -1) @ v).transpose(1, 2).reshape(ns * N, C)
+                o_ref.backward(dout_h[: ns * N])
+                cpu_s = time.perf_counter() - t0
+                err = float((out[: ns * N].float().cpu() - o_ref.detach()).norm() / o_ref.detach().norm())
+                fl = 4.0 * B_ * nH * N * N * hd
+                cases.append(dict(window=list(window), N=N, heads=nH, shifted=shifted, windows=B_,
+                                  fwd_ms=ms[0], bwd_ms=ms[1], windows_per_s=B_ / ((ms[0] + ms[1]) * 1e-3),
+                                  fwd_tflops=fl / ms[0] / 1e9, bwd_tflops=2 * fl / ms[1] / 1e9,
+                                  path="tcgen05" if N <= 448 else "cuda-core (no tcgen05 kernel for 1152-token windows)",
+                                  cpu_reference_windows_per_s=ns / cpu_s, cpu_sample_windows=ns,
+                                  fwd_rel_l2_vs_cpu_reference=err))
+    print(json.dumps({"metric": "WindowAttention3D core fwd+bwd windows/sec (BASELINE config 5 sweep)", "unit": "windows/s",
+                      "n_gpus": 1, "steps": args.steps, "dtype": "bf16", "data": "synthetic",
+                      "config": {"workload": "window 8x7x7 vs 8x12x12, shifted / unshifted, heads 4-32, head_dim 32, "
+                                 f"{clips} clips x 4 windows", "cpu": f"{threads} threads, {cpu_model_name()}, fp32, "
+                                 "video_swin.py:152-169 restated with torch ops on the first clip's windows"},
+                      "cases": cases}), flush=True)
 
 
 def cpu_model_name():
@@ -127,12 +242,18 @@ def main():
     ap.add_argument("--cpu-batch", type=int, default=2, help="clips per CPU-baseline step (BASELINE config 1: 2)")
     ap.add_argument("--backend", default="auto", choices=["auto", "simt", "tcgen05"])
     ap.add_argument("--dtype", default="bf16", choices=["bf16", "fp16"], help="16-bit compute type (both run on tcgen05)")
+    ap.add_argument("--mode", default="step", choices=["step", "attn_sweep"],
+                    help="step: the fwd+bwd encoder step (the contract line); attn_sweep: BASELINE config 5 microbench sweep")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     args = ap.parse_args()
     if args.impl != "reference" and args.warmup < 3:
         args.warmup = 3   # timing rules: at least 3 warm-up steps (the JSON line reports the value actually used)
 
+    if args.mode == "attn_sweep":
+        if int(os.environ.get("RANK", 0)) == 0:
+            attn_sweep(args)
+        return
     rank = int(os.environ.get("RANK", 0))
     world = int(os.environ.get("WORLD_SIZE", 1))
     local_rank = int(os.environ.get("LOCAL_RANK", 0))
@@ -146,15 +267,19 @@ def main():
             return
         threads = os.cpu_count() or 1
         steps = max(1, min(args.steps, 3))
-        cps, sec = cpu_reference_run(args.model, args.cpu_batch, steps, 1, threads)
+        kind = "reference" if reference_available() else "port"
+        run = cpu_true_reference_run if kind == "reference" else cpu_reference_run
+        cps, sec = run(args.model, args.cpu_batch, steps, 1, threads)
+        what = ("the unmodified visbackbone/video_swin.py imported from /root/reference" if kind == "reference"
+                else "oracle port of visbackbone/video_swin.py (the reference itself does not exist on this box)")
         sample = (f"{steps} timed steps (1 warm-up) of fwd+bwd over {args.cpu_batch} clips of 8x{side}^2, fp32, "
-                  f"oracle port of visbackbone/video_swin.py, torch {torch.__version__} CPU, {threads} threads, {cpu_model_name()}")
+                  f"{what}, torch {torch.__version__} CPU, {threads} threads, {cpu_model_name()}")
         print(json.dumps({
             "impl": "reference", "metric": "Video-Swin-B fwd+bwd clips/sec", "value": cps, "unit": "clips/s",
             "n_gpus": args.gpus, "steps": steps, "warmup": 1, "ms_per_step": sec * 1e3, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": workload, "cpu_sample_clips_per_step": args.cpu_batch},
-            "cpu_baseline": {"value": cps, "unit": "clips/s", "cores": threads, "kind": "port", "sample": sample},
+            "cpu_baseline": {"value": cps, "unit": "clips/s", "cores": threads, "kind": kind, "sample": sample},
             "e2e": {"value": cps, "unit": "clips/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         }))
         return
@@ -316,13 +441,18 @@ def main():
         tensor_bound = v["flops"] > 0
         ach = (v["flops"] / (v["ms"] * 1e-3) / 1e12) if tensor_bound else (v["bytes"] / (v["ms"] * 1e-3) / 1e9)
         peak = pk["tf_sustained"] if tensor_bound else pk["hbm"]
-        traffic = None   # dram bytes per launch of that kernel family from the committed ncu --set full capture
-        tpath = os.path.join(ROOT, "profiles", "ncu_traffic.json")
-        if os.path.exists(tpath) and args.model == "swin_b" and B == 32:
+        # dram__bytes per launch from an `ncu --set full` capture of THIS workload and THIS kernel generation
+        # (profiles/r02_ncu_traffic.json names the kernel symbol and the command); anything else reads null
+        traffic, traffic_source = None, None
+        tpath = os.path.join(ROOT, "profiles", "r02_ncu_traffic.json")
+        if os.path.exists(tpath) and args.model == "swin_b" and B == 32 and args.dtype == "bf16":
             with open(tpath) as f:
-                traffic = json.load(f).get(top, {}).get("avg_dram_bytes_per_launch")
+                ent = json.load(f).get(top)
+            if ent and ent.get("kernel") == CURRENT_KERNEL.get(top) and os.environ.get("VSW_ATTN_TC2") is None:
+                traffic, traffic_source = ent.get("avg_dram_bytes_per_launch"), ent.get("source")
         roofline = {"kernel": top, "bound": "tensor" if tensor_bound else "hbm", "achieved": ach, "peak": peak,
                     "unit": "TFLOP/s" if tensor_bound else "GB/s", "frac": ach / peak, "traffic": traffic,
+                    "traffic_source": traffic_source,
                     "algorithmic_bytes_per_launch": v["bytes"] / max(1, v["launches"]),
                     "peak_source": pk["source"] + (" (sustained bf16)" if tensor_bound else ""),
                     "launches_per_step": v["launches"] // psteps,
@@ -331,10 +461,13 @@ def main():
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         threads = os.cpu_count() or 1
-        cps, sec = cpu_reference_run(args.model, args.cpu_batch, 2, 1, threads)
-        cpu = {"value": cps, "unit": "clips/s", "cores": threads, "kind": "port",
+        kind = "reference" if reference_available() else "port"
+        run = cpu_true_reference_run if kind == "reference" else cpu_reference_run
+        cps, sec = run(args.model, args.cpu_batch, 2, 1, threads)
+        cpu = {"value": cps, "unit": "clips/s", "cores": threads, "kind": kind,
                "sample": f"2 timed steps (1 warm-up) of fwd+bwd over {args.cpu_batch} clips of 8x{side}^2, fp32, "
-                         f"{sec:.2f} s/step, {cpu_model_name()}"}
+                         f"{sec:.2f} s/step, {cpu_model_name()}"
+                         + ("" if kind == "reference" else "; oracle port (no /root/reference on this box)")}
 
     if rank == 0:
         pk = peaks()

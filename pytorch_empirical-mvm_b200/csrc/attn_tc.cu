@@ -61,7 +61,7 @@ __host__ __device__ inline int bias_dh(int l, int R1, int R2, int M1, int M2) { 
 inline BiasLayout bias_layout(int window_dims, int L) {
     BiasLayout b{0, 0, 0, 0, 0, L, 0, 0};
     const int wh = (window_dims >> 8) & 0xFF, ww = (window_dims >> 16) & 0xFF;
-    if (wh < 1 || ww < 1 || getenv("VSW_ATTN_DENSE_TABLE")) return b;
+    if (wh < 1 || ww < 1) return b;
     const int R2 = 2 * ww - 1, R1 = (2 * wh - 1) * R2;
     if (L % R1 != 0) return b;                       // not this window's table
     const int nd = L / R1;                            // 2wd-1
@@ -655,10 +655,10 @@ int tc_attn_fwd(const void* qkv, const void* table, const int32_t* rowcode, cons
         static bool init = false;
         if (!init) {
             init = true;
-            if (getenv("VSW_ATTN_DEBUG")) { cudaMalloc(&dbg, 64); cudaMemset(dbg, 0, 64); }
+            if (VSW_ATTN_PROF && getenv("VSW_ATTN_DEBUG")) { cudaMalloc(&dbg, 64); cudaMemset(dbg, 0, 64); }
         }
         p.dbg = dbg;
-        if (dbg && getenv("VSW_ATTN_DEBUG_DUMP")) {
+        if (VSW_ATTN_PROF && dbg && getenv("VSW_ATTN_DEBUG_DUMP")) {
             long long h[8];
             cudaMemcpy(h, dbg, 64, cudaMemcpyDeviceToHost);
             if (h[5]) fprintf(stderr, "[vsw attn fwd] tiles=%lld avg cycles: wait_s=%lld pass1=%lld pass2=%lld wait_o=%lld epi=%lld | aux warp per item: wait %lld work %lld\n", h[5], h[0]/h[5], h[1]/h[5], h[2]/h[5], h[3]/h[5], h[4]/h[5], h[6] * 4 / h[5], h[7] * 4 / h[5]);

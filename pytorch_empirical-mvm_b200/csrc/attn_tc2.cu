@@ -720,7 +720,7 @@ bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 
 long long* attn2_debug_buffer(const char* which) {
     static long long* dbg = nullptr;
     static std::once_flag once;
-    std::call_once(once, [] { if (getenv("VSW_ATTN_DEBUG")) { cudaMalloc(&dbg, 256); cudaMemset(dbg, 0, 256); } });
+    std::call_once(once, [] { if (VSW_ATTN2_PROF && getenv("VSW_ATTN_DEBUG")) { cudaMalloc(&dbg, 256); cudaMemset(dbg, 0, 256); } });
     if (!dbg) return nullptr;
     long long h[32];
     cudaMemcpy(h, dbg, 256, cudaMemcpyDeviceToHost);
@@ -816,7 +816,7 @@ int tc2_attn_fwd(const void* qkv, const void* table, const int32_t* rowcode, con
     p.tab_bytes = g.tab_bytes; p.NHt = 2 * g.wh - 1; p.wdc = g.wdc;
     p.scale_log2 = scale * LOG2E;
     { static const int fx = getenv("VSW_ATTN2_EXACT") ? atoi(getenv("VSW_ATTN2_EXACT")) : 0; p.force_exact = fx; }   // 1: always the two-pass softmax (tests)
-    { static const int pair = getenv("VSW_ATTN2_PAIR") ? atoi(getenv("VSW_ATTN2_PAIR")) : 1; p.pair = pair < 1 ? 1 : (pair > 2 ? 2 : pair); }
+    p.pair = 1;
     p.dbg = attn2_debug_buffer("fwd");
     int dev = 0, sms = kNumSMs;
     cudaGetDevice(&dev);

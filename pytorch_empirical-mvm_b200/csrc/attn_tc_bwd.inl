@@ -689,17 +689,17 @@ int tc_attn_bwd(const void* qkv, const void* out, const void* dout, const float*
     p.scale = scale; p.scale_log2 = scale * LOG2E;
     p.wh = bl.wh; p.ww = bl.ww; p.R1 = bl.R1; p.R2 = bl.R2; p.pad = bl.pad;
     p.Npad = (N + 15) / 16 * 16; p.nq = (N + QT - 1) / QT;
-    p.ntail = (N % QT != 0 && N % QT <= 8 && !getenv("VSW_ATTN_NO_TAIL")) ? N % QT : 0;
+    p.ntail = (N % QT != 0 && N % QT <= 8) ? N % QT : 0;
     p.wd = wd; p.hw = hw; p.boxhw = boxhw; p.nkb = (hw + boxhw - 1) / boxhw;
     {
         static long long* dbg = nullptr;
         static bool init = false;
         if (!init) {
             init = true;
-            if (getenv("VSW_ATTN_DEBUG")) { cudaMalloc(&dbg, 64); cudaMemset(dbg, 0, 64); }
+            if (VSW_ATTN_PROF && getenv("VSW_ATTN_DEBUG")) { cudaMalloc(&dbg, 64); cudaMemset(dbg, 0, 64); }
         }
         p.dbg = dbg;
-        if (dbg && getenv("VSW_ATTN_DEBUG_DUMP")) {
+        if (VSW_ATTN_PROF && dbg && getenv("VSW_ATTN_DEBUG_DUMP")) {
             long long h[8];
             cudaMemcpy(h, dbg, 64, cudaMemcpyDeviceToHost);
             fprintf(stderr, "[vsw attn bwd] blocks=%lld avg cycles: wait_s=%lld softmax=%lld ; kb epilogues=%lld wait_dkv=%lld\n", h[2], h[0]/(h[2]+1), h[1]/(h[2]+1), h[4], h[3]/(h[4]+1));

@@ -594,7 +594,7 @@ long long* gemm_dbg_buffer(int bn, bool amn, bool bmn, const TcParams& p) {
     static char last[128] = {0};
     if (!init) {
         init = true;
-        if (getenv("VSW_GEMM_DEBUG")) { cudaMalloc(&dbg, 1024); cudaMemset(dbg, 0, 1024); }
+        if (VSW_GEMM_PROF && getenv("VSW_GEMM_DEBUG")) { cudaMalloc(&dbg, 1024); cudaMemset(dbg, 0, 1024); }
     }
     if (!dbg) return nullptr;
     long long h[128];
@@ -684,18 +684,15 @@ bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 
 // N-tile: 256 halves the A-operand re-reads from L2 (the main loop is L2-bandwidth bound at 128x128), as long as
 // the tile count still fills the GPU
 static int pick_bn(int M, int N) {
-    if (getenv("VSW_GEMM_BN128")) return 128;
     if (N % 256 != 0) return 128;
     const long long tiles256 = (long long)ceil_div(M, BM) * (N / 256);
     return tiles256 >= kNumSMs ? 256 : 128;
 }
 
 // CTA-pair tiles when the 256-wide tile is in use, the reduction is long enough for the main loop to matter and there
-// are enough 256 x 256 tiles for the 74 pairs  (VSW_GEMM_PAIR=0 / 1 forces it off / on for experiments)
+// are enough 256 x 256 tiles for the 74 pairs
 static bool use_pair(int M, int N, int K, int BN) {
     if (BN != 256) return false;
-    static const char* env = getenv("VSW_GEMM_PAIR");
-    if (env) return env[0] == '1';
     return K >= 256 && (long long)ceil_div(M, 2 * BM) * (N / 256) >= kNumSMs / 2;
 }
 
@@ -766,7 +763,7 @@ int tc_dgrad(const TcDgradArgs& a, cudaStream_t st) {
 // ---------------------------------------------------------------------------------------------
 // wgrad: dw (N x K) = dy (M x N)^T x (M x K)
 // ---------------------------------------------------------------------------------------------
-static int wgrad_bn(int K) { return (K % 256 == 0 && !getenv("VSW_GEMM_BN128")) ? 256 : 128; }
+static int wgrad_bn(int K) { return K % 256 == 0 ? 256 : 128; }
 static void tc_wgrad_split(int M, int N, int K, int* splits, int* m_per_split) {
     // work items = output tiles x splits of the reduction over the M rows.  Pick the split count (each split >= 512
     // rows, at most ~4 items per SM) that wastes the fewest SM-slots in the last wave of the persistent grid.
@@ -791,10 +788,6 @@ static void tc_wgrad_split(int M, int N, int K, int* splits, int* m_per_split) {
         if (tiles * s < 2LL * kNumSMs - kNumSMs / 8 && s < smax) continue;   // fewer than ~2 waves
         best = s;
         break;
-    }
-    if (getenv("VSW_WGRAD_MAXSPLIT")) {   // experiment: previous heuristic (largest split count among the best)
-        best = 1; double be = -1.0;
-        for (long long s = 1; s <= smax; ++s) { const double e = eff(s) + 1e-3 * (double)s / (double)smax; if (e > be) { be = e; best = s; } }
     }
     int mps = (int)((M + best - 1) / best);
     mps = (mps + BK - 1) / BK * BK;
