@@ -124,6 +124,11 @@ int vsw_ln_bwd(const void* dy, const void* x, const void* gamma, const float* me
                int B, int Tin, int Tout, int C, int dtype, int dy_dtype, void* ws, size_t ws_bytes,
                void* stream);
 
+/* Stochastic-depth factors of DropPath (video_swin.py:46-54): out[b] = floor(keep + u[b]) / keep (fp32), where u holds the
+ * n uniform samples the caller drew (torch.rand in the activation dtype, so the random stream matches the reference) and the
+ * sum is rounded to that dtype before the floor, as the reference's `keep_prob + torch.rand(...)` is. */
+int vsw_drop_path_scale(const void* u, float keep, float* out, int n, int dtype, void* stream);
+
 /* Residual add with window-reverse scatter, for a residual stream kept wider than the branch (torch.autocast keeps
  * `shortcut + drop_path(x)` in fp32 while the Linear outputs are 16-bit, video_swin.py:256, 261):
  *   out[b, map[r], :] = x[b, map[r], :] + rowscale[b] * y[b, r, :]     (rows with map[r] < 0 skipped; map NULL = identity)

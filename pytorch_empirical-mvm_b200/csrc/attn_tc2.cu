@@ -68,7 +68,7 @@ constexpr int FWD_SMEM = OFF_BARS + 256 + 1024;          // + alignment slack
 struct FwdParams {
     const uint16_t* tabg; const float* tabstat; const int* poison; const uint8_t* region;
     void* out; float* lse;
-    int B_, nW, N, nH, wh, ww, KR, nq, nkb, tab_bytes, NHt;   // NHt = 2 wh - 1 (table rows per depth offset)
+    int B_, nW, N, nH, wh, ww, KR, nq, nkb, tab_bytes, NHt, blk;   // NHt = 2 wh - 1 (table rows per depth offset); blk = rows per w_i block
     int wdc;                                                  // configured window depth
     float scale_log2;
     int force_exact;
@@ -302,7 +302,7 @@ attn2_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
     for (int n = threadIdx.x; n < MAXNQ * QT; n += FWD_THREADS) {   // the divisions are done once, not once per tile
         const int ic = min(n, p.N - 1);
         const int wi = ic % p.ww, hi = (ic / p.ww) % p.wh, di = ic / (p.ww * p.wh);
-        reinterpret_cast<uint32_t*>(base + OFF_AROW)[n] = ((wi * (2 * p.wdc - 1) + di + p.wdc - 1) * p.NHt + hi + p.wh - 1) * 16;
+        reinterpret_cast<uint32_t*>(base + OFF_AROW)[n] = (wi * p.blk + (di + p.wdc - 1) * p.NHt + hi + p.wh - 1) * 16;
     }
     tc::tc_fence_before();
     __syncthreads();
@@ -754,7 +754,7 @@ uint8_t* scratch_for(cudaStream_t st, size_t bytes) {
     return b.p;
 }
 
-struct Geometry { int wdc, wh, ww, KR, nq, nkb, tab_bytes; };
+struct Geometry { int wdc, wh, ww, KR, nq, nkb, tab_bytes, blk; };
 // the shapes this kernel family takes: head_dim 32, window rows of ww <= 8 tokens, N a whole number of rows, N <= 448
 bool geometry_of(int N, int hd, int L, int window_dims, Geometry* g) {
     const int wh = (window_dims >> 8) & 0xFF, ww = (window_dims >> 16) & 0xFF;
@@ -768,7 +768,11 @@ bool geometry_of(int N, int hd, int L, int window_dims, Geometry* g) {
     if (KR > MAXKR || N > wdc * wh * ww) return false;
     g->wdc = wdc; g->wh = wh; g->ww = ww; g->KR = KR;
     g->nq = (N + QT - 1) / QT; g->nkb = (KR + KRB - 1) / KRB;
-    g->tab_bytes = ww * ND * NH * SLOT * 2;
+    // rows per w_i block, padded to 7 mod 8: the 16-byte bias vector of query (h, w) then starts in bank group (h - w) mod 8,
+    // and 8 consecutive queries of a 7-wide window row order hit 8 different groups (no shared-memory bank conflicts)
+    g->blk = ND * NH;
+    while (g->blk % 8 != 7) ++g->blk;
+    g->tab_bytes = ww * g->blk * SLOT * 2;
     return g->tab_bytes <= TAB_MAX_BYTES;
 }
 
@@ -805,15 +809,15 @@ int tc2_attn_fwd(const void* qkv, const void* table, const int32_t* rowcode, con
     int* poison = (int*)(scratch + tab_total + (size_t)nH * 8);
     cudaMemsetAsync(poison, 0, 4, st);
     if (dtype == VSW_BF16)
-        attn2_table_kernel<__nv_bfloat16><<<nH, 1024, 0, st>>>((const __nv_bfloat16*)table, rowcode, colcode, N, nH, L, g.wdc, g.wh, g.ww, 0, (2 * g.wdc - 1) * (2 * g.wh - 1), tabg, tabstat, poison);
+        attn2_table_kernel<__nv_bfloat16><<<nH, 1024, 0, st>>>((const __nv_bfloat16*)table, rowcode, colcode, N, nH, L, g.wdc, g.wh, g.ww, 0, g.blk, tabg, tabstat, poison);
     else
-        attn2_table_kernel<__half><<<nH, 1024, 0, st>>>((const __half*)table, rowcode, colcode, N, nH, L, g.wdc, g.wh, g.ww, 0, (2 * g.wdc - 1) * (2 * g.wh - 1), tabg, tabstat, poison);
+        attn2_table_kernel<__half><<<nH, 1024, 0, st>>>((const __half*)table, rowcode, colcode, N, nH, L, g.wdc, g.wh, g.ww, 0, g.blk, tabg, tabstat, poison);
     int rc = check_launch("attn2_table");
     if (rc) return rc;
     FwdParams p{};
     p.tabg = tabg; p.tabstat = tabstat; p.poison = poison; p.region = region; p.out = out; p.lse = lse;
     p.B_ = B_; p.nW = nW; p.N = N; p.nH = nH; p.wh = g.wh; p.ww = g.ww; p.KR = g.KR; p.nq = g.nq; p.nkb = g.nkb;
-    p.tab_bytes = g.tab_bytes; p.NHt = 2 * g.wh - 1; p.wdc = g.wdc;
+    p.tab_bytes = g.tab_bytes; p.NHt = 2 * g.wh - 1; p.wdc = g.wdc; p.blk = g.blk;
     p.scale_log2 = scale * LOG2E;
     { static const int fx = getenv("VSW_ATTN2_EXACT") ? atoi(getenv("VSW_ATTN2_EXACT")) : 0; p.force_exact = fx; }   // 1: always the two-pass softmax (tests)
     p.pair = 1;

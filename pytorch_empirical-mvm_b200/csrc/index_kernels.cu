@@ -136,3 +136,23 @@ extern "C" int vsw_residual_add(const void* x, const void* y, const int32_t* row
                                                                      rows_per_batch, dst_rows_per_batch, C))));
     return check_launch("residual_add");
 }
+
+// ---------------------------------------------------------------------------------------------
+// stochastic-depth factors (video_swin.py:46-54):  out[b] = floor(keep + u[b]) / keep, the sum rounded to the dtype of u
+// exactly as `keep_prob + torch.rand(shape, dtype=x.dtype)` rounds it.  One launch instead of add / floor / cast / div.
+// ---------------------------------------------------------------------------------------------
+namespace vsw {
+template <typename T>
+__global__ void drop_path_scale_kernel(const T* __restrict__ u, float keep, float* __restrict__ out, int n) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) out[i] = floorf(to_f<T>(from_f<T>(to_f<T>(u[i]) + keep))) / keep;
+}
+}  // namespace vsw
+
+extern "C" int vsw_drop_path_scale(const void* u, float keep, float* out, int n, int dtype, void* stream) {
+    using namespace vsw;
+    VSW_REQUIRE(u && out && n > 0 && keep > 0.f, VSW_ERR_ARG, "vsw_drop_path_scale: bad args");
+    cudaStream_t st = (cudaStream_t)stream;
+    VSW_DISPATCH_DTYPE(dtype, T, (drop_path_scale_kernel<T><<<(n + 127) / 128, 128, 0, st>>>((const T*)u, keep, out, n)));
+    return check_launch("drop_path_scale");
+}

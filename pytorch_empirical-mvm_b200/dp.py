@@ -170,7 +170,14 @@ class FlatGradReducer:
 
     ALIGN = 64   # elements: every slot starts 128-byte aligned for 16-bit types (the kernels need 16 bytes)
 
-    def __init__(self, module: torch.nn.Module, n_chunks: int = 4, install_sink: bool = True):
+    def __init__(self, module: torch.nn.Module, n_chunks: int = 4, install_sink: bool = True, unused: str = "zero"):
+        """unused: what a parameter without a local gradient gets after finish() when the job is distributed.
+        "zero" (default): its averaged slot (zeros if no rank had a gradient) -- every rank takes the same optimizer step and
+        nothing synchronises the host; "none": stays None unless some rank had a gradient, decided through a small extra
+        all-reduce of a presence bitmap that the host must read (one device synchronisation per step, like DDP's
+        find_unused_parameters)."""
+        assert unused in ("zero", "none")
+        self.unused = unused
         self.params = [p for p in reversed(list(module.parameters())) if p.requires_grad]
         self.flat = {}          # dtype -> flat tensor
         self.slot = {}          # id(p) -> (dtype, offset, numel)
@@ -274,7 +281,7 @@ class FlatGradReducer:
         n = len(self._works)
         distributed = dist.is_initialized() and dist.get_world_size() > 1
         present = None
-        if distributed:
+        if distributed and self.unused == "none":
             # which parameters received a gradient on ANY rank (a tiny extra collective, like DDP's unused-parameter bitmap):
             # those get their averaged slot as .grad on every rank, so that all replicas take the same optimizer step
             dev = next(iter(self.flat.values())).device
@@ -285,12 +292,15 @@ class FlatGradReducer:
             if buf is not None:
                 buf.div_(dist.get_world_size())
         self._works.clear()
-        if distributed:
+        if distributed and self.unused == "none":
             pw.wait()
             for p, c in zip(self.params, present.tolist()):
                 if c and p.grad is None:
                     p.grad = self._view(p)
-        # parameters without a gradient on every rank keep p.grad = None (their slots are zero), as plain autograd leaves them
+        elif distributed:
+            for p in self.params:
+                if p.grad is None:
+                    p.grad = self._view(p)
         return n
 
     def remove(self):

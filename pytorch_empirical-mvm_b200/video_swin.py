@@ -76,8 +76,14 @@ def drop_path(x, drop_prob: float = 0., training: bool = False):
 def _drop_path_scale(x, drop_prob: float) -> torch.Tensor:
     """(B,) fp32 factors floor(keep+U)/keep, drawing the same ``torch.rand`` the reference draws."""
     keep = 1 - drop_prob
-    r = keep + torch.rand((x.shape[0],) + (1,) * (x.ndim - 1), dtype=x.dtype, device=x.device)
-    return (r.floor_().reshape(-1).float() / keep).contiguous()
+    u = torch.rand((x.shape[0],) + (1,) * (x.ndim - 1), dtype=x.dtype, device=x.device)
+    if not u.is_cuda or u.dtype not in (torch.float32, torch.bfloat16, torch.float16):
+        return ((keep + u).floor_().reshape(-1).float() / keep).contiguous()
+    out = torch.empty(x.shape[0], dtype=torch.float32, device=x.device)
+    with torch.cuda.device(x.device):
+        L.check(L.lib().vsw_drop_path_scale(L.ptr(u), float(keep), L.ptr(out), x.shape[0], L.dt(u), L.stream()),
+                "vsw_drop_path_scale")
+    return out
 
 
 class DropPath(nn.Module):

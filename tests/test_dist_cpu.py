@@ -157,7 +157,7 @@ def _worker_flat(rank, world, port, tmpdir):
         torch.manual_seed(0)
         net, ref = Net().double(), Net().double()
         ref.load_state_dict(net.state_dict())
-        red = dp.FlatGradReducer(net, n_chunks=3, install_sink=False)
+        red = dp.FlatGradReducer(net, n_chunks=3, install_sink=False, unused="none")
         assert len(red.chunks) == 3 and red.chunks[0][1] == 0 and red.chunks[-1][2] == red.flat[torch.float64].numel()
         g = torch.Generator().manual_seed(3)
         x, t = torch.randn(6, 4, generator=g).double(), torch.randn(6, 2, generator=g).double()
