@@ -16,7 +16,8 @@
 namespace vsw {
 namespace {
 
-constexpr int B_THREADS = 384;          // warps 0..7: exp (2 groups x 4 lane quadrants); 8, 9: aux; 10: TMA; 11: MMA
+constexpr int B_THREADS = 512;          // warps 0..7: exp (2 groups x 4 lane quadrants); 8, 9: aux; 10: TMA; 11: MMA; 12..15: epilogue
+constexpr int BW_EPI = 12;              // epilogue warp q = warp - 12 reads TMEM lane quadrant q (12 % 4 == 0)
 constexpr int BW_AUX0 = 8, BW_AUX1 = 9, BW_TMA = 10, BW_MMA = 11;
 constexpr int KTR = 14;                 // key rows per key tile (2 x 14 = 28 of the 32 lanes of a quadrant)
 constexpr int QHR = 8;                  // query rows per half-block (64 padded query columns)
@@ -163,7 +164,7 @@ attn2_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
             tc::mbar_init(&s.aux_full[i], 2); tc::mbar_init(&s.aux_empty[i], 8);
         }
         for (int i = 0; i < NQD; ++i) { tc::mbar_init(&s.qd_full[i], 1); tc::mbar_init(&s.qd_empty[i], 1); }
-        tc::mbar_init(s.dq_full, 1); tc::mbar_init(s.dq_empty, 8);
+        tc::mbar_init(s.dq_full, 1); tc::mbar_init(s.dq_empty, 4);
         tc::fence_barrier_init();
     }
     if (warp == BW_MMA) tc::tmem_alloc(s.tmem_slot, TMEM_COLS);
@@ -360,8 +361,91 @@ attn2_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
             __syncwarp();
             if (lane == 0) tc::mbar_arrive(&s.aux_full[st]);
         }
+    } else if (warp >= BW_EPI) {
+        // ===================== epilogue warps: dK / dV per key tile, dQ per item =====================
+        // (On the exp warps these read-outs -- waiting for the tile's last MMA, the TMEM loads, packing, the stores -- cost ~11 %
+        // of a group's cycle and drained the pipeline at every item end; here they overlap the next tile's / item's scores.)
+        const int q = warp - BW_EPI;
+        const uint32_t lane_base = (uint32_t)(q * 32) << 16;
+        const int krow = q * 32 + lane;                     // row of this thread's key in the K / V tiles
+        int kt = 0;
+        for (int it = 0; it < n_items; ++it) {
+            const int b_ = gi + it * p.groups;
+            for (int T = 0; T < p.nT; ++T, ++kt) {
+                // dK / dV of the tile: TMEM -> registers -> (scaled, packed) into the tile's own K / V shared-memory buffer, whose
+                // rows are in TMEM lane order -> tensor-map stores with the boxes the tile was loaded with (window-row padding and
+                // rows beyond the window are clipped by the map; per-lane 16-byte global stores of 64-byte rows would cost 32 LSU
+                // wavefronts per instruction on the pipe the exp warps are bound by)
+                const int par = kt & 1;
+                wait2(&s.dkv_full[par], (kt >> 1) & 1, 9);
+                tc::tc_fence_after();
+                uint32_t dk[32], dv[32];
+                tc::tmem_ld_32x32(tmem + lane_base + TB_DKV + 64 * par, dk);
+                tc::tmem_ld_32x32(tmem + lane_base + TB_DKV + 64 * par + 32, dv);
+                tc::tmem_ld_wait();
+                tc::tc_fence_before();
+                __syncwarp();
+                if (lane == 0) tc::mbar_arrive(&s.dkv_empty[par]);
+                const uint32_t kva = base_a + BO_KV + par * 16384 + krow * 64;
+                if (lane < 2 * KTR) {                      // rows 28..31 of a quadrant stay zero (no box ever covers them)
+#pragma unroll
+                    for (int v4 = 0; v4 < 4; ++v4) {
+                        uint4 u, w;
+                        u.x = pack16<F16>(__uint_as_float(dk[8 * v4 + 0]) * p.scale, __uint_as_float(dk[8 * v4 + 1]) * p.scale);
+                        u.y = pack16<F16>(__uint_as_float(dk[8 * v4 + 2]) * p.scale, __uint_as_float(dk[8 * v4 + 3]) * p.scale);
+                        u.z = pack16<F16>(__uint_as_float(dk[8 * v4 + 4]) * p.scale, __uint_as_float(dk[8 * v4 + 5]) * p.scale);
+                        u.w = pack16<F16>(__uint_as_float(dk[8 * v4 + 6]) * p.scale, __uint_as_float(dk[8 * v4 + 7]) * p.scale);
+                        w.x = pack16<F16>(__uint_as_float(dv[8 * v4 + 0]), __uint_as_float(dv[8 * v4 + 1]));
+                        w.y = pack16<F16>(__uint_as_float(dv[8 * v4 + 2]), __uint_as_float(dv[8 * v4 + 3]));
+                        w.z = pack16<F16>(__uint_as_float(dv[8 * v4 + 4]), __uint_as_float(dv[8 * v4 + 5]));
+                        w.w = pack16<F16>(__uint_as_float(dv[8 * v4 + 6]), __uint_as_float(dv[8 * v4 + 7]));
+                        const uint32_t off = (uint32_t)((v4 ^ ((krow >> 1) & 3)) << 4);     // 64-byte swizzle of the tile
+                        tc::sts_u4(kva + off, u);
+                        tc::sts_u4(kva + 8192 + off, w);
+                    }
+                }
+                tc::fence_proxy_async();
+                tc::named_bar_sync(1, 128);                // the four epilogue warps
+                if (q == 0 && lane == 0) {
+                    const uint8_t* kv = base + BO_KV + par * 16384;
+#pragma unroll
+                    for (int which = 0; which < 2; ++which)
+#pragma unroll
+                        for (int qq = 0; qq < 4; ++qq)
+                            tc::tma_store_4d(&tmDKV, kv + which * 8192 + qq * 2048, (1 + which) * C + h * HD, 2 * qq, T * KTR, b_);
+                    tc::bulk_commit_group();
+                    tc::bulk_wait_read_all();              // the stores have read the buffer: it goes back to the loader
+                    tc::mbar_arrive(&s.kv_empty[par]);
+                }
+            }
+            // ---- dQ of the item: all of its MMAs have retired
+            wait2(s.dq_full, it & 1, 13);
+            tc::tc_fence_after();
+            for (int qb = 0; qb < (p.nhb + 1) / 2; ++qb) {
+                uint32_t o[32];
+                tc::tmem_ld_32x32(tmem + lane_base + TB_DQ + 32 * qb, o);
+                tc::tmem_ld_wait();
+                const int col = qb * 128 + q * 32 + lane, row = col >> 3, sl = col & 7;
+                if (sl < p.ww && row < p.KR) {
+                    uint4* dst = reinterpret_cast<uint4*>((uint16_t*)p.dqkv + (((long long)b_ * p.N + row * p.ww + sl) * 3) * C + h * HD);
+#pragma unroll
+                    for (int v4 = 0; v4 < 4; ++v4) {
+                        uint4 u;
+                        u.x = pack16<F16>(__uint_as_float(o[8 * v4 + 0]) * p.scale, __uint_as_float(o[8 * v4 + 1]) * p.scale);
+                        u.y = pack16<F16>(__uint_as_float(o[8 * v4 + 2]) * p.scale, __uint_as_float(o[8 * v4 + 3]) * p.scale);
+                        u.z = pack16<F16>(__uint_as_float(o[8 * v4 + 4]) * p.scale, __uint_as_float(o[8 * v4 + 5]) * p.scale);
+                        u.w = pack16<F16>(__uint_as_float(o[8 * v4 + 6]) * p.scale, __uint_as_float(o[8 * v4 + 7]) * p.scale);
+                        dst[v4] = u;
+                    }
+                }
+            }
+            tc::tc_fence_before();
+            __syncwarp();
+            if (lane == 0) tc::mbar_arrive(s.dq_empty);
+        }
+        if (q == 0 && lane == 0) tc::bulk_wait_all();      // this thread's dK / dV tile stores
     } else {
-        // ===================== exp / dS / epilogue warps: thread = key =====================
+        // ===================== exp / dS warps: thread = key =====================
         const int q = warp & 3, g = warp >> 2;
         const uint32_t lane_base = (uint32_t)(q * 32) << 16;
         const int wj = 2 * q + (lane & 1);                 // this thread's key column w_j (7 = dummy for a 7-wide window)
@@ -377,64 +461,6 @@ attn2_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
         const long long x_t0 = xprof ? clock64() : 0;
         int use_ds0 = 0, use_ds1 = 0;                        // uses so far of the even / odd dS chunk (all half-blocks, owned or not; scalars: a
                                                              // dynamically indexed array would live in local memory, ~700 cycles per access here)
-        int pendT = -1, pend_b = 0, pend_kt = 0;            // deferred dK / dV epilogue
-        // dK / dV of a finished key tile: TMEM -> registers -> (scaled, packed) into the tile's own K / V shared-memory buffer, whose
-        // rows are in TMEM lane order -> tensor-map stores with the boxes the tile was loaded with (window-row padding and rows
-        // beyond the window are clipped by the map).  Per-lane 16-byte global stores of 64-byte rows cost 32 LSU wavefronts per
-        // instruction -- 10 k cycles per item on the pipe the exp warps are bound by.  The K / V buffer goes back to the loader
-        // only after the stores have read it (kv_release, called after the group's next half-block).
-        int kv_pending = -1;
-        auto kv_release = [&]() {
-            if (kv_pending >= 0) {
-                if (q == 0 && lane == 0) { tc::bulk_wait_read_all(); tc::mbar_arrive(&s.kv_empty[kv_pending]); }
-                kv_pending = -1;
-            }
-        };
-        auto dkv_epilogue = [&](int T_, int eb, int ekt) {
-            const int par = ekt & 1;
-            const long long x_e0 = xprof ? clock64() : 0;
-            kv_release();
-            wait2(&s.dkv_full[par], (ekt >> 1) & 1, 9);
-            tc::tc_fence_after();
-            uint32_t dk[32], dv[32];
-            tc::tmem_ld_32x32(tmem + lane_base + TB_DKV + 64 * par, dk);
-            tc::tmem_ld_32x32(tmem + lane_base + TB_DKV + 64 * par + 32, dv);
-            tc::tmem_ld_wait();
-            tc::tc_fence_before();
-            __syncwarp();
-            if (lane == 0) tc::mbar_arrive(&s.dkv_empty[par]);
-            const uint32_t kva = base_a + BO_KV + par * 16384 + krow * 64;
-            if (lane < 2 * KTR) {                      // rows 28..31 of a quadrant stay zero (no box ever covers them)
-#pragma unroll
-                for (int v4 = 0; v4 < 4; ++v4) {
-                    uint4 u, w;
-                    u.x = pack16<F16>(__uint_as_float(dk[8 * v4 + 0]) * p.scale, __uint_as_float(dk[8 * v4 + 1]) * p.scale);
-                    u.y = pack16<F16>(__uint_as_float(dk[8 * v4 + 2]) * p.scale, __uint_as_float(dk[8 * v4 + 3]) * p.scale);
-                    u.z = pack16<F16>(__uint_as_float(dk[8 * v4 + 4]) * p.scale, __uint_as_float(dk[8 * v4 + 5]) * p.scale);
-                    u.w = pack16<F16>(__uint_as_float(dk[8 * v4 + 6]) * p.scale, __uint_as_float(dk[8 * v4 + 7]) * p.scale);
-                    w.x = pack16<F16>(__uint_as_float(dv[8 * v4 + 0]), __uint_as_float(dv[8 * v4 + 1]));
-                    w.y = pack16<F16>(__uint_as_float(dv[8 * v4 + 2]), __uint_as_float(dv[8 * v4 + 3]));
-                    w.z = pack16<F16>(__uint_as_float(dv[8 * v4 + 4]), __uint_as_float(dv[8 * v4 + 5]));
-                    w.w = pack16<F16>(__uint_as_float(dv[8 * v4 + 6]), __uint_as_float(dv[8 * v4 + 7]));
-                    const uint32_t off = (uint32_t)((v4 ^ ((krow >> 1) & 3)) << 4);     // 64-byte swizzle of the tile
-                    tc::sts_u4(kva + off, u);
-                    tc::sts_u4(kva + 8192 + off, w);
-                }
-            }
-            tc::fence_proxy_async();
-            tc::named_bar_sync(1 + g, 128);            // the four warps of this group
-            if (q == 0 && lane == 0) {
-                const uint8_t* kv = base + BO_KV + par * 16384;
-#pragma unroll
-                for (int which = 0; which < 2; ++which)
-#pragma unroll
-                    for (int qq = 0; qq < 4; ++qq)
-                        tc::tma_store_4d(&tmDKV, kv + which * 8192 + qq * 2048, (1 + which) * C + h * HD, 2 * qq, T_ * KTR, eb);
-                tc::bulk_commit_group();
-            }
-            kv_pending = par;
-            if (xprof) { x_epi += clock64() - x_e0; x_nepi += 1; }
-        };
         // (the integer divisions are ~1000 cycles of dependent instructions: once per kernel for the first four key tiles)
         auto rowbase_of = [&](int T) {
             const int dj = (T * KTR + rl) / p.wh, hj = (T * KTR + rl) % p.wh;
@@ -461,8 +487,6 @@ attn2_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
                     if ((c & 1) != g) continue;
                     const int st = c & 1;
                     if (xprof && x_last && hb >= 2) x_g3 += clock64() - x_last;
-                    // the deferred dK / dV epilogue of the previous key tile (this group's turn): its MMAs retired long ago
-                    if (pendT >= 0 && hb >= 2) { dkv_epilogue(pendT, pend_b, pend_kt); pendT = -1; }
                     long long x_a = 0, x_b = 0, x_c = 0;
                     if (xprof) {
                         x_a = clock64();
@@ -534,45 +558,13 @@ attn2_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
                     tc::tc_fence_before();
                     __syncwarp();
                     if (lane == 0) tc::mbar_arrive(&s.p_full[st]);
-                    kv_release();
                     if (xprof) { x_last = clock64(); x_ws += x_b - x_a; x_wd += x_c - x_b; x_work += x_last - x_c; x_n += 1; }
                 }
-                // this tile's dK / dV: read out by group T & 1, deferred into its work on the next tile
-                if ((kt & 1) == g) {
-                    if (pendT >= 0) dkv_epilogue(pendT, pend_b, pend_kt);
-                    pendT = T; pend_b = b_; pend_kt = kt;
-                }
             }
-            // ---- end of the item: flush the pending dK / dV epilogue, then dQ (group g: query blocks g, g + 2)
-            if (pendT >= 0) { dkv_epilogue(pendT, pend_b, pend_kt); pendT = -1; }
-            const long long x_q0 = xprof ? clock64() : 0;
-            wait2(s.dq_full, it & 1, 13);
-            tc::tc_fence_after();
-            for (int qb = g; qb < (p.nhb + 1) / 2; qb += 2) {
-                uint32_t o[32];
-                tc::tmem_ld_32x32(tmem + lane_base + TB_DQ + 32 * qb, o);
-                tc::tmem_ld_wait();
-                const int col = qb * 128 + q * 32 + lane, row = col >> 3, sl = col & 7;
-                if (sl < p.ww && row < p.KR) {
-                    uint4* dst = reinterpret_cast<uint4*>((uint16_t*)p.dqkv + (((long long)b_ * p.N + row * p.ww + sl) * 3) * C + h * HD);
-#pragma unroll
-                    for (int v4 = 0; v4 < 4; ++v4) {
-                        uint4 u;
-                        u.x = pack16<F16>(__uint_as_float(o[8 * v4 + 0]) * p.scale, __uint_as_float(o[8 * v4 + 1]) * p.scale);
-                        u.y = pack16<F16>(__uint_as_float(o[8 * v4 + 2]) * p.scale, __uint_as_float(o[8 * v4 + 3]) * p.scale);
-                        u.z = pack16<F16>(__uint_as_float(o[8 * v4 + 4]) * p.scale, __uint_as_float(o[8 * v4 + 5]) * p.scale);
-                        u.w = pack16<F16>(__uint_as_float(o[8 * v4 + 6]) * p.scale, __uint_as_float(o[8 * v4 + 7]) * p.scale);
-                        dst[v4] = u;
-                    }
-                }
-            }
-            tc::tc_fence_before();
+            // the item's side data (lse / delta, region ids) may be replaced
             __syncwarp();
-            if (lane == 0) { tc::mbar_arrive(s.dq_empty); tc::mbar_arrive(&s.aux_empty[ast]); }
-            kv_release();
-            if (xprof) x_dq += clock64() - x_q0;
+            if (lane == 0) tc::mbar_arrive(&s.aux_empty[ast]);
         }
-        if (q == 0 && lane == 0) tc::bulk_wait_all();      // this thread's dK / dV tile stores
         if (xprof) { p.dbg[0] += x_ws; p.dbg[1] += x_work; p.dbg[2] += x_n; p.dbg[3] += x_wd; p.dbg[6] += clock64() - x_t0; p.dbg[4] += x_nepi; p.dbg[5] += x_epi; p.dbg[7] += x_dq; p.dbg[14] += x_aux; p.dbg[15] += x_g0; p.dbg[17] += x_g1; p.dbg[18] += x_g2; p.dbg[19] += x_g3; }
     }
 
