@@ -640,11 +640,12 @@ int tc2_attn_bwd(const void* qkv, const void* out, const void* dout, const float
         const uint64_t dims[4] = {(uint64_t)3 * C, (uint64_t)g.ww, (uint64_t)g.KR, (uint64_t)B_};
         const uint64_t strides[4] = {1, (uint64_t)3 * C, (uint64_t)g.ww * 3 * C, (uint64_t)N * 3 * C};
         const uint32_t boxq[4] = {HD, SLOT, QHR, 1}, boxk[4] = {HD, 2, KTR, 1};
-        if (!make_tmap_nd_bf16(&tmQ, qkv, 4, dims, strides, boxq, 64) || !make_tmap_nd_bf16(&tmKV, qkv, 4, dims, strides, boxk, 64) ||
+        constexpr int promo = 64;   // see make_qkv_maps: 64-byte head slices, no over-fetch
+        if (!make_tmap_nd_bf16(&tmQ, qkv, 4, dims, strides, boxq, 64, promo) || !make_tmap_nd_bf16(&tmKV, qkv, 4, dims, strides, boxk, 64, promo) ||
             !make_tmap_nd_bf16(&tmDKV, dqkv, 4, dims, strides, boxk, 64)) return VSW_ERR_CUDA;
         const uint64_t dimo[4] = {(uint64_t)C, (uint64_t)g.ww, (uint64_t)g.KR, (uint64_t)B_};
         const uint64_t strido[4] = {1, (uint64_t)C, (uint64_t)g.ww * C, (uint64_t)N * C};
-        if (!make_tmap_nd_bf16(&tmDO, dout, 4, dimo, strido, boxq, 64)) return VSW_ERR_CUDA;
+        if (!make_tmap_nd_bf16(&tmDO, dout, 4, dimo, strido, boxq, 64, promo)) return VSW_ERR_CUDA;
     }
     const int blk = bwd2_blk(g), tabb = bwd2_tab_bytes(g);
     const size_t tab_total = (size_t)nH * tabb;

@@ -58,9 +58,14 @@ bool make_tmap_2d_bf16(CUtensorMap* out, const void* base, uint64_t rows, uint64
     return true;
 }
 
+static CUtensorMapL2promotion promo_of(int bytes) {
+    return bytes >= 256 ? CU_TENSOR_MAP_L2_PROMOTION_L2_256B : bytes >= 128 ? CU_TENSOR_MAP_L2_PROMOTION_L2_128B
+         : bytes >= 64 ? CU_TENSOR_MAP_L2_PROMOTION_L2_64B : CU_TENSOR_MAP_L2_PROMOTION_NONE;
+}
+
 bool make_tmap_3d_bf16(CUtensorMap* out, const void* base, uint64_t batch, uint64_t rows, uint64_t cols,
                        uint64_t row_stride_elems, uint64_t batch_stride_elems, uint32_t box_rows, uint32_t box_cols,
-                       int swizzle_bytes) {
+                       int swizzle_bytes, int l2_promotion_bytes) {
     auto fn = get_encode_fn();
     if (!fn) { set_error("cuTensorMapEncodeTiled entry point not available"); return false; }
     cuuint64_t gdim[3] = {cols, rows, batch};
@@ -70,7 +75,7 @@ bool make_tmap_3d_bf16(CUtensorMap* out, const void* base, uint64_t batch, uint6
     CUresult r = fn(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(base), gdim, gstride, box, estr,
                     CU_TENSOR_MAP_INTERLEAVE_NONE,
                     swizzle_bytes == 64 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_128B,
-                    CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+                    promo_of(l2_promotion_bytes), CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) {
         set_error("cuTensorMapEncodeTiled(3d) failed (%d) batch=%llu rows=%llu cols=%llu", (int)r,
                   (unsigned long long)batch, (unsigned long long)rows, (unsigned long long)cols);
@@ -80,7 +85,7 @@ bool make_tmap_3d_bf16(CUtensorMap* out, const void* base, uint64_t batch, uint6
 }
 
 bool make_tmap_nd_bf16(CUtensorMap* out, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_elems,
-                       const uint32_t* box, int swizzle_bytes) {
+                       const uint32_t* box, int swizzle_bytes, int l2_promotion_bytes) {
     auto fn = get_encode_fn();
     if (!fn || rank < 1 || rank > 5) { set_error("cuTensorMapEncodeTiled entry point not available"); return false; }
     cuuint64_t gdim[5], gstride[4];
@@ -90,7 +95,7 @@ bool make_tmap_nd_bf16(CUtensorMap* out, const void* base, int rank, const uint6
     CUresult r = fn(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, rank, const_cast<void*>(base), gdim, gstride, bx, estr,
                     CU_TENSOR_MAP_INTERLEAVE_NONE,
                     swizzle_bytes == 64 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_128B,
-                    CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+                    promo_of(l2_promotion_bytes), CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled(rank %d) failed (%d)", rank, (int)r); return false; }
     return true;
 }

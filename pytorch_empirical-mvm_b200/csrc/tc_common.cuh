@@ -378,10 +378,12 @@ bool make_tmap_2d_bf16(CUtensorMap* out, const void* base, uint64_t rows, uint64
                        uint32_t box_rows, uint32_t box_cols);
 // generic rank-N bf16 tensor map (dims/strides innermost first, strides in ELEMENTS for dims 1..rank-1)
 bool make_tmap_nd_bf16(CUtensorMap* out, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_elems,
-                       const uint32_t* box, int swizzle_bytes);
+                       const uint32_t* box, int swizzle_bytes, int l2_promotion_bytes = 256);
 // 3-D (batch, rows, cols) bf16 tensor, box (1, box_rows, box_cols); swizzle_bytes in {64, 128}
 bool make_tmap_3d_bf16(CUtensorMap* out, const void* base, uint64_t batch, uint64_t rows, uint64_t cols,
                        uint64_t row_stride_elems, uint64_t batch_stride_elems, uint32_t box_rows, uint32_t box_cols,
-                       int swizzle_bytes);
+                       int swizzle_bytes, int l2_promotion_bytes = 256);
+// l2_promotion_bytes: how much the L2 fetches around a missing box row (0 / 64 / 128 / 256).  A head's 64-byte slice of a qkv
+// row promoted to 256 bytes drags in three other heads' slices, which other CTAs want at some other time.
 
 }  // namespace vsw
