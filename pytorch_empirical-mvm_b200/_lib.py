@@ -71,12 +71,20 @@ def _load():
         if _lib is not None:
             return _lib
         if not os.path.exists(LIB_PATH):
-            # the built .so normally travels with the tree; building needs nvcc only (no GPU)
+            # the built .so normally travels with the tree; building needs nvcc only (no GPU).  Under torchrun every rank gets
+            # here at once: an inter-process file lock lets one of them build while the others wait, then find the library.
+            import fcntl
             import importlib.util
-            spec = importlib.util.spec_from_file_location("_vsw_build", os.path.join(_HERE, "build.py"))
-            mod = importlib.util.module_from_spec(spec)
-            spec.loader.exec_module(mod)
-            mod.build()
+            with open(os.path.join(_HERE, ".build.lock"), "w") as lockf:
+                fcntl.flock(lockf, fcntl.LOCK_EX)
+                try:
+                    if not os.path.exists(LIB_PATH):
+                        spec = importlib.util.spec_from_file_location("_vsw_build", os.path.join(_HERE, "build.py"))
+                        mod = importlib.util.module_from_spec(spec)
+                        spec.loader.exec_module(mod)
+                        mod.build()
+                finally:
+                    fcntl.flock(lockf, fcntl.LOCK_UN)
         lib = C.CDLL(LIB_PATH)  # raises OSError loudly if missing / unloadable
         for name, (res, args) in SIGNATURES.items():
             fn = getattr(lib, name)  # AttributeError if the library does not export it

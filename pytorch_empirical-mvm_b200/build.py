@@ -63,11 +63,13 @@ def build(force: bool = False, verbose: bool = False) -> str:
         res = list(ex.map(lambda s: _compile(s, hd, force, verbose), _sources()))
     objs = [o for o, _ in res]
     if force or any(ch for _, ch in res) or not os.path.exists(LIB):
-        cmd = [NVCC, "-shared", "-o", LIB, *objs, "-gencode", "arch=compute_100a,code=sm_100a",
+        tmp = LIB + f".tmp{os.getpid()}"   # link beside the target, then rename: no reader ever sees a half-written library
+        cmd = [NVCC, "-shared", "-o", tmp, *objs, "-gencode", "arch=compute_100a,code=sm_100a",
                "-Xcompiler", "-fPIC"]
         r = subprocess.run(cmd, capture_output=True, text=True)
         if r.returncode != 0:
             raise RuntimeError(f"link failed:\n{r.stdout}\n{r.stderr}")
+        os.replace(tmp, LIB)
     return LIB
 
 

@@ -321,7 +321,7 @@ def _grad_to(g, like, key=0):
 class _AttnBranch(torch.autograd.Function):
     @staticmethod
     def forward(ctx, x, g1, b1, wqkv, bqkv, table, wproj, bproj, rowscale, plan: WindowPlan, rowcode, colcode,
-                dense_mask, nH, scale, cfg_window=None):
+                dense_mask, nH, scale, cfg_window=None, use_region=True):
         B, T, C = x.shape
         nW, N = plan.nW, plan.N
         hd = C // nH
@@ -332,7 +332,7 @@ class _AttnBranch(torch.autograd.Function):
         wide = x.dtype != wqkv.dtype
         xw, mean, rstd = ln_fwd(x, g1, b1, plan.gather, B, T, R, C, out_dtype=wqkv.dtype)
         qkv = linear_fwd(xw.view(B * R, C), wqkv, bqkv, B * R, 3 * C, C)
-        region = plan.region if (plan.shifted and dense_mask is None) else None
+        region = plan.region if (plan.shifted and dense_mask is None and use_region) else None
         o, lse = attn_fwd(qkv, table, rowcode, colcode, region, dense_mask, B * nW, nW, N, nH, hd, scale, window=cfg_window)
         if wide:
             y = linear_fwd(o, wproj, bproj, B * R, C, C)
@@ -343,6 +343,7 @@ class _AttnBranch(torch.autograd.Function):
         ctx.save_for_backward(x, g1, wqkv, table, wproj, rowscale, xw, mean, rstd, qkv, o, lse, rowcode, colcode,
                               dense_mask)
         ctx.plan, ctx.nH, ctx.scale, ctx.cfg_window = plan, nH, scale, cfg_window
+        ctx.use_region = use_region
         ctx.has_qkv_bias = bqkv is not None
         ctx.keys = (_key(g1), _key(b1), _key(bqkv), _key(bproj))
         return x1
@@ -367,7 +368,7 @@ class _AttnBranch(torch.autograd.Function):
         kg1, kb1, kbq, kbp = ctx.keys
         dwp, dbp = linear_wgrad(a_buf, o, M, C, C, w_key=_key(wproj), b_key=kbp)
         del a_buf
-        region = plan.region if (plan.shifted and dense_mask is None) else None
+        region = plan.region if (plan.shifted and dense_mask is None and ctx.use_region) else None
         dqkv, dtable = attn_bwd(qkv, o, dO, lse, table, rowcode, colcode, region, dense_mask, B * nW, nW, N, nH, hd, scale,
                                 planes=plan.ws[0], window=ctx.cfg_window)
         del dO
@@ -376,7 +377,7 @@ class _AttnBranch(torch.autograd.Function):
         del dqkv
         dx, dg1, db1 = ln_bwd(dxw, x, g1, mean, rstd, plan.gather, dx1, B, T, R, C)
         return (dx, _grad_to(dg1, g1, kg1), _grad_to(db1, g1, kb1), dwq, dbq, _grad_to(dtable, table, _key(table)), dwp, dbp,
-                None, None, None, None, None, None, None, None)
+                None, None, None, None, None, None, None, None, None)
 
 
 # ----------------------------------------------------------------------------------------------
@@ -746,10 +747,11 @@ class _MaskedL1(torch.autograd.Function):
 
 # public functional entry points --------------------------------------------------------------
 def attn_branch(x, g1, b1, wqkv, bqkv, table, wproj, bproj, rowscale, plan, rowcode, colcode, dense_mask, nH, scale,
-                cfg_window=None):
-    """cfg_window: the module's CONFIGURED window (whose relative_position_index produced the codes) -- a layout hint"""
+                cfg_window=None, use_region=True):
+    """cfg_window: the module's CONFIGURED window (whose relative_position_index produced the codes) -- a layout hint.
+    use_region=False: no shift mask at all (the reference's `mask_matrix=None` on a shifted block, video_swin.py:231-235)"""
     return _AttnBranch.apply(x, g1, b1, wqkv, bqkv, table, wproj, bproj, rowscale, plan, rowcode, colcode, dense_mask,
-                             nH, scale, cfg_window)
+                             nH, scale, cfg_window, use_region)
 
 
 def mlp_branch(x, g2, b2, w1, bb1, w2, bb2, rowscale):

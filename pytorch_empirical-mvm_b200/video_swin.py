@@ -264,12 +264,18 @@ class SwinTransformerBlock3D(nn.Module):
         dense = None
         if plan.shifted and isinstance(mask_matrix, torch.Tensor):
             # a caller-supplied dense mask is honoured verbatim (reference semantics, :220-227)
+            if tuple(mask_matrix.shape) != (plan.nW, plan.N, plan.N):
+                raise ValueError(f"mask_matrix has shape {tuple(mask_matrix.shape)}, this block's windows need "
+                                 f"{(plan.nW, plan.N, plan.N)}")
             dense = _cast(mask_matrix, cd).contiguous()
+        # BasicLayer passes the _RegionMask token (= the canonical shift mask, derived from region ids in the kernels); an
+        # explicit None means NO mask even on a shifted block, as in the reference (video_swin.py:231-235)
+        use_region = isinstance(mask_matrix, _RegionMask)
         rowcode, colcode = self.attn.bias_codes(plan.N)
         wq, bq, tab, wp, bp = self.attn.params(cd)
         y = VF.attn_branch(x.view(B, D * H * W, C), _cast(self.norm1.weight, x.dtype), _cast(self.norm1.bias, x.dtype), wq, bq,
                            tab, wp, bp, self._dp_scale(x), plan, rowcode, colcode, dense, self.num_heads,
-                           self.attn.scale, cfg_window=self.attn.window_size)
+                           self.attn.scale, cfg_window=self.attn.window_size, use_region=use_region)
         return y.view(B, D, H, W, C)
 
     def _part2(self, x, cd):

@@ -110,10 +110,18 @@ def test_block_module_with_dense_mask_and_drop_path(vsw, oracle):
     assert 0 < k1.count_nonzero() + k2.count_nonzero() < 2 * B
     yo = oracle.swin_block(x.cpu(), sd, "b.", nH, window, shift, (C // nH) ** -0.5, k1, k2)
     assert rel_l2(y, yo) < 1e-4
-    # region-id path (what BasicLayer uses) == dense-mask path
+    # region-id path (the token BasicLayer passes) == dense-mask path
     torch.manual_seed(123)
-    y2 = blk(x, None)
+    y2 = blk(x, vsw.video_swin._RegionMask((D, H, W), window, shift))
     assert rel_l2(y2, y) < 1e-6
+    # an explicit None is NO mask, even on a shifted block (video_swin.py:231-235): same as an all-zero dense mask
+    torch.manual_seed(123)
+    y3 = blk(x, None)
+    torch.manual_seed(123)
+    y4 = blk(x, torch.zeros_like(mask))
+    assert rel_l2(y3, y4) < 1e-6 and rel_l2(y3, y) > 1e-3
+    with pytest.raises(ValueError):
+        blk(x, mask[:, :-1])
     blk.eval()
     ye = blk(x, mask)
     assert rel_l2(ye, oracle.swin_block(x.cpu(), sd, "b.", nH, window, shift, (C // nH) ** -0.5)) < 1e-4
