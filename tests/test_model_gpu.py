@@ -2,9 +2,9 @@
 reference and against the CPU oracle on the same seeded inputs.
 
 Tolerances (north_star): fp32 rel-L2 1e-4 on activations and every gradient tensor; bf16 rel-L2 2e-2
-on activations, and on gradients 2e-2 except the handful of tensors whose bf16 noise is higher in
-the REFERENCE itself (norm1.bias of the first blocks up to 0.37) -- those are bounded by
-an explicit looser limit written below."""
+on activations; on gradients the median is held to 2e-2 and every tensor to a bound derived from the
+REFERENCE's own bf16 noise for that tensor (tests/golden/tiny_bf16_noise.json for the tiny fixtures,
+tests/golden/fullsize.pt at the benchmarked widths in test_fullsize_gpu.py)."""
 import os
 
 import pytest
@@ -76,9 +76,14 @@ def test_bf16_forward_backward(vsw, oracle, name, mode):
     (y.float() * R.cuda()).sum().backward()
     _, go = oracle.forward_backward(sd, x, cfg, R)
     errs = {k: rel_l2(p.grad, go[k]) for k, p in m.named_parameters()}
-    loose = [k for k in errs if "norm" in k or k.endswith(".bias") or "bias_table" in k or "patch_embed" in k]
-    for k, e in errs.items():
-        assert e < (0.4 if k in loose else 6e-2), (k, e)
+    # per-tensor bounds from the REFERENCE's own bf16 noise on this fixture (autocast-bf16 vs fp32 run of the unmodified module,
+    # tests/golden/make_golden_tiny_noise.py): max(4e-2, 2 x noise[k]).  (Few tokens and 32-channel LayerNorms make the tiny
+    # models much noisier than the real widths: norm1.bias reaches 0.22 in the reference itself.)
+    import json
+    with open(os.path.join(GOLD, "tiny_bf16_noise.json")) as f:
+        noise = json.load(f)[name]["grads"]
+    bad = {k: (e, max(4e-2, 2 * noise[k])) for k, e in errs.items() if not e < max(4e-2, 2 * noise[k])}
+    assert not bad, bad
     med = sorted(errs.values())[len(errs) // 2]
     assert med < 2e-2, med
     if mode == "autocast":
