@@ -129,6 +129,13 @@ int vsw_ln_bwd(const void* dy, const void* x, const void* gamma, const float* me
  * sum is rounded to that dtype before the floor, as the reference's `keep_prob + torch.rand(...)` is. */
 int vsw_drop_path_scale(const void* u, float keep, float* out, int n, int dtype, void* stream);
 
+/* vsw_ln_bwd with dgamma / dbeta written in `dparam_dtype` (the parameters' dtype) instead of fp32: the fixed-order fp32 column
+ * reduction is rounded once by the finish kernel, so no cast kernel has to follow. */
+int vsw_ln_bwd_ex(const void* dy, const void* x, const void* gamma, const float* mean, const float* rstd,
+                  const int32_t* map, const void* dres, void* dx, void* dgamma, void* dbeta,
+                  int B, int Tin, int Tout, int C, int dtype, int dy_dtype, int dparam_dtype, void* ws, size_t ws_bytes,
+                  void* stream);
+
 /* Residual add with window-reverse scatter, for a residual stream kept wider than the branch (torch.autocast keeps
  * `shortcut + drop_path(x)` in fp32 while the Linear outputs are 16-bit, video_swin.py:256, 261):
  *   out[b, map[r], :] = x[b, map[r], :] + rowscale[b] * y[b, r, :]     (rows with map[r] < 0 skipped; map NULL = identity)

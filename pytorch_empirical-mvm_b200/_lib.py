@@ -36,6 +36,7 @@ SIGNATURES = {
     "vsw_ln_fwd": (_i, [_vp] * 7 + [_i] * 4 + [_f, _i, _i, _vp]),
     "vsw_ln_bwd_workspace": (_sz, [_i]),
     "vsw_ln_bwd": (_i, [_vp] * 10 + [_i] * 6 + [_vp, _sz, _vp]),
+    "vsw_ln_bwd_ex": (_i, [_vp] * 10 + [_i] * 7 + [_vp, _sz, _vp]),
     "vsw_drop_path_scale": (_i, [_vp, _f, _vp, _i, _i, _vp]),
     "vsw_residual_add": (_i, [_vp] * 5 + [_i] * 6 + [_vp]),
     "vsw_merge_ln_fwd": (_i, [_vp] * 7 + [_i] * 4 + [_f, _i, _vp]),

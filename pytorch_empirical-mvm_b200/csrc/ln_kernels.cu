@@ -330,8 +330,8 @@ __global__ void __launch_bounds__(256) ln_colsum_kernel(const TDY* __restrict__ 
 // fixed-order combine through shared memory.  Many small blocks: the partial matrix is read by the whole chip.
 constexpr int kFinTX = 8, kFinTY = 128;
 __global__ void __launch_bounds__(kFinTX * kFinTY)
-colsum_finish_kernel(const float* __restrict__ part, int splits, int Cw, float* __restrict__ dgamma,
-                     float* __restrict__ dbeta) {
+colsum_finish_kernel(const float* __restrict__ part, int splits, int Cw, void* __restrict__ dgamma,
+                     void* __restrict__ dbeta, int gdtype) {
     __shared__ float sm[2][kFinTY][kFinTX + 1];
     const int c = blockIdx.x * kFinTX + threadIdx.x;
     float s1 = 0.f, s2 = 0.f;
@@ -346,8 +346,12 @@ colsum_finish_kernel(const float* __restrict__ part, int splits, int Cw, float* 
     if (threadIdx.y < 2 && c < Cw) {   // row 0 of the block finishes dgamma, row 1 dbeta (serial, fixed order)
         float t = 0.f;
         for (int y = 0; y < kFinTY; ++y) t += sm[threadIdx.y][y][threadIdx.x];
-        float* out = threadIdx.y == 0 ? dgamma : dbeta;
-        if (out) out[c] = t;
+        void* out = threadIdx.y == 0 ? dgamma : dbeta;   // written in the parameters' dtype: no cast kernel behind this one
+        if (out) {
+            if (gdtype == VSW_F32) reinterpret_cast<float*>(out)[c] = t;
+            else if (gdtype == VSW_BF16) reinterpret_cast<__nv_bfloat16*>(out)[c] = __float2bfloat16_rn(t);
+            else reinterpret_cast<__half*>(out)[c] = __float2half_rn(t);
+        }
     }
 }
 
@@ -409,8 +413,8 @@ static int launch_ln_fwd(const void* x, const void* gamma, const void* beta, con
 
 template <typename T, typename TDY, int GROUPS>
 static int launch_ln_bwd(const void* dy, const void* x, const void* gamma, const float* mean, const float* rstd,
-                         const int32_t* map, const void* dres, void* dx, float* dgamma, float* dbeta, int B, int Tin,
-                         int Tout, int C, void* ws, size_t ws_bytes, cudaStream_t st) {
+                         const int32_t* map, const void* dres, void* dx, void* dgamma, void* dbeta, int B, int Tin,
+                         int Tout, int C, void* ws, size_t ws_bytes, cudaStream_t st, int gdtype = VSW_F32) {
     constexpr int VN = Vec16<T>::N;
     RowCfg cfg;
     const int Cw = C * GROUPS;
@@ -452,7 +456,7 @@ static int launch_ln_bwd(const void* dy, const void* x, const void* gamma, const
         int rc = check_launch("ln_bwd");
         if (rc) return rc;
         if (fuse) {
-            colsum_finish_kernel<<<ceil_div(Cw, kFinTX), dim3(kFinTX, kFinTY), 0, st>>>((const float*)ws, grid, Cw, dgamma, dbeta);
+            colsum_finish_kernel<<<ceil_div(Cw, kFinTX), dim3(kFinTX, kFinTY), 0, st>>>((const float*)ws, grid, Cw, dgamma, dbeta, gdtype);
             return check_launch("ln_colsum_finish");
         }
     }
@@ -469,7 +473,7 @@ static int launch_ln_bwd(const void* dy, const void* x, const void* gamma, const
                                                                      (float*)ws, B, Tin, Tout, C);
         int rc = check_launch("ln_colsum");
         if (rc) return rc;
-        colsum_finish_kernel<<<ceil_div(Cw, kFinTX), dim3(kFinTX, kFinTY), 0, st>>>((const float*)ws, splits, Cw, dgamma, dbeta);
+        colsum_finish_kernel<<<ceil_div(Cw, kFinTX), dim3(kFinTX, kFinTY), 0, st>>>((const float*)ws, splits, Cw, dgamma, dbeta, gdtype);
         rc = check_launch("ln_colsum_finish");
         if (rc) return rc;
     }
@@ -504,9 +508,12 @@ extern "C" int vsw_ln_fwd(const void* x, const void* gamma, const void* beta, co
     return VSW_OK;
 }
 
-extern "C" int vsw_ln_bwd(const void* dy, const void* x, const void* gamma, const float* mean, const float* rstd,
-                          const int32_t* map, const void* dres, void* dx, float* dgamma, float* dbeta, int B, int Tin,
-                          int Tout, int C, int dtype, int dy_dtype, void* ws, size_t ws_bytes, void* stream) {
+extern "C" int vsw_ln_bwd_ex(const void* dy, const void* x, const void* gamma, const float* mean, const float* rstd,
+                             const int32_t* map, const void* dres, void* dx, void* dgamma, void* dbeta, int B, int Tin,
+                             int Tout, int C, int dtype, int dy_dtype, int dparam_dtype, void* ws, size_t ws_bytes,
+                             void* stream) {
+    VSW_REQUIRE(dparam_dtype == VSW_F32 || dparam_dtype == VSW_BF16 || dparam_dtype == VSW_F16, VSW_ERR_DTYPE,
+                "vsw_ln_bwd: bad dparam_dtype %d", dparam_dtype);
     VSW_REQUIRE(dy && x && gamma && mean && rstd && B > 0 && Tin > 0 && Tout > 0 && C > 0, VSW_ERR_ARG,
                 "vsw_ln_bwd: bad args");
     VSW_REQUIRE(map || Tin == Tout, VSW_ERR_ARG, "vsw_ln_bwd: identity map needs Tin == Tout");
@@ -514,19 +521,26 @@ extern "C" int vsw_ln_bwd(const void* dy, const void* x, const void* gamma, cons
     if (dy_dtype == dtype) {
         VSW_DISPATCH_DTYPE(dtype, T,
                            return (launch_ln_bwd<T, T, 1>(dy, x, gamma, mean, rstd, map, dres, dx, dgamma, dbeta, B, Tin,
-                                                          Tout, C, ws, ws_bytes, st)));
+                                                          Tout, C, ws, ws_bytes, st, dparam_dtype)));
     }
     if (dtype == VSW_F32) {   // fp32 x / dres / dx with a 16-bit dy (the autocast case of vsw_ln_fwd above)
         VSW_REQUIRE(dy_dtype == VSW_BF16 || dy_dtype == VSW_F16, VSW_ERR_DTYPE, "vsw_ln_bwd: bad dy_dtype %d", dy_dtype);
         if (dy_dtype == VSW_BF16)
-            return launch_ln_bwd<float, __nv_bfloat16, 1>(dy, x, gamma, mean, rstd, map, dres, dx, dgamma, dbeta, B, Tin, Tout, C, ws, ws_bytes, st);
-        return launch_ln_bwd<float, __half, 1>(dy, x, gamma, mean, rstd, map, dres, dx, dgamma, dbeta, B, Tin, Tout, C, ws, ws_bytes, st);
+            return launch_ln_bwd<float, __nv_bfloat16, 1>(dy, x, gamma, mean, rstd, map, dres, dx, dgamma, dbeta, B, Tin, Tout, C, ws, ws_bytes, st, dparam_dtype);
+        return launch_ln_bwd<float, __half, 1>(dy, x, gamma, mean, rstd, map, dres, dx, dgamma, dbeta, B, Tin, Tout, C, ws, ws_bytes, st, dparam_dtype);
     }
     VSW_REQUIRE(dy_dtype == VSW_F32, VSW_ERR_DTYPE, "vsw_ln_bwd: dy_dtype must equal dtype or be fp32");
     VSW_DISPATCH_DTYPE(dtype, T,
                        return (launch_ln_bwd<T, float, 1>(dy, x, gamma, mean, rstd, map, dres, dx, dgamma, dbeta, B, Tin,
-                                                          Tout, C, ws, ws_bytes, st)));
+                                                          Tout, C, ws, ws_bytes, st, dparam_dtype)));
     return VSW_OK;
+}
+
+extern "C" int vsw_ln_bwd(const void* dy, const void* x, const void* gamma, const float* mean, const float* rstd,
+                          const int32_t* map, const void* dres, void* dx, float* dgamma, float* dbeta, int B, int Tin,
+                          int Tout, int C, int dtype, int dy_dtype, void* ws, size_t ws_bytes, void* stream) {
+    return vsw_ln_bwd_ex(dy, x, gamma, mean, rstd, map, dres, dx, dgamma, dbeta, B, Tin, Tout, C, dtype, dy_dtype, VSW_F32, ws,
+                         ws_bytes, stream);
 }
 
 extern "C" int vsw_merge_ln_fwd(const void* x, const void* gamma, const void* beta, const int32_t* map4, void* y,

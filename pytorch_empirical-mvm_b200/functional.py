@@ -165,16 +165,24 @@ def ln_fwd(x, gamma, beta, gmap, B, Tin, Tout, C, out_dtype=None, want_stats=Tru
     return y, mean, rstd
 
 
-def ln_bwd(dy, x, gamma, mean, rstd, gmap, dres, B, Tin, Tout, C, need_dx=True, need_dparams=True):
+def ln_bwd(dy, x, gamma, mean, rstd, gmap, dres, B, Tin, Tout, C, need_dx=True, need_dparams=True, grad_dtype=None,
+           g_key=0, b_key=0):
+    """grad_dtype: dtype dgamma / dbeta are written in (default fp32); g_key / b_key: gradient-sink keys of the two parameters
+    (with a sink installed the kernel writes straight into their slots of the flat gradient buffer)"""
     dx = _empty((B, Tin, C), x.dtype, x.device) if need_dx else None
-    dg = _empty((C,), torch.float32, x.device) if need_dparams else None
-    db = _empty((C,), torch.float32, x.device) if need_dparams else None
+    gdt = grad_dtype or torch.float32
+    dg = db = None
+    if need_dparams:
+        dg = _sink_view(g_key, (C,), gdt)
+        db = _sink_view(b_key, (C,), gdt)
+        dg = dg if dg is not None else _empty((C,), gdt, x.device)
+        db = db if db is not None else _empty((C,), gdt, x.device)
     wsb = int(L.lib().vsw_ln_bwd_workspace(C)) if need_dparams else 0
     ws = _empty((max(wsb, 4),), torch.uint8, x.device) if need_dparams else None
     t0 = PROFILER.begin() if PROFILER is not None else None
-    L.check(L.lib().vsw_ln_bwd(L.ptr(dy), L.ptr(x), L.ptr(gamma), L.ptr(mean), L.ptr(rstd), L.ptr(gmap), L.ptr(dres),
-                               L.ptr(dx), L.ptr(dg), L.ptr(db), B, Tin, Tout, C, L.dt(x), L.dt(dy), L.ptr(ws), wsb,
-                               L.stream()), "vsw_ln_bwd")
+    L.check(L.lib().vsw_ln_bwd_ex(L.ptr(dy), L.ptr(x), L.ptr(gamma), L.ptr(mean), L.ptr(rstd), L.ptr(gmap), L.ptr(dres),
+                                  L.ptr(dx), L.ptr(dg), L.ptr(db), B, Tin, Tout, C, L.dt(x), L.dt(dy), L.dt(gdt), L.ptr(ws), wsb,
+                                  L.stream()), "vsw_ln_bwd")
     if t0 is not None:
         PROFILER.end("ln_bwd", t0, 0.0, B * C * (Tout * dy.element_size() + Tin * _esz(x) * (2 + (dres is not None))))
     return dx, dg, db
@@ -375,8 +383,8 @@ class _AttnBranch(torch.autograd.Function):
         dxw = linear_dgrad(dqkv, wqkv, M, 3 * C, C)
         dwq, dbq = linear_wgrad(dqkv, xw.view(M, C), M, 3 * C, C, need_bias=ctx.has_qkv_bias, w_key=_key(wqkv), b_key=kbq)
         del dqkv
-        dx, dg1, db1 = ln_bwd(dxw, x, g1, mean, rstd, plan.gather, dx1, B, T, R, C)
-        return (dx, _grad_to(dg1, g1, kg1), _grad_to(db1, g1, kb1), dwq, dbq, _grad_to(dtable, table, _key(table)), dwp, dbp,
+        dx, dg1, db1 = ln_bwd(dxw, x, g1, mean, rstd, plan.gather, dx1, B, T, R, C, grad_dtype=g1.dtype, g_key=kg1, b_key=kb1)
+        return (dx, dg1, db1, dwq, dbq, _grad_to(dtable, table, _key(table)), dwp, dbp,
                 None, None, None, None, None, None, None, None, None)
 
 
@@ -424,8 +432,8 @@ class _MlpBranch(torch.autograd.Function):
         dn2 = linear_dgrad(du, w1, M, Hd, C)
         dw1, db1 = linear_wgrad(du, n2.view(M, C), M, Hd, C, w_key=_key(w1), b_key=kbb1)
         del du
-        dx, dg2, dbeta2 = ln_bwd(dn2, x, g2, mean, rstd, None, dout, B, T, T, C)
-        return dx, _grad_to(dg2, g2, kg2), _grad_to(dbeta2, g2, kb2), dw1, db1, dw2, db2, None
+        dx, dg2, dbeta2 = ln_bwd(dn2, x, g2, mean, rstd, None, dout, B, T, T, C, grad_dtype=g2.dtype, g_key=kg2, b_key=kb2)
+        return dx, dg2, dbeta2, dw1, db1, dw2, db2, None
 
 
 # ----------------------------------------------------------------------------------------------
