@@ -18,7 +18,7 @@
  *   - re-entrant, callable from any host thread (autograd engine thread included);
  *   - deterministic: no floating-point atomics, fixed reduction orders.
  *   - "dtype" is the storage type of activations/weights (vsw_dtype); arithmetic is always fp32
- *     (or bf16 x bf16 -> fp32 on the tensor cores for VSW_BF16 GEMM/attention tiles);
+ *     (or 16-bit x 16-bit -> fp32 on the tensor cores for VSW_BF16 and VSW_F16 GEMM / attention tiles);
  *     statistics (mean/rstd/lse) and index maps are fp32 / int32 / uint8 regardless of dtype.
  *
  * Token layout: channels-last.  An activation is (B, T, C) with T = D*H*W tokens in row-major
@@ -221,7 +221,11 @@ int vsw_window_attn_fwd(const void* qkv, const void* bias_table, const int32_t* 
  * window_dims (both directions) = wd_eff | wh << 8 | ww << 16, any field 0 if unknown -- layout hints only, validated
  * against the codes inside the kernels:  wd_eff = depth of the EFFECTIVE window (N = wd_eff * tokens per plane; lets the
  * backward order keys plane-minor);  wh, ww = height / width of the CONFIGURED window whose relative_position_index
- * produced rowcode/colcode (lets the kernels pad the on-chip bias table against shared-memory bank conflicts). */
+ * produced rowcode/colcode.  With wh and ww given (ww <= 8, N <= 448, head_dim 32) the second-generation tcgen05 kernels
+ * run for VSW_BF16 and VSW_F16: they keep a per-head table T[w_i][d_i-d_j][h_i-h_j][8 key slots] on chip, so the bias of 8
+ * consecutive keys is one 16-byte load; without the hint the first-generation bf16 kernels or the CUDA-core kernels run.
+ * Same results either way (the kernels check the hint against rowcode / colcode; a wrong hint yields NaN, never a wrong
+ * finite result). */
 size_t vsw_window_attn_bwd_workspace(int B_, int N, int nH, int hd, int L);
 int vsw_window_attn_bwd(const void* qkv, const void* out, const void* dout, const float* lse,
                         const void* bias_table, const int32_t* rowcode, const int32_t* colcode,
