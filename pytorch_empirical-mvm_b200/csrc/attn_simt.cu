@@ -205,6 +205,7 @@ __global__ void __launch_bounds__(NWARPS * 32) attn_rows_kernel(AttnArgs a) {
                         }
                         sc[t] = ds;
                     }
+                    __syncwarp();   // the next query row of this warp may hit the same histogram slots from other lanes
                     const int tmax = (kc + 31) / 32;
                     for (int t = 0; t < tmax; ++t)
 #pragma unroll
