@@ -401,6 +401,17 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             const int split = w / tiles, t = w - split * tiles;
             const int m0 = (t / p.n_tiles_n) * TILE_M + (int)cta_rank * BM, n0 = (t % p.n_tiles_n) * BN;
             long long e_a = GCLK(), dbg_ld = 0, dbg_math = 0, dbg_st = 0;
+            // the bias of this warp's first chunk is fetched BEFORE the wait for the accumulator (an L2 round trip of ~400
+            // cycles otherwise sits in front of every chunk's arithmetic); later chunks fetch theirs behind the TMEM load
+            uint4 bq[4];
+            auto fetch_bias = [&](int c) {
+#pragma unroll
+                for (int g = 0; g < 4; ++g) {
+                    const int col = n0 + c * 32 + g * 8;
+                    bq[g] = (p.bias && col < p.N) ? __ldg(reinterpret_cast<const uint4*>(p.bias + col)) : make_uint4(0, 0, 0, 0);
+                }
+            };
+            if (EPI != TE_PARTIAL) fetch_bias(half);
             tc::mbar_wait(&tfull[acc], acc_phase);
             tc::tc_fence_after();
             long long e_b = GCLK();
@@ -428,6 +439,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 long long c_a = GCLK();
                 tc::tmem_ld_32x32(tmem_base + acc * BN + c * 32 + ((uint32_t)(q * 32) << 16), r32);
                 const int col0 = n0 + c * 32;
+                if (EPI != TE_PARTIAL && c != half) fetch_bias(c);
                 // Side tensor of the epilogue (residual / GELU' / pre-activation), same (row, column) footprint as the output:
                 // loaded COALESCED (4 lanes per 64-byte row segment, rows via the owning lanes' registers) into the warp's
                 // staging buffer while the TMEM load is in flight, then re-read in the thread-per-row layout.
@@ -482,7 +494,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                     if (col < p.N) {
                         if (p.bias) {
                             float bb[8];
-                            ld8<F16>(p.bias + col, bb);
+                            unpack8<F16>(bq[g], bb);
 #pragma unroll
                             for (int e = 0; e < 8; ++e) v[e] += bb[e];
                         }
