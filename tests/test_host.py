@@ -195,3 +195,25 @@ def test_block_sampler_edge_cases(vsw):
     g = vsw.mvm.sample_block_masks(2, 8, 7, 7)
     assert np.array_equal(g, vsw.mvm.sample_block_masks(2, 8, 7, 7, rng=np.random.RandomState(5)))
     assert g.max() == 1 and g.dtype == np.uint8
+
+
+def test_bench_reference_arm_contract():
+    """`bench.py --impl reference` (the driver's reference arm): one JSON line on stdout with the contract's keys; in the build
+    container it times the unmodified reference (kind "reference"), elsewhere the oracle port (kind "port")."""
+    import json
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, os.path.join(root, "bench.py"), "--impl", "reference", "--model", "violet", "--steps", "1",
+                        "--warmup", "1", "--cpu-batch", "1"], capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stderr[-2000:]
+    lines = [l for l in r.stdout.splitlines() if l.strip()]
+    assert len(lines) == 1
+    d = json.loads(lines[0])
+    for k in ("impl", "metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling",
+              "vs_baseline", "dtype", "data", "config", "cpu_baseline", "e2e"):
+        assert k in d, k
+    assert d["impl"] == "reference" and d["value"] > 0 and d["unit"] == "clips/s"
+    assert d["cpu_baseline"]["kind"] == ("reference" if os.path.isdir("/root/reference/visbackbone") else "port")
+    assert d["cpu_baseline"]["value"] == d["value"] and d["e2e"]["h2d_bytes_per_step"] == 0
+    assert "workload" in d["config"] and "model" not in d["config"]
