@@ -120,7 +120,10 @@ constexpr int A_BYTES = BM * BK * 2;  // 16 KB
 constexpr int NUM_EPI_WARPS = 16;   // 4 per TMEM lane quadrant: the fused epilogues are latency/MUFU bound, not issue bound
 constexpr int NUM_THREADS = 64 + NUM_EPI_WARPS * 32;
 
-enum TcEpi { TE_BIAS = 0, TE_GELU = 1, TE_RESIDUAL = 2, TE_DGRAD = 3, TE_PARTIAL = 4, TE_DGRAD_GELU = 5, TE_GELU_GRAD = 6, TE_DGRAD_MUL = 7 };
+// TE_RESIDUAL_ID: the residual epilogue whose output rows ARE the tile's rows (fc2: no window-reverse row map), so that both the
+// residual tile and the output can go through the tensor maps
+enum TcEpi { TE_BIAS = 0, TE_GELU = 1, TE_RESIDUAL = 2, TE_DGRAD = 3, TE_PARTIAL = 4, TE_DGRAD_GELU = 5, TE_GELU_GRAD = 6, TE_DGRAD_MUL = 7,
+             TE_RESIDUAL_ID = 8 };
 
 struct TcParams {
     int M, N, K;                 // output M x N, reduction length K
@@ -218,7 +221,11 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     // the fp32 split-K partials keep their own paths
     // (epilogues with a side tensor use the staging buffer twice per chunk -- the wait for the bulk store's read in between made
     // them 8 % slower, measured -- and keep the per-lane stores too)
-    constexpr bool TMA_OUT = (EPI == TE_BIAS || EPI == TE_GELU || EPI == TE_GELU_GRAD || EPI == TE_DGRAD);
+    // SIDE2 (dgrad x GELU' forms, residual with identity rows): the side tensor tile of a chunk arrives by a tensor-map LOAD into a second per-warp buffer (one
+    // TMA stage fewer), issued one chunk ahead -- instead of 4 x (2 SHFL + LDG + STS) per lane on the chunk's critical path --
+    // and the output leaves by a tensor-map store like the side-less epilogues
+    constexpr bool SIDE2 = (EPI == TE_DGRAD_MUL || EPI == TE_DGRAD_GELU || EPI == TE_RESIDUAL_ID);
+    constexpr bool TMA_OUT = (EPI == TE_BIAS || EPI == TE_GELU || EPI == TE_GELU_GRAD || EPI == TE_DGRAD || SIDE2);
     constexpr int CS_WARPS = COLSUM ? 4 : 0;
     constexpr int EPI_WARPS = NUM_EPI_WARPS - CS_WARPS;
     constexpr int BNL = PAIR ? BN / 2 : BN;           // B rows this CTA loads
@@ -240,6 +247,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
     constexpr uint32_t STG_BYTES = 32 * 64;   // per-epilogue-warp transposition buffer (32 rows x 64 B, XOR-swizzled 16-B units)
     const uint32_t stage_base = tc::smem_u32(smem + STAGES * STAGE_BYTES + 256);
+    uint64_t* side_bar = reinterpret_cast<uint64_t*>(smem + STAGES * STAGE_BYTES + 256 + 2 * NUM_EPI_WARPS * STG_BYTES);   // SIDE2: one per epilogue warp
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int tiles = p.n_tiles_m * p.n_tiles_n;
@@ -250,6 +258,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         tc::prefetch_tmap(&tmB);
         for (int s = 0; s < STAGES; ++s) { tc::mbar_init(&full[s], PAIR ? 2 : 1); tc::mbar_init(&empty[s], 1 + CS_WARPS); }
         for (int a = 0; a < 2; ++a) { tc::mbar_init(&tfull[a], 1); tc::mbar_init(&tempty[a], (PAIR ? 2 : 1) * EPI_WARPS); }
+        if constexpr (SIDE2) { for (int w8 = 0; w8 < NUM_EPI_WARPS; ++w8) tc::mbar_init(&side_bar[w8], 1); }
         tc::fence_barrier_init();
     }
     if (warp == 1) { if constexpr (PAIR) tc::tmem_alloc_2cta(tmem_slot, TMEM_COLS); else tc::tmem_alloc(tmem_slot, TMEM_COLS); }
@@ -405,10 +414,24 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         const int q = warp & 3;                 // TMEM lane quadrant this warp may access
         const int half = (warp - 2) >> 2;       // which interleaved 32-column chunks it owns (0..EPI_WARPS/4-1)
         int acc = 0; uint32_t acc_phase = 0;
+        uint32_t side_phase = 0;                 // SIDE2: parity of this warp's side-tile barrier
+        const uint32_t stg_w = stage_base + (uint32_t)(warp - 2) * STG_BYTES;
+        const uint32_t sstg_w = stg_w + NUM_EPI_WARPS * STG_BYTES;      // SIDE2: the side tile's own buffer
+        uint64_t* sbar = &side_bar[warp - 2];
+        // SIDE2: tensor-map load of the 32 x 32 side tile of chunk c of tile (m0, n0) (rows >= M / columns >= N arrive as zeros)
+        auto issue_side = [&](int m0, int n0, int c) {
+            if constexpr (SIDE2) {
+                if (lane == 0) {
+                    tc::mbar_expect_tx(sbar, STG_BYTES);
+                    tc::tma_load_2d(&tmAux, sbar, smem + (sstg_w - tc::smem_u32(smem)), n0 + c * 32, m0 + q * 32);
+                }
+            }
+        };
         for (int w = unit; w < total; w += n_units) {
             const int split = w / tiles, t = w - split * tiles;
             const int m0 = (t / p.n_tiles_n) * TILE_M + (int)cta_rank * BM, n0 = (t % p.n_tiles_n) * BN;
             long long e_a = GCLK(), dbg_ld = 0, dbg_math = 0, dbg_st = 0;
+            issue_side(m0, n0, half);            // in flight while the accumulator is still being computed
             // the bias of this warp's first chunk is fetched BEFORE the wait for the accumulator (an L2 round trip of ~400
             // cycles otherwise sits in front of every chunk's arithmetic); later chunks fetch theirs behind the TMEM load
             uint4 bq[4];
@@ -428,6 +451,9 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             long long drow = row;
             float rsc = 1.f;
             bool row_ok = row_in;
+            if (EPI == TE_RESIDUAL_ID && row_in) {
+                if (p.rowscale) rsc = __ldg(p.rowscale + row / p.rows_per_batch);
+            }
             if (EPI == TE_RESIDUAL && row_in) {
                 const int b = row / p.rows_per_batch;
                 const int r = row - b * p.rows_per_batch;
@@ -452,9 +478,18 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 // Side tensor of the epilogue (residual / GELU' / pre-activation), same (row, column) footprint as the output:
                 // loaded COALESCED (4 lanes per 64-byte row segment, rows via the owning lanes' registers) into the warp's
                 // staging buffer while the TMEM load is in flight, then re-read in the thread-per-row layout.
-                constexpr bool HAS_SIDE = (EPI == TE_RESIDUAL || EPI == TE_DGRAD_MUL || EPI == TE_DGRAD_GELU);
+                constexpr bool HAS_SIDE = (EPI == TE_RESIDUAL || EPI == TE_RESIDUAL_ID || EPI == TE_DGRAD_MUL || EPI == TE_DGRAD_GELU);
                 uint4 side[HAS_SIDE ? 4 : 1];
-                if constexpr (HAS_SIDE) {
+                if constexpr (SIDE2) {
+                    tc::mbar_wait(sbar, side_phase);
+                    side_phase ^= 1;
+                    const uint32_t rowa = sstg_w + lane * 64;    // the TMA unit's 64-byte swizzle is keyed by the absolute address
+#pragma unroll
+                    for (int g = 0; g < 4; ++g) side[g] = tc::lds_u4(rowa + ((g ^ ((rowa >> 7) & 3)) << 4));
+                    tc::fence_proxy_async();                     // our reads of the buffer come before the next tile load into it
+                    __syncwarp();
+                    if (c + EPI_WARPS / 4 < BN / 32) issue_side(m0, n0, c + EPI_WARPS / 4);
+                } else if constexpr (HAS_SIDE) {
                     const __nv_bfloat16* sp = (EPI == TE_RESIDUAL) ? p.res : p.gelu_pre;
                     const int unit = lane & 3;
                     const int colu = col0 + unit * 8;
@@ -526,7 +561,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                             if constexpr (EPI == TE_DGRAD_MUL) {
 #pragma unroll
                                 for (int e = 0; e < 8; ++e) v[e] *= u[e];
-                            } else if constexpr (EPI == TE_RESIDUAL) {
+                            } else if constexpr (EPI == TE_RESIDUAL || EPI == TE_RESIDUAL_ID) {
 #pragma unroll
                                 for (int e = 0; e < 8; ++e) v[e] = fmaf(rsc, v[e], u[e]);
                             } else {
@@ -652,8 +687,10 @@ long long* gemm_dbg_buffer(int bn, bool amn, bool bmn, const TcParams& p) {
 template <int BN, bool A_MN, bool B_MN, int EPI, bool COLSUM = false, bool PAIR = false, bool F16 = false>
 int launch_tc_epi(const CUtensorMap& tmA, const CUtensorMap& tmB, const TcParams& p, cudaStream_t st, const CUtensorMap* outs) {
     constexpr int STAGE = A_BYTES + (PAIR ? BN / 2 : BN) * BK * 2;
-    constexpr int STAGES = PAIR ? 6 : (BN <= 128 ? 5 : 4);
-    constexpr size_t SMEM = (size_t)STAGES * STAGE + 1024 + 256 + NUM_EPI_WARPS * 32 * 64;
+    constexpr bool SIDE2 = (EPI == TE_DGRAD_MUL || EPI == TE_DGRAD_GELU || EPI == TE_RESIDUAL_ID);   // second per-warp staging buffer (+ 16 barriers) instead of one TMA stage
+    constexpr int STAGES = (PAIR ? 6 : (BN <= 128 ? 5 : 4)) - (SIDE2 ? 1 : 0);
+    constexpr size_t SMEM = (size_t)STAGES * STAGE + 1024 + 256 + (SIDE2 ? 2 : 1) * NUM_EPI_WARPS * 32 * 64 + (SIDE2 ? 128 : 0);
+    static_assert(SMEM <= 227 * 1024, "GEMM shared-memory layout exceeds 227 KB");
     auto kern = tc_gemm_kernel<BN, A_MN, B_MN, STAGES, EPI, COLSUM, PAIR, F16>;
     const int dev = current_device();
     static bool configured[kMaxDevices] = {};  // per device (function attributes are); benign race: the attribute is idempotent
@@ -709,6 +746,7 @@ int launch_tc_t(const CUtensorMap& tmA, const CUtensorMap& tmB, const TcParams& 
             case TE_GELU: return launch_tc_epi<BN, false, false, TE_GELU, false, PAIR, F16>(tmA, tmB, p, st, outs);
             case TE_GELU_GRAD: return launch_tc_epi<BN, false, false, TE_GELU_GRAD, false, PAIR, F16>(tmA, tmB, p, st, outs);
             case TE_RESIDUAL: return launch_tc_epi<BN, false, false, TE_RESIDUAL, false, PAIR, F16>(tmA, tmB, p, st, outs);
+            case TE_RESIDUAL_ID: return launch_tc_epi<BN, false, false, TE_RESIDUAL_ID, false, PAIR, F16>(tmA, tmB, p, st, outs);
             default: return launch_tc_epi<BN, false, false, TE_BIAS, false, PAIR, F16>(tmA, tmB, p, st, outs);
         }
     }
@@ -774,8 +812,10 @@ int tc_linear(const TcLinearArgs& a, cudaStream_t st) {
     p.res = (const __nv_bfloat16*)a.res; p.rowmap = a.rowmap; p.rowscale = a.rowscale;
     p.rows_per_batch = a.rows_per_batch; p.dst_rows_per_batch = a.dst_rows_per_batch; p.ldc = a.N;
     const bool f16 = a.dtype == VSW_F16;
+    // residual epilogue without a row map (fc2 + residual, video_swin.py:261): output rows = tile rows
+    if (p.epi == TE_RESIDUAL && !a.rowmap && a.rows_per_batch == a.dst_rows_per_batch) p.epi = TE_RESIDUAL_ID;
     CUtensorMap outs[2];
-    if (!make_out_maps(outs, a.y, a.aux_out, a.M, a.N, a.N)) return VSW_ERR_CUDA;
+    if (!make_out_maps(outs, a.y, p.epi == TE_RESIDUAL_ID ? a.res : a.aux_out, a.M, a.N, a.N)) return VSW_ERR_CUDA;
     if (pair) return launch_tc<256, false, false, true>(tmA, tmB, p, f16, st, outs);
     return BN == 256 ? launch_tc<256, false, false>(tmA, tmB, p, f16, st, outs) : launch_tc<128, false, false>(tmA, tmB, p, f16, st, outs);
 }
@@ -814,7 +854,7 @@ int tc_dgrad(const TcDgradArgs& a, cudaStream_t st) {
     p.epi = (a.gelu_pre && a.pre_is_grad) ? TE_DGRAD_MUL : TE_DGRAD;
     p.out = (__nv_bfloat16*)a.dx; p.gelu_pre = (const __nv_bfloat16*)a.gelu_pre; p.ldc = a.K;
     CUtensorMap outs[2];
-    if (!make_out_maps(outs, a.dx, nullptr, a.M, a.K, a.K)) return VSW_ERR_CUDA;
+    if (!make_out_maps(outs, a.dx, a.gelu_pre, a.M, a.K, a.K)) return VSW_ERR_CUDA;   // second map: the side tensor (GELU' or pre-activation), same shape as dx
     if (pair) return launch_tc<256, false, true, true>(tmA, tmB, p, f16, st, outs);
     return BN == 256 ? launch_tc<256, false, true>(tmA, tmB, p, f16, st, outs) : launch_tc<128, false, true>(tmA, tmB, p, f16, st, outs);
 }
