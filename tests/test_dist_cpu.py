@@ -215,3 +215,34 @@ def test_two_rank_gradient_allreduce_matches_single_process(tmp_path):
         port = s.getsockname()[1]
     mp.spawn(_worker, args=(2, port, str(tmp_path)), nprocs=2, join=True)
     assert os.path.exists(tmp_path / "ok0") and os.path.exists(tmp_path / "ok1")
+
+
+def test_flat_grad_reducer_layout_and_single_process():
+    """no process group: slots are aligned, chunks tile every flat buffer exactly, mixed dtypes get one buffer each, gradients
+    that arrive the ordinary way are copied into their slots and equal plain autograd's"""
+    dp = importlib.import_module("pytorch_empirical-mvm_b200.dp")
+    torch.manual_seed(0)
+    net = torch.nn.Sequential(torch.nn.Linear(5, 7), torch.nn.Tanh(), torch.nn.Linear(7, 3).double(), torch.nn.Linear(3, 1).double())
+    ref = [p.detach().clone().requires_grad_(True) for p in net.parameters()]
+    red = dp.FlatGradReducer(net, n_chunks=8, install_sink=False)     # more chunks than parameters per dtype: clamped
+    assert set(red.flat) == {torch.float32, torch.float64}
+    for dt, flat in red.flat.items():
+        ch = sorted((a, b) for d, a, b in red.chunks if d == dt)
+        assert ch[0][0] == 0 and ch[-1][1] == flat.numel() and all(x[1] == y[0] for x, y in zip(ch, ch[1:]))
+    for p in red.params:
+        _, off, n = red.slot[id(p)]
+        assert off % dp.FlatGradReducer.ALIGN == 0 and n == p.numel()
+    x = torch.randn(4, 5)
+
+    def loss(ps):
+        h = torch.tanh(x @ ps[0].t() + ps[1]).double()
+        return ((h @ ps[2].t() + ps[3]) @ ps[4].t() + ps[5]).pow(2).sum()
+    for _ in range(2):
+        red.zero_grad()
+        loss(list(net.parameters())).backward()
+        assert red.finish() == 0
+    loss(ref).backward()
+    for p, q in zip(net.parameters(), ref):
+        assert torch.allclose(p.grad, q.grad, rtol=1e-12, atol=0)
+        assert p.grad.untyped_storage().data_ptr() == red.flat[p.dtype].untyped_storage().data_ptr()
+    red.remove()
