@@ -73,7 +73,15 @@ def all_reduce_gradients_coalesced(params: Iterable[torch.Tensor]) -> int:
             dist.all_reduce(g, op=dist.ReduceOp.SUM)
             g.div_(dist.get_world_size())
         return len(grads)
-    with dist._coalescing_manager(device=grads[0].device, async_ops=True) as cm:
+    # (torch.distributed._coalescing_manager is a private API -- present in torch 2.1 ... 2.11; without it the same reductions
+    # are issued one by one.  dp.FlatGradReducer, the default exchange, uses public APIs only.)
+    cmgr = getattr(dist, "_coalescing_manager", None)
+    if cmgr is None:
+        works = [dist.all_reduce(g, op=dist.ReduceOp.AVG, async_op=True) for g in grads]
+        for w in works:
+            w.wait()
+        return len(grads)
+    with cmgr(device=grads[0].device, async_ops=True) as cm:
         for g in grads:
             dist.all_reduce(g, op=dist.ReduceOp.AVG)
     cm.wait()
@@ -81,7 +89,9 @@ def all_reduce_gradients_coalesced(params: Iterable[torch.Tensor]) -> int:
 
 
 class OverlappedGradReducer:
-    """The exchange step overlapped with backward, still copy-free: parameters are grouped (one group per direct child of
+    """(Earlier form, kept for A/B against FlatGradReducer; it builds each collective's tensor list from the gradients present
+    on the local rank, so every rank must produce gradients for the same parameters.)
+    The exchange step overlapped with backward, still copy-free: parameters are grouped (one group per direct child of
     every ``nn.ModuleList`` / top-level sub-module, i.e. one per Swin block), and as soon as autograd has accumulated the
     gradient of the last parameter of a group the group's ``.grad`` tensors are averaged in place by ONE coalesced, asynchronous
     NCCL call.  ``finish()`` (after ``loss.backward()``) reduces whatever is left and waits for all outstanding calls."""
